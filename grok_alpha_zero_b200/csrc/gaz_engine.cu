@@ -1,0 +1,686 @@
+// gaz_engine.cu -- engine object, kernels and the C ABI (include/gaz_b200.h).
+//
+// Build (product):  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false ... -> libgaz_b200.so
+// Build (tests)  :  g++ -x c++ -DGAZ_EMUL ...  -> tests/_emul/libgaz_emul.so  (host emulation of the
+//                   warp code for the CPU test-suite; never loaded by the package).
+#include "../../include/gaz_b200.h"
+#include "gaz_core.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+#ifndef GAZ_EMUL
+#include <cuda_runtime.h>
+#endif
+
+using namespace gaz;
+
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+// ---------------------------------------------------------------- memory ----
+#ifdef GAZ_EMUL
+typedef int gaz_stream_t;
+static int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : -1; }
+static void dev_free(void *p) { free(p); }
+static int h2d(void *d, const void *h, size_t n, gaz_stream_t) { memcpy(d, h, n); return 0; }
+static int d2h(void *h, const void *d, size_t n, gaz_stream_t) { memcpy(h, d, n); return 0; }
+static int dev_zero(void *d, size_t n, gaz_stream_t) { memset(d, 0, n); return 0; }
+static int stream_sync(gaz_stream_t) { return 0; }
+#else
+typedef cudaStream_t gaz_stream_t;
+#define CK(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) return fail("%s: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+static int dev_alloc(void **p, size_t n) {
+    CK(cudaMalloc(p, n ? n : 1));
+    CK(cudaMemset(*p, 0, n ? n : 1));
+    return 0;
+}
+static void dev_free(void *p) { if (p) cudaFree(p); }
+static int h2d(void *d, const void *h, size_t n, gaz_stream_t s) {
+    CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+static int d2h(void *h, const void *d, size_t n, gaz_stream_t s) {
+    CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+static int dev_zero(void *d, size_t n, gaz_stream_t s) { CK(cudaMemsetAsync(d, 0, n, s)); return 0; }
+static int stream_sync(gaz_stream_t s) { CK(cudaStreamSynchronize(s)); return 0; }
+#endif
+
+struct gaz_engine {
+    gaz_config cfg;
+    View v;
+    gaz_stream_t stream;
+    int64_t bytes;
+    std::vector<void *> allocs;
+    int32_t *d_limits;   // [n_trees]
+    int16_t *d_actions;  // [n_trees]
+    uint8_t *d_mask;     // [n_trees]
+    int32_t *d_counter;  // scratch counter
+    int32_t *d_winners;  // [n_games]
+    double *d_noise;
+    double *d_lut;
+    float *d_pi;         // [MAXL]
+};
+
+template <class T> static int ealloc(gaz_engine *e, T **p, size_t count) {
+    void *q = nullptr;
+    if (dev_alloc(&q, count * sizeof(T)) != 0) return -1;
+    e->allocs.push_back(q);
+    e->bytes += (int64_t)(count * sizeof(T));
+    *p = (T *)q;
+    return 0;
+}
+
+// --------------------------------------------------------------- kernels ----
+static constexpr int WARPS = 4;
+static constexpr int THREADS = WARPS * 32;
+
+// hash evaluator: one warp per leaf (oracle/hash_eval.py, oracle/mcts_oracle.c:orc_hash_eval)
+GAZ_HD uint64_t mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ULL;
+    z ^= z >> 27; z *= 0x94d049bb133111ebULL;
+    z ^= z >> 31;
+    return z;
+}
+#define GAZ_GOLD 0x9E3779B97F4A7C15ULL
+
+template <class CG> GAZ_HD void hash_eval_leaf(const CG &cg, const View &v, int leaf, uint64_t salt, int logits) {
+    const int n = v.ncell * v.C;
+    const int8_t *st = v.leaf_state + (size_t)leaf * n;
+    uint64_t acc = 0;
+    for (int i = cg.lane; i < n; i += cg.width())
+        acc += (uint64_t)(int64_t)(st[i] + 2) * mix64((uint64_t)(i + 1) * GAZ_GOLD);
+    acc = cg.sum64(acc);
+    uint64_t h0 = mix64(acc + salt * 0xD1B54A32D192ED03ULL);
+    float *pol = v.policy + (size_t)leaf * v.P;
+    for (int i = cg.lane; i < v.P; i += cg.width()) {
+        uint64_t r = mix64(h0 + (uint64_t)(i + 1) * GAZ_GOLD);
+        uint32_t k = (uint32_t)(((r >> 52) << 8) | (uint64_t)i) + 1u;
+        pol[i] = logits ? (float)k * 0x1p-17f - 4.0f : (float)k;
+    }
+    if (cg.lane == 0) {
+        uint64_t rv = mix64(h0 + 0x5851F42D4C957F2DULL);
+        v.value[leaf] = (float)(rv >> 40) * 0x1p-23f - 1.0f;
+    }
+}
+
+// Start of run(): budget rules MCTS.py:542-546 / MCTS_Gumbel.py:570-599
+template <class CG> GAZ_HD void run_begin_tree(const CG &cg, const View &v, int tree, int limit) {
+    TreeState &ts = v.trees[tree];
+    const GameState &g = v.games[tree / v.trees_per_game];
+    int nids = n_action_ids(v);
+    int n_legal = 0;
+    for (int a = cg.lane; a < nids; a += cg.width()) n_legal += action_legal(v, g.board, a) ? 1 : 0;
+    n_legal = cg.sum(n_legal);
+    cg.sync();
+    if (cg.lane != 0) return;
+    ts.iter = 0;
+    if (limit <= 0 || ts.root < 0) { ts.limit = 0; ts.g_state = GS_IDLE; return; }
+    if (!v.gumbel) {
+        if (n_legal == 1) limit = 1;
+        else if (limit < n_legal) limit = n_legal * 3;
+        ts.limit = limit;
+    } else {
+        if (ts.g_m > n_legal) ts.g_m = n_legal; // permanent (MCTS_Gumbel.py:581-582)
+        ts.g_n = limit;
+        ts.g_phase = 0;
+        ts.g_curiter = 0;
+        ts.g_ntop = nr_L(*node_ptr(v, tree, ts.root));
+        ts.g_cur = 0;
+        ts.g_done_in_child = -1;
+        if (n_legal > 1) { ts.g_state = GS_HALVE; ts.limit = 1; ts.g_best_slot = -1; }
+        else { ts.g_state = GS_DONE; ts.limit = 0; ts.g_best_slot = 0; }
+    }
+}
+
+// game.do_action + check_win (Self_Play.py:142-144)
+GAZ_HD void apply_action_game(const View &v, int gi, int action, int32_t *winners) {
+    GameState &g = v.games[gi];
+    if (action >= 0 && g.winner == -2) {
+        int r = reply_result(v, g.board, action, g.next_player);
+        board_play(v, g.board, action, g.next_player);
+        if (r == TERM_WIN) g.winner = g.next_player;
+        else if (r == TERM_DRAW) g.winner = 0;
+        g.last3 = push_last3(g.last3, action);
+        g.hist_len++;
+        g.last_action = action;
+        g.next_player = -g.next_player;
+    }
+    if (winners) winners[gi] = g.winner;
+}
+
+#ifndef GAZ_EMUL
+#define WARP_PROLOGUE(count)                                          \
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    \
+    if (widx >= (count)) return;                                      \
+    __shared__ Scratch s_sc[WARPS];                                   \
+    Scratch &sc = s_sc[threadIdx.x >> 5];                             \
+    Coop cg;
+
+__global__ void __launch_bounds__(THREADS) k_select(View v) {
+    WARP_PROLOGUE(v.n_trees)
+    if (v.gumbel) gumbel_step(cg, v, widx, sc);
+    else puct_select_step(cg, v, widx, sc);
+}
+__global__ void __launch_bounds__(THREADS) k_expand(View v) {
+    WARP_PROLOGUE(*v.leaf_count)
+    expand_finish(cg, v, widx, sc);
+}
+__global__ void __launch_bounds__(THREADS) k_hash_eval(View v, uint64_t salt, int logits) {
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= *v.leaf_count) return;
+    Coop cg;
+    hash_eval_leaf(cg, v, widx, salt, logits);
+}
+__global__ void __launch_bounds__(THREADS) k_new_roots(View v, const uint8_t *mask) {
+    WARP_PROLOGUE(v.n_trees)
+    if (mask && !mask[widx]) return;
+    root_begin(cg, v, widx, sc);
+}
+__global__ void __launch_bounds__(THREADS) k_run_begin(View v, const int32_t *limits) {
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= v.n_trees) return;
+    Coop cg;
+    run_begin_tree(cg, v, widx, limits[widx]);
+}
+__global__ void __launch_bounds__(THREADS) k_prune(View v, const int16_t *actions, int create_new_root) {
+    WARP_PROLOGUE(v.n_trees)
+    if (actions[widx] < 0) return;
+    prune_step(cg, v, widx, actions[widx], create_new_root, sc);
+}
+__global__ void k_apply(View v, const int16_t *actions, int32_t *winners) {
+    int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= v.n_games) return;
+    apply_action_game(v, gi, actions[gi], winners);
+}
+__global__ void k_remaining(View v, int32_t *counter) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool run = false;
+    if (t < v.n_trees) {
+        const TreeState &ts = v.trees[t];
+        run = v.gumbel ? (ts.limit > 0 && ts.g_state != GS_DONE && ts.g_state != GS_IDLE)
+                       : (ts.limit > 0 && ts.iter < ts.limit);
+        run = run || ts.pending;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, run);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, __popc(m));
+}
+__global__ void k_reset_counter(int32_t *c) { *c = 0; }
+__global__ void __launch_bounds__(32) k_gumbel_pi(View v, int tree, float *out) {
+    __shared__ Scratch sc;
+    Coop cg;
+    gumbel_final_pi(cg, v, tree, sc, out);
+}
+static inline int grid_warps(int n) { return (n + WARPS - 1) / WARPS; }
+#endif
+
+// ------------------------------------------------------------- launchers ----
+static int launch_select(gaz_engine *e) {
+#ifdef GAZ_EMUL
+    *e->v.leaf_count = 0;
+    for (int t = 0; t < e->v.n_trees; t++) {
+        Coop cg; Scratch sc;
+        if (e->v.gumbel) gumbel_step(cg, e->v, t, sc);
+        else puct_select_step(cg, e->v, t, sc);
+    }
+#else
+    k_reset_counter<<<1, 1, 0, e->stream>>>(e->v.leaf_count);
+    k_select<<<grid_warps(e->v.n_trees), THREADS, 0, e->stream>>>(e->v);
+    CK(cudaGetLastError());
+#endif
+    return 0;
+}
+static int launch_expand(gaz_engine *e) {
+#ifdef GAZ_EMUL
+    for (int l = 0; l < *e->v.leaf_count; l++) { Coop cg; Scratch sc; expand_finish(cg, e->v, l, sc); }
+    *e->v.leaf_count = 0;
+#else
+    k_expand<<<grid_warps(e->v.n_trees), THREADS, 0, e->stream>>>(e->v);
+    CK(cudaGetLastError());
+#endif
+    return 0;
+}
+static int launch_hash(gaz_engine *e, uint64_t salt, int logits) {
+#ifdef GAZ_EMUL
+    for (int l = 0; l < *e->v.leaf_count; l++) { Coop cg; hash_eval_leaf(cg, e->v, l, salt, logits); }
+#else
+    k_hash_eval<<<grid_warps(e->v.n_trees), THREADS, 0, e->stream>>>(e->v, salt, logits);
+    CK(cudaGetLastError());
+#endif
+    return 0;
+}
+static int read_leaf_count(gaz_engine *e) {
+    int32_t n = 0;
+    if (d2h(&n, e->v.leaf_count, sizeof n, e->stream) != 0) return -1;
+    return n;
+}
+
+// ------------------------------------------------------------------ ABI -----
+extern "C" {
+
+const char *gaz_last_error(void) { return g_err.c_str(); }
+int gaz_abi_version(void) { return 1; }
+
+int gaz_create(const gaz_config *cfg, gaz_engine **out) {
+    if (!cfg || !out) return fail("null argument");
+    if (cfg->game < 0 || cfg->game > 2) return fail("bad game %d", cfg->game);
+    if (cfg->n_games <= 0 || cfg->trees_per_game <= 0 || cfg->trees_per_game > 2) return fail("bad n_games/trees_per_game");
+    if (cfg->node_cap < 8 || cfg->slot_cap < 256) return fail("node_cap/slot_cap too small");
+#ifndef GAZ_EMUL
+    {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev <= 0)
+            return fail("no CUDA device (%s): libgaz_b200 has no CPU path", cudaGetErrorString(ce));
+        CK(cudaSetDevice(cfg->device));
+    }
+#endif
+    gaz_engine *e = new gaz_engine();
+    e->cfg = *cfg;
+    e->bytes = 0;
+    View &v = e->v;
+    memset(&v, 0, sizeof v);
+    v.game = cfg->game;
+    if (cfg->game == GAME_TTT) { v.H = 3; v.W = 3; v.C = 2; v.P = 9; v.NW = 2; }
+    else if (cfg->game == GAME_C4) { v.H = 6; v.W = 7; v.C = 4; v.P = 7; v.NW = 4; }
+    else { v.H = 15; v.W = 15; v.C = 2; v.P = 225; v.NW = 16; }
+    v.ncell = v.H * v.W;
+    v.n_games = cfg->n_games;
+    v.trees_per_game = cfg->trees_per_game;
+    v.n_trees = cfg->n_games * cfg->trees_per_game;
+    v.node_cap = cfg->node_cap;
+    v.slot_cap = cfg->slot_cap;
+    v.gumbel = cfg->mode == GAZ_MODE_GUMBEL;
+    v.c_init = cfg->c_puct_init;
+    v.c_base = cfg->c_puct_base;
+    v.c_visit = (float)cfg->c_visit;
+    v.c_scale = (float)cfg->c_scale;
+    v.c_visit_d = cfg->c_visit;
+    v.c_scale_d = cfg->c_scale;
+    v.use_softmax = cfg->use_softmax;
+    v.gm_cap = MAXL;
+    v.lut_n = cfg->lut_n > 0 ? cfg->lut_n : (1 << 20);
+#ifndef GAZ_EMUL
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+#else
+    e->stream = 0;
+#endif
+    const size_t NT = (size_t)v.n_trees;
+    int rc = 0;
+    rc |= ealloc(e, &v.nodes, NT * v.node_cap);
+    rc |= ealloc(e, &v.boards, NT * v.node_cap * v.NW);
+    rc |= ealloc(e, &v.slot_val, NT * v.slot_cap);
+    rc |= ealloc(e, &v.slot_act, NT * v.slot_cap);
+    if (v.gumbel) rc |= ealloc(e, &v.slot_child, NT * v.slot_cap);
+    rc |= ealloc(e, &v.trees, NT);
+    rc |= ealloc(e, &v.games, (size_t)v.n_games);
+    rc |= ealloc(e, &v.remap, NT * v.node_cap);
+    rc |= ealloc(e, &v.leaf_count, 4);
+    rc |= ealloc(e, &v.leaves, NT);
+    rc |= ealloc(e, &v.leaf_state, NT * v.ncell * v.C);
+    rc |= ealloc(e, &v.policy, NT * v.P);
+    rc |= ealloc(e, &v.value, NT);
+    rc |= ealloc(e, &v.status, 4);
+    if (v.gumbel) {
+        rc |= ealloc(e, &v.gm_ids, NT * v.gm_cap);
+        rc |= ealloc(e, &v.gm_g, NT * v.gm_cap);
+    }
+    rc |= ealloc(e, &e->d_limits, NT);
+    rc |= ealloc(e, &e->d_actions, NT);
+    rc |= ealloc(e, &e->d_mask, NT);
+    rc |= ealloc(e, &e->d_counter, 4);
+    rc |= ealloc(e, &e->d_winners, (size_t)v.n_games);
+    rc |= ealloc(e, &e->d_lut, (size_t)v.lut_n);
+    rc |= ealloc(e, &e->d_pi, MAXL);
+    e->d_noise = nullptr;
+    if (rc != 0) { gaz_destroy(e); return g_err.empty() ? fail("allocation failed") : -1; }
+    v.c_lut = e->d_lut;
+    *out = e;
+    if (gaz_set_puct_params(e, cfg->c_puct_init, cfg->c_puct_base) < 0) { gaz_destroy(e); *out = nullptr; return -1; }
+    if (gaz_set_gumbel_params(e, cfg->gumbel_m, cfg->c_visit, cfg->c_scale, cfg->use_softmax) < 0) { gaz_destroy(e); *out = nullptr; return -1; }
+    if (gaz_reset_games(e) < 0) { gaz_destroy(e); *out = nullptr; return -1; }
+    return 0;
+}
+
+void gaz_destroy(gaz_engine *e) {
+    if (!e) return;
+#ifndef GAZ_EMUL
+    cudaStreamSynchronize(e->stream);
+#endif
+    for (void *p : e->allocs) dev_free(p);
+#ifndef GAZ_EMUL
+    cudaStreamDestroy(e->stream);
+#endif
+    delete e;
+}
+
+int gaz_set_puct_params(gaz_engine *e, float c_init, float c_base) {
+    if (!e) return fail("null engine");
+    e->v.c_init = c_init;
+    e->v.c_base = c_base;
+    // C(N) = c_init + ln((N + c_base + 1) / c_base) with the host libm (glibc) so it equals the
+    // oracle's / numba's values
+    std::vector<double> lut((size_t)e->v.lut_n);
+    for (int N = 0; N < e->v.lut_n; N++)
+        lut[(size_t)N] = (double)c_init + log(((double)N + (double)c_base + 1.0) / (double)c_base);
+    if (h2d(e->d_lut, lut.data(), lut.size() * sizeof(double), e->stream) != 0) return -1;
+    return stream_sync(e->stream);
+}
+
+int gaz_set_gumbel_params(gaz_engine *e, int m, double c_visit, double c_scale, int use_softmax) {
+    if (!e) return fail("null engine");
+    View &v = e->v;
+    v.c_visit = (float)c_visit; v.c_scale = (float)c_scale;
+    v.c_visit_d = c_visit; v.c_scale_d = c_scale;
+    v.use_softmax = use_softmax;
+    e->cfg.gumbel_m = m;
+    std::vector<TreeState> ts((size_t)v.n_trees);
+    if (d2h(ts.data(), v.trees, ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
+    for (auto &t : ts) t.g_m = m;
+    if (h2d(v.trees, ts.data(), ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
+    return stream_sync(e->stream);
+}
+
+static void cells_to_board(const View &v, const int8_t *cells, uint32_t *b) {
+    for (int w = 0; w < MAXNW; w++) b[w] = 0;
+    for (int c = 0; c < v.ncell; c++) {
+        if (cells[c] == 0) continue;
+        int p = cells[c] > 0 ? 1 : 0;
+        if (v.game == GAME_GOMOKU) {
+            int y = c / 15, x = c % 15;
+            b[p * 8 + (y >> 1)] |= 1u << (x + (y & 1) * 16);
+        } else if (v.game == GAME_C4) {
+            int y = c / 7, x = c % 7;
+            int bit = x * 7 + (5 - y);
+            b[p * 2 + (bit >> 5)] |= 1u << (bit & 31);
+        } else {
+            b[p] |= 1u << c;
+        }
+    }
+}
+
+int gaz_set_game(gaz_engine *e, int game, const int8_t *board, int next_player, const int16_t *hist_tail, int hist_len) {
+    if (!e || !board) return fail("null argument");
+    if (game < 0 || game >= e->v.n_games) return fail("game index %d out of range", game);
+    GameState g;
+    memset(&g, 0, sizeof g);
+    cells_to_board(e->v, board, g.board);
+    g.next_player = next_player;
+    g.hist_len = hist_len;
+    g.last3 = 0;
+    int cnt = hist_len < 3 ? hist_len : 3;
+    for (int i = cnt - 1; i >= 0; i--) g.last3 = push_last3(g.last3, hist_tail[i]);
+    g.winner = -2;
+    g.last_action = cnt > 0 ? hist_tail[0] : -1;
+    if (h2d(e->v.games + game, &g, sizeof g, e->stream) != 0) return -1;
+    return stream_sync(e->stream);
+}
+
+int gaz_reset_games(gaz_engine *e) {
+    if (!e) return fail("null engine");
+    std::vector<GameState> gs((size_t)e->v.n_games);
+    memset(gs.data(), 0, gs.size() * sizeof(GameState));
+    for (auto &g : gs) { g.next_player = -1; g.winner = -2; g.last_action = -1; }
+    if (h2d(e->v.games, gs.data(), gs.size() * sizeof(GameState), e->stream) != 0) return -1;
+    std::vector<TreeState> ts((size_t)e->v.n_trees);
+    memset(ts.data(), 0, ts.size() * sizeof(TreeState));
+    for (auto &t : ts) { t.root = -1; t.g_m = e->cfg.gumbel_m; }
+    if (h2d(e->v.trees, ts.data(), ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
+    if (dev_zero(e->v.leaf_count, sizeof(int32_t), e->stream) != 0) return -1;
+    return stream_sync(e->stream);
+}
+
+int gaz_apply_actions(gaz_engine *e, const int16_t *actions, int32_t *winners_out) {
+    if (!e || !actions) return fail("null argument");
+    const View &v = e->v;
+    if (h2d(e->d_actions, actions, (size_t)v.n_games * sizeof(int16_t), e->stream) != 0) return -1;
+#ifdef GAZ_EMUL
+    for (int g = 0; g < v.n_games; g++) apply_action_game(v, g, e->d_actions[g], e->d_winners);
+#else
+    k_apply<<<(v.n_games + 127) / 128, 128, 0, e->stream>>>(v, e->d_actions, e->d_winners);
+    CK(cudaGetLastError());
+#endif
+    if (winners_out) return d2h(winners_out, e->d_winners, (size_t)v.n_games * sizeof(int32_t), e->stream);
+    return stream_sync(e->stream);
+}
+
+int gaz_get_game(gaz_engine *e, int game, int8_t *board_out, int32_t *info_out) {
+    if (!e) return fail("null engine");
+    if (game < 0 || game >= e->v.n_games) return fail("game index %d out of range", game);
+    GameState g;
+    if (d2h(&g, e->v.games + game, sizeof g, e->stream) != 0) return -1;
+    if (board_out)
+        for (int c = 0; c < e->v.ncell; c++) board_out[c] = (int8_t)cell_value(e->v, g.board, c);
+    if (info_out) { info_out[0] = g.next_player; info_out[1] = g.hist_len; info_out[2] = g.winner; }
+    return 0;
+}
+
+int gaz_new_roots(gaz_engine *e, const uint8_t *tree_mask) {
+    if (!e) return fail("null engine");
+    const View &v = e->v;
+    const uint8_t *dm = nullptr;
+    if (tree_mask) {
+        if (h2d(e->d_mask, tree_mask, (size_t)v.n_trees, e->stream) != 0) return -1;
+        dm = e->d_mask;
+    }
+#ifdef GAZ_EMUL
+    *v.leaf_count = 0;
+    for (int t = 0; t < v.n_trees; t++) {
+        if (dm && !dm[t]) continue;
+        Coop cg; Scratch sc;
+        root_begin(cg, v, t, sc);
+    }
+#else
+    k_reset_counter<<<1, 1, 0, e->stream>>>(v.leaf_count);
+    k_new_roots<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, dm);
+    CK(cudaGetLastError());
+#endif
+    return read_leaf_count(e);
+}
+
+int gaz_run_begin(gaz_engine *e, const int32_t *limits) {
+    if (!e || !limits) return fail("null argument");
+    const View &v = e->v;
+    if (h2d(e->d_limits, limits, (size_t)v.n_trees * sizeof(int32_t), e->stream) != 0) return -1;
+#ifdef GAZ_EMUL
+    for (int t = 0; t < v.n_trees; t++) { Coop cg; run_begin_tree(cg, v, t, e->d_limits[t]); }
+#else
+    k_run_begin<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, e->d_limits);
+    CK(cudaGetLastError());
+#endif
+    return stream_sync(e->stream);
+}
+
+int gaz_select(gaz_engine *e) {
+    if (!e) return fail("null engine");
+    if (launch_select(e) != 0) return -1;
+    return read_leaf_count(e);
+}
+
+int gaz_get_leaves(gaz_engine *e, int8_t *states_out, int32_t *trees_out) {
+    if (!e) return fail("null engine");
+    const View &v = e->v;
+    int n = read_leaf_count(e);
+    if (n <= 0) return n;
+    if (states_out && d2h(states_out, v.leaf_state, (size_t)n * v.ncell * v.C, e->stream) != 0) return -1;
+    if (trees_out) {
+        std::vector<LeafRec> lr((size_t)n);
+        if (d2h(lr.data(), v.leaves, lr.size() * sizeof(LeafRec), e->stream) != 0) return -1;
+        for (int i = 0; i < n; i++) trees_out[i] = lr[(size_t)i].tree;
+    }
+    return n;
+}
+
+int gaz_put_evals(gaz_engine *e, const float *policy, const float *value, int n) {
+    if (!e || !policy || !value) return fail("null argument");
+    const View &v = e->v;
+    if (n < 0 || n > v.n_trees) return fail("bad eval count %d", n);
+    if (n == 0) return 0;
+    if (h2d(v.policy, policy, (size_t)n * v.P * sizeof(float), e->stream) != 0) return -1;
+    if (h2d(v.value, value, (size_t)n * sizeof(float), e->stream) != 0) return -1;
+    return stream_sync(e->stream);
+}
+
+int gaz_eval_hash(gaz_engine *e, uint64_t salt, int logits) {
+    if (!e) return fail("null engine");
+    return launch_hash(e, salt, logits);
+}
+
+int gaz_expand(gaz_engine *e) {
+    if (!e) return fail("null engine");
+    if (launch_expand(e) != 0) return -1;
+    return stream_sync(e->stream);
+}
+
+int gaz_remaining(gaz_engine *e) {
+    if (!e) return fail("null engine");
+    const View &v = e->v;
+#ifdef GAZ_EMUL
+    int c = 0;
+    for (int t = 0; t < v.n_trees; t++) {
+        const TreeState &ts = v.trees[t];
+        bool run = v.gumbel ? (ts.limit > 0 && ts.g_state != GS_DONE && ts.g_state != GS_IDLE)
+                            : (ts.limit > 0 && ts.iter < ts.limit);
+        c += (run || ts.pending) ? 1 : 0;
+    }
+    return c;
+#else
+    k_reset_counter<<<1, 1, 0, e->stream>>>(e->d_counter);
+    k_remaining<<<(v.n_trees + 127) / 128, 128, 0, e->stream>>>(v, e->d_counter);
+    CK(cudaGetLastError());
+    int32_t c = 0;
+    if (d2h(&c, e->d_counter, sizeof c, e->stream) != 0) return -1;
+    return c;
+#endif
+}
+
+int gaz_rounds_hash(gaz_engine *e, int n_rounds, uint64_t salt, int logits) {
+    if (!e) return fail("null engine");
+    for (int r = 0; r < n_rounds; r++) {
+        if (launch_select(e) != 0) return -1;
+        if (launch_hash(e, salt, logits) != 0) return -1;
+        if (launch_expand(e) != 0) return -1;
+    }
+    return stream_sync(e->stream);
+}
+
+int gaz_prune(gaz_engine *e, const int16_t *actions, int create_new_root) {
+    if (!e || !actions) return fail("null argument");
+    const View &v = e->v;
+    if (h2d(e->d_actions, actions, (size_t)v.n_trees * sizeof(int16_t), e->stream) != 0) return -1;
+#ifdef GAZ_EMUL
+    *v.leaf_count = 0;
+    for (int t = 0; t < v.n_trees; t++) {
+        if (e->d_actions[t] < 0) continue;
+        Coop cg; Scratch sc;
+        prune_step(cg, v, t, e->d_actions[t], create_new_root, sc);
+    }
+#else
+    k_reset_counter<<<1, 1, 0, e->stream>>>(v.leaf_count);
+    k_prune<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, e->d_actions, create_new_root);
+    CK(cudaGetLastError());
+#endif
+    return read_leaf_count(e);
+}
+
+int gaz_root_stats(gaz_engine *e, int tree, int16_t *actions, uint32_t *visits, float *values, float *priors,
+                   float *raws, int8_t *term, int8_t *expanded, int64_t *info_out) {
+    if (!e) return fail("null engine");
+    const View &v = e->v;
+    if (tree < 0 || tree >= v.n_trees) return fail("tree index %d out of range", tree);
+    TreeState ts;
+    if (d2h(&ts, v.trees + tree, sizeof ts, e->stream) != 0) return -1;
+    if (ts.root < 0) return fail("tree %d has no root", tree);
+    NodeRec r;
+    if (d2h(&r, v.nodes + (size_t)tree * v.node_cap + ts.root, sizeof r, e->stream) != 0) return -1;
+    const int L = nr_L(r);
+    std::vector<uint32_t> sv((size_t)(L ? L : 1)), sch((size_t)(L ? L : 1));
+    std::vector<uint8_t> sa((size_t)(L ? L : 1));
+    if (L > 0) {
+        if (d2h(sv.data(), v.slot_val + (size_t)tree * v.slot_cap + r.slot_base, (size_t)L * 4, e->stream) != 0) return -1;
+        if (d2h(sa.data(), v.slot_act + (size_t)tree * v.slot_cap + r.slot_base, (size_t)L, e->stream) != 0) return -1;
+        if (v.gumbel && d2h(sch.data(), v.slot_child + (size_t)tree * v.slot_cap + r.slot_base, (size_t)L * 4, e->stream) != 0) return -1;
+    }
+    int nexp = 0;
+    for (int i = 0; i < L; i++) {
+        int child;
+        if (v.gumbel) child = sch[(size_t)i] == 0xffffffffu ? -1 : (int)sch[(size_t)i];
+        else child = (nr_tparent(r) || i < nr_nexp(r)) ? (int)sv[(size_t)i] : -1;
+        if (actions) actions[i] = sa[(size_t)i];
+        if (child >= 0) {
+            NodeRec c;
+            if (d2h(&c, v.nodes + (size_t)tree * v.node_cap + child, sizeof c, e->stream) != 0) return -1;
+            if (visits) visits[i] = c.visits;
+            if (values) values[i] = c.value;
+            if (priors) priors[i] = c.prior;
+            if (raws) raws[i] = c.raw;
+            if (term) term[i] = (int8_t)nr_term(c);
+            if (expanded) expanded[i] = 1;
+            nexp++;
+        } else {
+            if (visits) visits[i] = 0;
+            if (values) values[i] = 0.0f;
+            if (priors) priors[i] = u2f(sv[(size_t)i]);
+            if (raws) raws[i] = 0.0f;
+            if (term) term[i] = TERM_NONE;
+            if (expanded) expanded[i] = 0;
+        }
+    }
+    if (info_out) {
+        info_out[0] = L; info_out[1] = nexp; info_out[2] = ts.root_visits; info_out[3] = ts.g_best_slot;
+        info_out[4] = ts.n_nodes; info_out[5] = ts.n_slots; info_out[6] = ts.iter; info_out[7] = ts.evals;
+    }
+    return L;
+}
+
+int gaz_gumbel_pi(gaz_engine *e, int tree, float *pi_out) {
+    if (!e || !pi_out) return fail("null argument");
+    const View &v = e->v;
+    if (!v.gumbel) return fail("engine is not in Gumbel mode");
+    if (tree < 0 || tree >= v.n_trees) return fail("tree index %d out of range", tree);
+#ifdef GAZ_EMUL
+    { Coop cg; Scratch sc; gumbel_final_pi(cg, v, tree, sc, e->d_pi); }
+#else
+    k_gumbel_pi<<<1, 32, 0, e->stream>>>(v, tree, e->d_pi);
+    CK(cudaGetLastError());
+#endif
+    return d2h(pi_out, e->d_pi, MAXL * sizeof(float), e->stream);
+}
+
+int gaz_set_gumbel_noise(gaz_engine *e, const double *noise) {
+    if (!e) return fail("null engine");
+    if (!noise) { e->v.gumbel_noise = nullptr; return 0; }
+    if (!e->d_noise && ealloc(e, &e->d_noise, (size_t)e->v.n_trees * MAXL) != 0) return -1;
+    if (h2d(e->d_noise, noise, (size_t)e->v.n_trees * MAXL * sizeof(double), e->stream) != 0) return -1;
+    e->v.gumbel_noise = e->d_noise;
+    return stream_sync(e->stream);
+}
+
+int gaz_status(gaz_engine *e) {
+    if (!e) return fail("null engine");
+    int32_t s = 0;
+    if (d2h(&s, e->v.status, sizeof s, e->stream) != 0) return -1;
+    return s;
+}
+
+int64_t gaz_bytes_allocated(gaz_engine *e) { return e ? e->bytes : 0; }
+
+} // extern "C"
