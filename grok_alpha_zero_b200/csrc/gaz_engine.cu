@@ -3,23 +3,16 @@
 // Build (product):  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false ... -> libgaz_b200.so
 // Build (tests)  :  g++ -x c++ -DGAZ_EMUL ...  -> tests/_emul/libgaz_emul.so  (host emulation of the
 //                   warp code for the CPU test-suite; never loaded by the package).
-#include "../../include/gaz_b200.h"
-#include "gaz_core.cuh"
+#include "gaz_internal.h"
 
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include <string>
-#include <vector>
-
-#ifndef GAZ_EMUL
-#include <cuda_runtime.h>
-#endif
 
 using namespace gaz;
 
 static thread_local std::string g_err;
-static int fail(const char *fmt, ...) {
+int gaz_fail(const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -28,57 +21,7 @@ static int fail(const char *fmt, ...) {
     g_err = buf;
     return -1;
 }
-
-// ---------------------------------------------------------------- memory ----
-#ifdef GAZ_EMUL
-typedef int gaz_stream_t;
-static int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : -1; }
-static void dev_free(void *p) { free(p); }
-static int h2d(void *d, const void *h, size_t n, gaz_stream_t) { memcpy(d, h, n); return 0; }
-static int d2h(void *h, const void *d, size_t n, gaz_stream_t) { memcpy(h, d, n); return 0; }
-static int dev_zero(void *d, size_t n, gaz_stream_t) { memset(d, 0, n); return 0; }
-static int stream_sync(gaz_stream_t) { return 0; }
-#else
-typedef cudaStream_t gaz_stream_t;
-#define CK(x)                                                                                         \
-    do {                                                                                              \
-        cudaError_t _e = (x);                                                                         \
-        if (_e != cudaSuccess) return fail("%s: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
-static int dev_alloc(void **p, size_t n) {
-    CK(cudaMalloc(p, n ? n : 1));
-    CK(cudaMemset(*p, 0, n ? n : 1));
-    return 0;
-}
-static void dev_free(void *p) { if (p) cudaFree(p); }
-static int h2d(void *d, const void *h, size_t n, gaz_stream_t s) {
-    CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s));
-    return 0;
-}
-static int d2h(void *h, const void *d, size_t n, gaz_stream_t s) {
-    CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return 0;
-}
-static int dev_zero(void *d, size_t n, gaz_stream_t s) { CK(cudaMemsetAsync(d, 0, n, s)); return 0; }
-static int stream_sync(gaz_stream_t s) { CK(cudaStreamSynchronize(s)); return 0; }
-#endif
-
-struct gaz_engine {
-    gaz_config cfg;
-    View v;
-    gaz_stream_t stream;
-    int64_t bytes;
-    std::vector<void *> allocs;
-    int32_t *d_limits;   // [n_trees]
-    int16_t *d_actions;  // [n_trees]
-    uint8_t *d_mask;     // [n_trees]
-    int32_t *d_counter;  // scratch counter
-    int32_t *d_winners;  // [n_games]
-    double *d_noise;
-    double *d_lut;
-    float *d_pi;         // [MAXL]
-};
+#define fail gaz_fail
 
 template <class T> static int ealloc(gaz_engine *e, T **p, size_t count) {
     void *q = nullptr;
@@ -267,6 +210,8 @@ static int launch_hash(gaz_engine *e, uint64_t salt, int logits) {
 #endif
     return 0;
 }
+int gaz_internal_launch_select(gaz_engine *e) { return launch_select(e); }
+int gaz_internal_launch_expand(gaz_engine *e) { return launch_expand(e); }
 static int read_leaf_count(gaz_engine *e) {
     int32_t n = 0;
     if (d2h(&n, e->v.leaf_count, sizeof n, e->stream) != 0) return -1;
@@ -296,6 +241,7 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     gaz_engine *e = new gaz_engine();
     e->cfg = *cfg;
     e->bytes = 0;
+    e->net = nullptr;
     View &v = e->v;
     memset(&v, 0, sizeof v);
     v.game = cfg->game;

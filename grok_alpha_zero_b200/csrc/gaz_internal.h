@@ -1,0 +1,69 @@
+// gaz_internal.h -- engine internals shared by gaz_engine.cu and gaz_net.cu (not part of the ABI).
+#pragma once
+#include "../../include/gaz_b200.h"
+#include "gaz_core.cuh"
+
+#include <string>
+#include <vector>
+
+#ifndef GAZ_EMUL
+#include <cuda_runtime.h>
+#endif
+
+int gaz_fail(const char *fmt, ...);
+
+// ---------------------------------------------------------------- memory ----
+#ifdef GAZ_EMUL
+typedef int gaz_stream_t;
+inline int dev_alloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : -1; }
+inline void dev_free(void *p) { free(p); }
+inline int h2d(void *d, const void *h, size_t n, gaz_stream_t) { memcpy(d, h, n); return 0; }
+inline int d2h(void *h, const void *d, size_t n, gaz_stream_t) { memcpy(h, d, n); return 0; }
+inline int dev_zero(void *d, size_t n, gaz_stream_t) { memset(d, 0, n); return 0; }
+inline int stream_sync(gaz_stream_t) { return 0; }
+#else
+typedef cudaStream_t gaz_stream_t;
+#define CK(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) return gaz_fail("%s: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+inline int dev_alloc(void **p, size_t n) {
+    CK(cudaMalloc(p, n ? n : 1));
+    CK(cudaMemset(*p, 0, n ? n : 1));
+    return 0;
+}
+inline void dev_free(void *p) { if (p) cudaFree(p); }
+inline int h2d(void *d, const void *h, size_t n, gaz_stream_t s) {
+    CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+inline int d2h(void *h, const void *d, size_t n, gaz_stream_t s) {
+    CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+inline int dev_zero(void *d, size_t n, gaz_stream_t s) { CK(cudaMemsetAsync(d, 0, n, s)); return 0; }
+inline int stream_sync(gaz_stream_t s) { CK(cudaStreamSynchronize(s)); return 0; }
+#endif
+
+struct gaz_engine {
+    gaz_config cfg;
+    gaz::View v;
+    gaz_stream_t stream;
+    int64_t bytes;
+    std::vector<void *> allocs;
+    struct gaz_net *net; // attached evaluator (gaz_net.cu) or null
+    int32_t *d_limits;   // [n_trees]
+    int16_t *d_actions;  // [n_trees]
+    uint8_t *d_mask;     // [n_trees]
+    int32_t *d_counter;  // scratch counter
+    int32_t *d_winners;  // [n_games]
+    double *d_noise;
+    double *d_lut;
+    float *d_pi;         // [MAXL]
+};
+
+
+int gaz_internal_launch_select(gaz_engine *e);
+int gaz_internal_launch_expand(gaz_engine *e);

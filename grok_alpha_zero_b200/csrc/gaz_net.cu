@@ -1,0 +1,834 @@
+// gaz_net.cu -- policy/value network evaluator (include/gaz_net.h).
+//
+// Trunk convolutions (C_in in {64,128,256}, C_out in {32,64,128}) run as implicit GEMMs on the 5th-gen
+// tensor cores: one persistent, warp-specialised kernel per layer
+//   warp 0      TMA producer   - per K-block one 128-row x 64-channel activation tile (row-shifted by the
+//                                filter tap) and one C_out x 64 weight tile, SWIZZLE_128B, mbarrier ring
+//   warp 1      MMA issuer     - tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128
+//   warps 2..5  epilogue       - tcgen05.ld -> bias (+ fp32 residual) -> fp32 residual stream and/or
+//                                relu(BN(.)) bf16 operand(s) of the next layer, zeroing the padding rows
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Stem (C_in 2/4), small head convolutions, SE and dense layers are CUDA-core kernels (fp32).
+// Reference network definitions: */Build_Model.py, Net/ResNet/ResNet_Block.py:27-41,
+// Net/SE/SE_Block.py:15-23, Net/Stablemax.py:7-11.
+#include "../../include/gaz_net.h"
+#include "gaz_internal.h"
+#include "gaz_tc.cuh"
+
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdio.h>
+
+using namespace gaz_tc;
+
+#define CKN(x)                                                                                             \
+    do {                                                                                                   \
+        cudaError_t _e = (x);                                                                              \
+        if (_e != cudaSuccess) return gaz_fail("%s: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ====================================================================== tcgen05 conv ==
+struct ConvArgs {
+    const int32_t *count;
+    int max_count;
+    int P_pad, Wp;
+    int taps, kpt; // filter taps (1 or 9), 64-channel K-blocks per tap
+    const float *bias;
+    const float *res;
+    float *out_raw;
+    __nv_bfloat16 *out_a;
+    const float *scale_a, *shift_a;
+    __nv_bfloat16 *out_b;
+    const float *scale_b, *shift_b;
+};
+
+template <int BN> struct ConvCfg {
+    static constexpr int STAGES = BN == 128 ? 6 : 8;
+    static constexpr int A_BYTES = 128 * 64 * 2;
+    static constexpr int B_BYTES = BN * 64 * 2;
+    static constexpr int TMEM_COLS = BN == 128 ? 256 : (BN == 64 ? 128 : 64);
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 512 /*barriers*/ + 5 * BN * 4;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
+    using Cfg = ConvCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;
+    uint8_t *sB = base + STAGES * Cfg::A_BYTES;
+    uint64_t *bars = (uint64_t *)(sB + STAGES * Cfg::B_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
+    float *s_par = (float *)(bars + 2 * STAGES + 8); // bias | scale_a | shift_a | scale_b | shift_b
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int valid_rows = cnt * p.P_pad;
+    const int n_mtiles = (valid_rows + 127) >> 7;
+    const int n_kb = p.taps * p.kpt;
+
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+        s_par[i] = p.bias ? p.bias[i] : 0.0f;
+        s_par[BN + i] = p.scale_a ? p.scale_a[i] : 1.0f;
+        s_par[2 * BN + i] = p.shift_a ? p.shift_a[i] : 0.0f;
+        s_par[3 * BN + i] = p.scale_b ? p.scale_b[i] : 1.0f;
+        s_par[4 * BN + i] = p.shift_b ? p.shift_b[i] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) { // ---------------- TMA producer
+            int stage = 0, phase = 0;
+            for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+                for (int kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
+                    int shift = 0;
+                    if (p.taps == 9) shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+                    tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, mt * 128 + shift);
+                    tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) { // ---------------- MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+            int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < n_kb; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else { // ---------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
+        const int q = warp & 3;
+        int acc = 0, acc_phase = 0;
+        for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row = mt * 128 + q * 32 + lane;
+            const int pos = row % p.P_pad;
+            const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
+            const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ch++) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + s_par[ch * 32 + j];
+                if (p.res) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(p.res + (size_t)row * BN + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 t = rp[j];
+                        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                    }
+                }
+                if (p.out_raw) {
+                    float4 *op = reinterpret_cast<float4 *>(p.out_raw + (size_t)row * BN + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        op[j] = live ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int o = 0; o < 2; o++) {
+                    __nv_bfloat16 *outp = o == 0 ? p.out_a : p.out_b;
+                    if (!outp) continue;
+                    const float *sc = s_par + (1 + 2 * o) * BN + ch * 32, *sh = s_par + (2 + 2 * o) * BN + ch * 32;
+                    uint4 *op = reinterpret_cast<uint4 *>(outp + (size_t)row * BN + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            int c = 8 * j + 2 * t;
+                            float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
+                            float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
+                            w[t] = *reinterpret_cast<uint32_t *>(&h);
+                        }
+                        op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ====================================================================== CUDA-core kernels ==
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+struct StemArgs {
+    const int32_t *count;
+    int max_count;
+    const int8_t *states; // [leaf][H*W*Cin] HWC
+    int H, W, Cin, Cout, K, P_pad, Wp, act;
+    const float *w;       // [K*K][Cin][Cout]
+    const float *bias, *scale, *shift; // conv bias, stem BN affine
+    __nv_bfloat16 *out_q; // activation itself in bf16 (operand of a 1x1 projection), optional
+    float *out_raw;       // activation itself in fp32 (residual stream), optional
+    __nv_bfloat16 *out_a; // relu(BN_a(activation)) = first block's conv1 operand, optional
+    const float *scale_a, *shift_a;
+};
+
+// one warp per padded row; lane owns Cout/32 consecutive channels
+template <int CPL> __global__ void __launch_bounds__(256) stem_kernel(StemArgs p) {
+    extern __shared__ float s_w[];
+    const int nW = p.K * p.K * p.Cin * p.Cout;
+    for (int i = threadIdx.x; i < nW; i += blockDim.x) s_w[i] = p.w[i];
+    __syncthreads();
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int total_rows = ((cnt * p.P_pad + 127) >> 7) << 7;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kh = p.K >> 1;
+    const int c0 = lane * CPL;
+    for (int row = blockIdx.x * 8 + warp; row < total_rows; row += gridDim.x * 8) {
+        const int b = row / p.P_pad, pos = row - b * p.P_pad;
+        const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
+        const bool live = b < cnt && yy >= 0 && xx < p.W;
+        float acc[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; j++) acc[j] = 0.0f;
+        if (live) {
+            const int8_t *st = p.states + (size_t)b * p.H * p.W * p.Cin;
+            for (int ky = 0; ky < p.K; ky++) {
+                const int iy = yy + ky - kh;
+                if (iy < 0 || iy >= p.H) continue;
+                for (int kx = 0; kx < p.K; kx++) {
+                    const int ix = xx + kx - kh;
+                    if (ix < 0 || ix >= p.W) continue;
+                    const int8_t *sp = st + (iy * p.W + ix) * p.Cin;
+                    const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * p.Cout + c0;
+                    for (int ci = 0; ci < p.Cin; ci++) {
+                        const int s = sp[ci];
+                        if (s == 0) continue;
+                        const float fs = (float)s;
+#pragma unroll
+                        for (int j = 0; j < CPL; j++) acc[j] = fmaf(fs, wp[ci * p.Cout + j], acc[j]);
+                    }
+                }
+            }
+        }
+        float v[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; j++) {
+            float t = acc[j] + p.bias[c0 + j];
+            t = fmaf(p.scale[c0 + j], t, p.shift[c0 + j]);
+            t = p.act == GAZ_ACT_RELU ? fmaxf(t, 0.0f) : (p.act == GAZ_ACT_GELU ? gelu_exact(t) : t);
+            v[j] = live ? t : 0.0f;
+        }
+        const size_t o = (size_t)row * p.Cout + c0;
+#pragma unroll
+        for (int j = 0; j < CPL; j++) {
+            if (p.out_raw) p.out_raw[o + j] = v[j];
+            if (p.out_q) p.out_q[o + j] = __float2bfloat16_rn(v[j]);
+            if (p.out_a) {
+                float a = fmaxf(fmaf(p.scale_a[c0 + j], v[j], p.shift_a[c0 + j]), 0.0f);
+                p.out_a[o + j] = __float2bfloat16_rn(live ? a : 0.0f);
+            }
+        }
+    }
+}
+
+struct SeArgs {
+    const int32_t *count;
+    int max_count, H, W, C, R, P_pad, Wp;
+    const float *c2;  // conv2 output (+bias), fp32 padded rows
+    const float *res; // residual stream
+    const float *w1, *b1, *w2, *b2; // dense1 [C][R], dense2 [R][C]
+    float *out_raw;
+    __nv_bfloat16 *out_a, *out_b;
+    const float *scale_a, *shift_a, *scale_b, *shift_b;
+};
+
+// Net/SE/SE_Block.py:15-23 + the block's skip add; one CTA per board, thread = channel
+__global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
+    __shared__ float s_mean[128], s_hid[64], s_gate[128];
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int c = threadIdx.x;
+    for (int b = blockIdx.x; b < cnt; b += gridDim.x) {
+        const size_t base = (size_t)b * p.P_pad * p.C;
+        float s = 0.0f;
+        for (int y = 0; y < p.H; y++)
+            for (int x = 0; x < p.W; x++) s += p.c2[base + (size_t)((y + 1) * p.Wp + x) * p.C + c];
+        s_mean[c] = s / (float)(p.H * p.W);
+        __syncthreads();
+        if (c < p.R) {
+            float h = p.b1[c];
+            for (int i = 0; i < p.C; i++) h = fmaf(s_mean[i], p.w1[i * p.R + c], h);
+            s_hid[c] = fmaxf(h, 0.0f);
+        }
+        __syncthreads();
+        {
+            float g = p.b2[c];
+            for (int i = 0; i < p.R; i++) g = fmaf(s_hid[i], p.w2[i * p.C + c], g);
+            s_gate[c] = 1.0f / (1.0f + expf(-g));
+        }
+        const float gate = s_gate[c];
+        for (int pos = 0; pos < p.P_pad; pos++) {
+            const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
+            const bool live = yy != 0 && xx != p.Wp - 1;
+            const size_t o = base + (size_t)pos * p.C + c;
+            float v = live ? fmaf(p.c2[o], gate, p.res[o]) : 0.0f;
+            if (p.out_raw) p.out_raw[o] = v;
+            if (p.out_a) p.out_a[o] = __float2bfloat16_rn(live ? fmaxf(fmaf(p.scale_a[c], v, p.shift_a[c]), 0.0f) : 0.0f);
+            if (p.out_b) p.out_b[o] = __float2bfloat16_rn(live ? fmaxf(fmaf(p.scale_b[c], v, p.shift_b[c]), 0.0f) : 0.0f);
+        }
+        __syncthreads();
+    }
+}
+
+struct HeadConvArgs {
+    const int32_t *count;
+    int max_count, H, W, Cin, Cout, K, P_pad, Wp, in_f32;
+    long long in_rows;  // allocated rows of the input buffer
+    const void *in;     // padded rows, bf16 or fp32
+    const float *w;     // [K*K][Cin][Cout]
+    const float *bias;
+    float *out;         // flat [leaf][H*W*Cout] (H,W,C order)
+};
+
+// small convolutions of the heads (C_out <= 16): thread per (leaf, cell), weights in shared memory
+__global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
+    extern __shared__ float s_w[];
+    const int nW = p.K * p.K * p.Cin * p.Cout;
+    for (int i = threadIdx.x; i < nW; i += blockDim.x) s_w[i] = p.w[i];
+    __syncthreads();
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int ncell = p.H * p.W;
+    const long long total = (long long)cnt * ncell;
+    const int kh = p.K >> 1;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / ncell), cell = (int)(idx - (long long)b * ncell);
+        const int y = cell / p.W, x = cell - y * p.W;
+        const long long r0 = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = j < p.Cout ? p.bias[j] : 0.0f;
+        for (int ky = 0; ky < p.K; ky++)
+            for (int kx = 0; kx < p.K; kx++) {
+                const long long r = r0 + (ky - kh) * p.Wp + (kx - kh);
+                if (r < 0 || r >= p.in_rows) continue;
+                const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * p.Cout;
+                if (p.in_f32) {
+                    const float *ip = (const float *)p.in + r * p.Cin;
+                    for (int ci = 0; ci < p.Cin; ci++) {
+                        const float a = ip[ci];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) if (j < p.Cout) acc[j] = fmaf(a, wp[ci * p.Cout + j], acc[j]);
+                    }
+                } else {
+                    const __nv_bfloat16 *ip = (const __nv_bfloat16 *)p.in + r * p.Cin;
+                    for (int ci = 0; ci < p.Cin; ci++) {
+                        const float a = __bfloat162float(ip[ci]);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) if (j < p.Cout) acc[j] = fmaf(a, wp[ci * p.Cout + j], acc[j]);
+                    }
+                }
+            }
+        float *op = p.out + (size_t)b * ncell * p.Cout + (size_t)cell * p.Cout;
+#pragma unroll
+        for (int j = 0; j < 16; j++) if (j < p.Cout) op[j] = acc[j];
+    }
+}
+
+struct DenseArgs {
+    const int32_t *count;
+    int max_count, In, Out, act, pre_affine, pre_relu;
+    const float *in;  // [leaf][In]
+    const float *w;   // [In][Out]
+    const float *bias;
+    const float *pre_scale, *pre_shift;
+    float *out;       // [leaf][Out]
+};
+
+// fp32 GEMM, 64x64 tile, 16-deep K slices, 4x4 outputs per thread
+__global__ void __launch_bounds__(256) dense_kernel(DenseArgs p) {
+    __shared__ float sA[16][64 + 1], sB[16][64 + 1];
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    if (m0 >= cnt) return;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < p.In; k0 += 16) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int kk = i & 15, mm = i >> 4;
+            const int k = k0 + kk, m = m0 + mm;
+            float a = 0.0f;
+            if (k < p.In && m < cnt) {
+                a = p.in[(size_t)m * p.In + k];
+                if (p.pre_affine) a = fmaf(p.pre_scale[k], a, p.pre_shift[k]);
+                if (p.pre_relu) a = fmaxf(a, 0.0f);
+            }
+            sA[kk][mm] = a;
+        }
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int nn = i & 63, kk = i >> 6;
+            const int k = k0 + kk, n = n0 + nn;
+            sB[kk][nn] = (k < p.In && n < p.Out) ? p.w[(size_t)k * p.Out + n] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= cnt) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.Out) continue;
+            float v = acc[i][j] + p.bias[n];
+            if (p.act == GAZ_ACT_RELU) v = fmaxf(v, 0.0f);
+            else if (p.act == GAZ_ACT_TANH) v = tanhf(v);
+            p.out[(size_t)m * p.Out + n] = v;
+        }
+    }
+}
+
+// "policy" output activation (Build_Model.py: softmax in float64 / Net/Stablemax.py / linear); warp per leaf
+__global__ void __launch_bounds__(128) policy_out_kernel(const int32_t *count, int max_count, int P, int mode,
+                                                         const float *logits, float *policy) {
+    int cnt = *count;
+    if (cnt > max_count) cnt = max_count;
+    const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (leaf >= cnt) return;
+    const float *lg = logits + (size_t)leaf * P;
+    float *po = policy + (size_t)leaf * P;
+    if (mode == GAZ_POLICY_LINEAR) {
+        for (int i = lane; i < P; i += 32) po[i] = lg[i];
+        return;
+    }
+    if (mode == GAZ_POLICY_SOFTMAX) {
+        double mx = -1e300;
+        for (int i = lane; i < P; i += 32) mx = fmax(mx, (double)lg[i]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double s = 0.0;
+        for (int i = lane; i < P; i += 32) s += exp((double)lg[i] - mx);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        for (int i = lane; i < P; i += 32) po[i] = (float)(exp((double)lg[i] - mx) / s);
+        return;
+    }
+    float s = 0.0f;
+    for (int i = lane; i < P; i += 32) {
+        float x = lg[i];
+        s += x >= 0.0f ? x + 1.0f : 1.0f / (1.0f - x);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int i = lane; i < P; i += 32) {
+        float x = lg[i];
+        po[i] = (x >= 0.0f ? x + 1.0f : 1.0f / (1.0f - x)) / s;
+    }
+}
+
+__global__ void set_count_kernel(int32_t *c, int v) { *c = v; }
+
+// ====================================================================== executor ==
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct NetBuf { int kind, width; void *ptr; size_t bytes; };
+struct NetOp {
+    gaz_net_op d;
+    CUtensorMap tmA, tmB;
+};
+
+struct gaz_net {
+    int game, H, W, Cin, P, Wp, P_pad, max_batch, policy_mode, device;
+    long long rows_alloc;
+    std::vector<NetBuf> bufs;
+    std::vector<NetOp> ops;
+    float *wf;
+    uint16_t *wh;
+    int64_t bytes;
+    int n_sm;
+    cudaStream_t stream;
+    // own I/O buffers for the host path
+    int8_t *d_states;
+    int32_t *d_count;
+    float *d_policy, *d_value;
+    int logits_buf; // id of the flat buffer holding the policy logits
+    // profiling of the tcgen05 conv launches
+    int profile;
+    std::vector<cudaEvent_t> ev;
+    size_t ev_used;
+    std::vector<int> ev_op;
+};
+
+static int make_map(PFN_encodeTiled enc, CUtensorMap *m, void *ptr, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gaz_fail("cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu box=%u", (int)r,
+                                           (unsigned long long)inner, (unsigned long long)rows, box_rows);
+    return 0;
+}
+
+template <int BN> static int launch_conv(gaz_net *n, NetOp &op, const ConvArgs &a, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CKN(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM));
+        attr_set = true;
+    }
+    conv_tc_kernel<BN><<<n->n_sm, 192, ConvCfg<BN>::SMEM, s>>>(op.tmA, op.tmB, a);
+    return 0;
+}
+
+static const float *wfp(gaz_net *n, int64_t off) { return off < 0 ? nullptr : n->wf + off; }
+
+static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, float *policy, float *value, cudaStream_t s) {
+    n->ev_used = n->profile ? n->ev_used : 0;
+    for (size_t oi = 0; oi < n->ops.size(); oi++) {
+        NetOp &op = n->ops[oi];
+        const gaz_net_op &d = op.d;
+        auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
+        switch (d.type) {
+        case GAZ_OP_STEM: {
+            StemArgs a;
+            a.count = count; a.max_count = n->max_batch; a.states = states;
+            a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize; a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act;
+            a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.scale = wfp(n, d.scale_b); a.shift = wfp(n, d.shift_b);
+            a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
+            a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
+            size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
+            int grid = n->n_sm * 8;
+            if (d.cout == 256) stem_kernel<8><<<grid, 256, sm, s>>>(a);
+            else if (d.cout == 128) stem_kernel<4><<<grid, 256, sm, s>>>(a);
+            else if (d.cout == 64) stem_kernel<2><<<grid, 256, sm, s>>>(a);
+            else return gaz_fail("stem cout %d unsupported", d.cout);
+            break;
+        }
+        case GAZ_OP_CONV_TC: {
+            ConvArgs a;
+            a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
+            a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64;
+            a.bias = wfp(n, d.bias); a.res = (const float *)buf(d.res_buf); a.out_raw = (float *)buf(d.out_raw);
+            a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
+            a.out_b = (__nv_bfloat16 *)buf(d.out_b); a.scale_b = wfp(n, d.scale_b); a.shift_b = wfp(n, d.shift_b);
+            if (n->profile && n->ev_used + 2 <= n->ev.size()) {
+                n->ev_op.push_back((int)oi);
+                CKN(cudaEventRecord(n->ev[n->ev_used++], s));
+            }
+            int rc = d.cout == 128 ? launch_conv<128>(n, op, a, s) : d.cout == 64 ? launch_conv<64>(n, op, a, s)
+                     : d.cout == 32 ? launch_conv<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
+            if (rc != 0) return rc;
+            if (n->profile && (n->ev_used & 1)) CKN(cudaEventRecord(n->ev[n->ev_used++], s));
+            break;
+        }
+        case GAZ_OP_SE: {
+            SeArgs a;
+            a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.C = d.cout; a.R = d.cin;
+            a.P_pad = n->P_pad; a.Wp = n->Wp;
+            a.c2 = (const float *)buf(d.in_buf); a.res = (const float *)buf(d.res_buf);
+            a.w1 = wfp(n, d.w2); a.b1 = wfp(n, d.bias2); a.w2 = wfp(n, d.w3); a.b2 = wfp(n, d.bias3);
+            a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.out_b = (__nv_bfloat16 *)buf(d.out_b);
+            a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a); a.scale_b = wfp(n, d.scale_b); a.shift_b = wfp(n, d.shift_b);
+            if (d.cout != 128 || d.cin > 64) return gaz_fail("SE supports C=128, R<=64");
+            se_kernel<<<n->n_sm * 16, 128, 0, s>>>(a);
+            break;
+        }
+        case GAZ_OP_HEADCONV: {
+            HeadConvArgs a;
+            a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize;
+            a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32;
+            a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
+            size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
+            if (d.cout > 16 || sm > 48 * 1024) return gaz_fail("headconv shape unsupported (cout %d, %zu B weights)", d.cout, sm);
+            headconv_kernel<<<n->n_sm * 16, 128, sm, s>>>(a);
+            break;
+        }
+        case GAZ_OP_DENSE: {
+            DenseArgs a;
+            a.count = count; a.max_count = n->max_batch; a.In = d.cin; a.Out = d.cout; a.act = d.act;
+            a.pre_affine = d.flags & 1; a.pre_relu = (d.flags >> 1) & 1;
+            a.in = (const float *)buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias);
+            a.pre_scale = wfp(n, d.scale_a); a.pre_shift = wfp(n, d.shift_a);
+            a.out = (d.flags & 4) ? value : (float *)buf(d.out_raw);
+            dim3 grid((unsigned)((n->max_batch + 63) / 64), (unsigned)((d.cout + 63) / 64));
+            dense_kernel<<<grid, 256, 0, s>>>(a);
+            break;
+        }
+        case GAZ_OP_POLICY_OUT: {
+            policy_out_kernel<<<(n->max_batch + 3) / 4, 128, 0, s>>>(count, n->max_batch, n->P, n->policy_mode,
+                                                                     (const float *)buf(d.in_buf), policy);
+            break;
+        }
+        default:
+            return gaz_fail("unknown op type %d", d.type);
+        }
+    }
+    CKN(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
+    if (!desc || !out) return gaz_fail("null argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0) return gaz_fail("no CUDA device (%s): the network has no CPU path", cudaGetErrorString(ce));
+    CKN(cudaSetDevice(desc->device));
+    PFN_encodeTiled enc = nullptr;
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CKN(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return gaz_fail("cuTensorMapEncodeTiled not available");
+        enc = (PFN_encodeTiled)fn;
+    }
+    gaz_net *n = new gaz_net();
+    n->game = desc->game;
+    if (desc->game == GAZ_GAME_TICTACTOE) { n->H = 3; n->W = 3; n->Cin = 2; n->P = 9; }
+    else if (desc->game == GAZ_GAME_CONNECT4) { n->H = 6; n->W = 7; n->Cin = 4; n->P = 7; }
+    else { n->H = 15; n->W = 15; n->Cin = 2; n->P = 225; }
+    n->Wp = n->W + 1;
+    n->P_pad = (n->H + 1) * n->Wp;
+    n->max_batch = desc->max_batch;
+    n->policy_mode = desc->policy_mode;
+    n->device = desc->device;
+    n->rows_alloc = (((long long)n->max_batch * n->P_pad + 127) / 128) * 128;
+    n->bytes = 0;
+    n->profile = 0;
+    n->ev_used = 0;
+    n->logits_buf = -1;
+    cudaDeviceProp prop;
+    CKN(cudaGetDeviceProperties(&prop, desc->device));
+    n->n_sm = prop.multiProcessorCount;
+    CKN(cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking));
+    auto alloc = [&](void **p, size_t bytes) -> int {
+        CKN(cudaMalloc(p, bytes ? bytes : 16));
+        CKN(cudaMemset(*p, 0, bytes ? bytes : 16));
+        n->bytes += (int64_t)bytes;
+        return 0;
+    };
+    int rc = 0;
+    rc |= alloc((void **)&n->wf, (size_t)desc->n_wf * 4);
+    rc |= alloc((void **)&n->wh, (size_t)desc->n_wh * 2);
+    if (rc == 0 && desc->n_wf) CKN(cudaMemcpy(n->wf, desc->wf, (size_t)desc->n_wf * 4, cudaMemcpyHostToDevice));
+    if (rc == 0 && desc->n_wh) CKN(cudaMemcpy(n->wh, desc->wh, (size_t)desc->n_wh * 2, cudaMemcpyHostToDevice));
+    for (int i = 0; i < desc->n_bufs && rc == 0; i++) {
+        NetBuf b;
+        b.kind = desc->bufs[i].kind;
+        b.width = desc->bufs[i].width;
+        if (b.kind == GAZ_BUF_ROWS_BF16) b.bytes = (size_t)n->rows_alloc * b.width * 2;
+        else if (b.kind == GAZ_BUF_ROWS_F32) b.bytes = (size_t)n->rows_alloc * b.width * 4;
+        else b.bytes = (size_t)n->max_batch * b.width * 4;
+        b.ptr = nullptr;
+        rc |= alloc(&b.ptr, b.bytes);
+        n->bufs.push_back(b);
+    }
+    rc |= alloc((void **)&n->d_states, (size_t)n->max_batch * n->H * n->W * n->Cin);
+    rc |= alloc((void **)&n->d_count, 16);
+    rc |= alloc((void **)&n->d_policy, (size_t)n->max_batch * n->P * 4);
+    rc |= alloc((void **)&n->d_value, (size_t)n->max_batch * 4);
+    if (rc != 0) { gaz_net_destroy(n); return -1; }
+    for (int i = 0; i < desc->n_ops; i++) {
+        NetOp op;
+        op.d = desc->ops[i];
+        memset(&op.tmA, 0, sizeof op.tmA);
+        memset(&op.tmB, 0, sizeof op.tmB);
+        const gaz_net_op &d = op.d;
+        if (d.type == GAZ_OP_CONV_TC) {
+            if (d.cin % 64 != 0 || (d.cout != 32 && d.cout != 64 && d.cout != 128) || (d.ksize != 1 && d.ksize != 3)) {
+                gaz_net_destroy(n);
+                return gaz_fail("conv_tc op %d: unsupported shape cin=%d cout=%d k=%d", i, d.cin, d.cout, d.ksize);
+            }
+            const NetBuf &ib = n->bufs[(size_t)d.in_buf];
+            if (ib.kind != GAZ_BUF_ROWS_BF16 || ib.width != d.cin) {
+                gaz_net_destroy(n);
+                return gaz_fail("conv_tc op %d: input buffer must be bf16 rows of width cin", i);
+            }
+            if (make_map(enc, &op.tmA, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, 128) != 0 ||
+                make_map(enc, &op.tmB, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout) != 0) {
+                gaz_net_destroy(n);
+                return -1;
+            }
+        }
+        if (d.type == GAZ_OP_POLICY_OUT) n->logits_buf = d.in_buf;
+        n->ops.push_back(op);
+    }
+    CKN(cudaDeviceSynchronize());
+    *out = n;
+    return 0;
+}
+
+void gaz_net_destroy(gaz_net *n) {
+    if (!n) return;
+    cudaStreamSynchronize(n->stream);
+    for (auto &b : n->bufs) cudaFree(b.ptr);
+    cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_policy); cudaFree(n->d_value);
+    for (auto e : n->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(n->stream);
+    delete n;
+}
+
+int gaz_net_forward_host(gaz_net *n, const int8_t *states, int cnt, float *policy, float *value, float *logits) {
+    if (!n || !states) return gaz_fail("null argument");
+    if (cnt < 0 || cnt > n->max_batch) return gaz_fail("batch %d exceeds max_batch %d", cnt, n->max_batch);
+    if (cnt == 0) return 0;
+    const size_t ss = (size_t)n->H * n->W * n->Cin;
+    CKN(cudaMemcpyAsync(n->d_states, states, (size_t)cnt * ss, cudaMemcpyHostToDevice, n->stream));
+    set_count_kernel<<<1, 1, 0, n->stream>>>(n->d_count, cnt);
+    if (net_forward(n, n->d_states, n->d_count, n->d_policy, n->d_value, n->stream) != 0) return -1;
+    if (policy) CKN(cudaMemcpyAsync(policy, n->d_policy, (size_t)cnt * n->P * 4, cudaMemcpyDeviceToHost, n->stream));
+    if (value) CKN(cudaMemcpyAsync(value, n->d_value, (size_t)cnt * 4, cudaMemcpyDeviceToHost, n->stream));
+    if (logits && n->logits_buf >= 0)
+        CKN(cudaMemcpyAsync(logits, n->bufs[(size_t)n->logits_buf].ptr, (size_t)cnt * n->P * 4, cudaMemcpyDeviceToHost, n->stream));
+    CKN(cudaStreamSynchronize(n->stream));
+    return cnt;
+}
+
+int gaz_attach_net(gaz_engine *e, gaz_net *n) {
+    if (!e) return gaz_fail("null engine");
+    if (n) {
+        if (n->game != e->cfg.game) return gaz_fail("network game %d != engine game %d", n->game, e->cfg.game);
+        if (n->max_batch < e->v.n_trees) return gaz_fail("network max_batch %d < engine trees %d", n->max_batch, e->v.n_trees);
+    }
+    e->net = n;
+    return 0;
+}
+
+int gaz_eval_net(gaz_engine *e) {
+    if (!e || !e->net) return gaz_fail("no network attached");
+    return net_forward(e->net, e->v.leaf_state, e->v.leaf_count, e->v.policy, e->v.value, e->stream);
+}
+
+int gaz_rounds_net(gaz_engine *e, int n_rounds) {
+    if (!e || !e->net) return gaz_fail("no network attached");
+    for (int r = 0; r < n_rounds; r++) {
+        if (gaz_internal_launch_select(e) != 0) return -1;
+        if (net_forward(e->net, e->v.leaf_state, e->v.leaf_count, e->v.policy, e->v.value, e->stream) != 0) return -1;
+        if (gaz_internal_launch_expand(e) != 0) return -1;
+    }
+    CKN(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
+
+int gaz_net_launches_per_forward(gaz_net *n) { return n ? (int)n->ops.size() : 0; }
+
+/* profile = number of conv launches to keep events for (0 disables).  While enabled every tcgen05 conv
+ * launch is bracketed by CUDA events on the launching stream. */
+int gaz_net_profile(gaz_net *n, int max_launches) {
+    if (!n) return gaz_fail("null net");
+    n->profile = max_launches > 0;
+    n->ev_used = 0;
+    n->ev_op.clear();
+    while ((int)n->ev.size() < 2 * max_launches) {
+        cudaEvent_t ev;
+        CKN(cudaEventCreate(&ev));
+        n->ev.push_back(ev);
+    }
+    return 0;
+}
+
+/* Sum / count of the bracketed conv launches since gaz_net_profile(); per_op_ms (n_ops floats, optional)
+ * receives the per-op totals.  Call after synchronising the stream. */
+int gaz_net_profile_read(gaz_net *n, float *total_ms, int *n_launches, float *per_op_ms) {
+    if (!n) return gaz_fail("null net");
+    float tot = 0.0f;
+    int cnt = 0;
+    if (per_op_ms) for (size_t i = 0; i < n->ops.size(); i++) per_op_ms[i] = 0.0f;
+    for (size_t i = 0; i + 1 < n->ev_used; i += 2) {
+        float ms = 0.0f;
+        CKN(cudaEventElapsedTime(&ms, n->ev[i], n->ev[i + 1]));
+        tot += ms;
+        if (per_op_ms && i / 2 < n->ev_op.size()) per_op_ms[n->ev_op[i / 2]] += ms;
+        cnt++;
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = cnt;
+    return cnt;
+}
+
+int gaz_net_time_forward(gaz_net *n, int cnt, int iters, float *ms_out) {
+    if (!n || !ms_out) return gaz_fail("null argument");
+    if (cnt <= 0 || cnt > n->max_batch) return gaz_fail("bad batch %d", cnt);
+    set_count_kernel<<<1, 1, 0, n->stream>>>(n->d_count, cnt);
+    for (int i = 0; i < 3; i++)
+        if (net_forward(n, n->d_states, n->d_count, n->d_policy, n->d_value, n->stream) != 0) return -1;
+    cudaEvent_t e0, e1;
+    CKN(cudaEventCreate(&e0));
+    CKN(cudaEventCreate(&e1));
+    CKN(cudaStreamSynchronize(n->stream));
+    CKN(cudaEventRecord(e0, n->stream));
+    for (int i = 0; i < iters; i++)
+        if (net_forward(n, n->d_states, n->d_count, n->d_policy, n->d_value, n->stream) != 0) return -1;
+    CKN(cudaEventRecord(e1, n->stream));
+    CKN(cudaStreamSynchronize(n->stream));
+    float ms = 0.0f;
+    CKN(cudaEventElapsedTime(&ms, e0, e1));
+    ms_out[0] = ms / (float)iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+} // extern "C"

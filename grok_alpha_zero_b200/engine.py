@@ -167,6 +167,12 @@ class Engine:
         self._ck(self.lib.gaz_gumbel_pi(self._h, tree, _p(pi)))
         return pi
 
+    def eval_net(self):
+        self._ck(self.lib.gaz_eval_net(self._h))
+
+    def rounds_net(self, n):
+        self._ck(self.lib.gaz_rounds_net(self._h, int(n)))
+
     def status(self):
         return self._ck(self.lib.gaz_status(self._h))
 

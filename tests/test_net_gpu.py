@@ -1,0 +1,97 @@
+"""GPU suite: CUDA policy/value network (tcgen05 trunk) vs the fp32 PyTorch restatement.
+
+Tolerance = BASELINE.json north_star: policy logits atol 2e-2, value atol 1e-2 (bf16 operands,
+fp32 accumulate, fp32 residual stream) on the synthetic weights of netspec.init_weights."""
+import numpy as np
+import pytest
+
+import engine_parity as ep
+import net_util
+import oracle as orc
+from grok_alpha_zero_b200 import netspec
+from grok_alpha_zero_b200.engine import Engine
+from grok_alpha_zero_b200.net import Net
+from net_oracle import NetOracle
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 2e-2
+VALUE_ATOL = 1e-2
+
+CASES = [
+    ("tictactoe", "softmax", {}, 37),
+    ("connect4", "softmax", {}, 70),
+    ("connect4", "stablemax", dict(num_blocks=2), 5),
+    ("gomoku", "softmax", dict(num_blocks=1, use_se=False), 9),
+    ("gomoku", "softmax", dict(num_blocks=2, use_se=True), 9),
+    ("gomoku", "softmax", {}, 40),
+    ("gomoku", "linear", dict(use_se=False), 21),
+    ("gomoku", "stablemax", {}, 3),
+]
+
+
+@pytest.mark.parametrize("game,head,over,n", CASES, ids=lambda c: str(c).replace(" ", ""))
+def test_net_matches_fp32_oracle(game, head, over, n):
+    spec = netspec.build_spec(game, head, **over)
+    W = netspec.init_weights(spec, seed=1)
+    st = net_util.random_states(game, n, seed=4)
+    ref = NetOracle(spec, W).forward(st)
+    net = Net(spec, W, max_batch=max(n, 8))
+    pol, val, lg = net.forward(st, want_logits=True)
+    err_l = np.abs(lg - ref["logits"].numpy()).max()
+    err_v = np.abs(val - ref["value"].numpy().reshape(-1)).max()
+    err_p = np.abs(pol - ref["policy"].numpy()).max()
+    print("%s %s %s: logits err %.4g (absmax %.3g) value err %.4g policy err %.3g" %
+          (game, head, over, err_l, np.abs(lg).max(), err_v, err_p))
+    assert np.isfinite(lg).all() and np.isfinite(val).all()
+    assert err_l <= LOGIT_ATOL, err_l
+    assert err_v <= VALUE_ATOL, err_v
+    # a second pass with a smaller batch must reproduce the same rows bit for bit (row independence)
+    pol2, val2 = net.forward(st[: max(1, n // 3)])
+    np.testing.assert_array_equal(pol2, pol[: len(pol2)])
+    np.testing.assert_array_equal(val2, val[: len(val2)])
+    net.close()
+
+
+@pytest.mark.parametrize("game,over,iters", [("connect4", dict(num_blocks=2), 120), ("gomoku", dict(num_blocks=2, use_se=True), 250)])
+def test_closed_loop_search_with_cuda_net_is_bit_exact(game, over, iters):
+    """Engine + attached CUDA network (leaves never leave HBM) vs the C oracle calling the SAME CUDA
+    network through the host path: visit counts / value sums / actions must be identical."""
+    spec = netspec.build_spec(game, "softmax", **over)
+    W = netspec.init_weights(spec, seed=2)
+    n_games = 6
+    net = Net(spec, W, max_batch=64)
+    eng = Engine(game, n_games=n_games, mode="puct", trees_per_game=1, c_puct_init=2.5, iters_hint=iters)
+    net.attach(eng)
+    rng = np.random.RandomState(0)
+    games = [ep.random_position(game, rng, rng.randint(0, 8)) for _ in range(n_games)]
+    for i, g in enumerate(games):
+        eng.set_game(i, g.board, g.next_player, g.history)
+    if eng.new_roots() > 0:
+        eng.eval_net()
+        eng.expand()
+    eng.run_begin([iters] * n_games)
+    guard = 0
+    while eng.remaining() > 0:
+        if eng.select() > 0:
+            eng.eval_net()
+            eng.expand()
+        guard += 1
+        assert guard < 10000
+    assert eng.status() == 0
+
+    def host_eval(state):
+        p, v = net.forward(state[None])
+        return p[0], v[0]
+
+    for i, g in enumerate(games):
+        t = orc.OracleTree(game, False, evaluator=host_eval, c_puct_init=2.5)
+        t.new_root(g)
+        t.run(iters)
+        ref = t.root_stats()
+        st = eng.root_stats(i)
+        np.testing.assert_array_equal(st["action"], ref["action"])
+        np.testing.assert_array_equal(st["visits"], ref["visits"])
+        np.testing.assert_array_equal(st["values"].view(np.uint32), ref["values"].view(np.uint32))
+    eng.close()
+    net.close()
