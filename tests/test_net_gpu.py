@@ -25,7 +25,7 @@ CASES = [
     ("gomoku", "softmax", dict(num_blocks=1, use_se=False), 9),
     ("gomoku", "softmax", dict(num_blocks=2, use_se=True), 9),
     ("gomoku", "softmax", {}, 40),
-    ("gomoku", "linear", dict(use_se=False), 21),
+    ("gomoku", "linear", dict(num_blocks=4, use_se=False), 21),  # Gomoku/Gomoku.py:5 default depth
     ("gomoku", "stablemax", {}, 3),
 ]
 
