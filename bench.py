@@ -1,0 +1,482 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS simulations/s of the self-play hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config gomoku|connect4|gumbel|tictactoe]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # CPU arm: the oracle port of the reference path on the host cores
+
+Workload (BASELINE.json configs[2], the config the north-star target is quoted on): Gomoku 15x15 self-play,
+PUCT with 800 sims/move (Self_Play.py:99 passes int(800*1.5) = 1200 iterations), 10-block ResNet(128)+SE in
+bf16, 16384 concurrent games per GPU, two trees per game as in Self_Play.py:39-57, random-init synthetic
+weights (no checkpoint exists anywhere).  Games shard over GPUs by index with no collective on the search
+path, so scaling is "weak": per-GPU work is fixed.
+
+A STEP is one search round: one simulation in every running tree = select (PUCT descent, terminal
+look-ahead, leaf encode) -> network forward on the gathered leaves -> expand + backup.  `value` counts the
+simulations the device actually performed (iteration counters read back), divided by the CUDA-event time of
+the K timed rounds on the engine's stream, max over ranks.  When a run reaches its iteration limit inside the
+timed region the move transition (root stats -> argmax move -> apply -> re-root both trees -> next run)
+happens inside the timed region too.
+
+`e2e` is the same metric through the public host-buffer API: every e2e pass uploads all live game boards from
+pinned host memory (gaz_set_games), builds fresh roots (1 evaluation each, the MCTS constructor of
+MCTS.py:132), runs K rounds and reads every root's visit counts / value sums / chosen move back to the host
+(gaz_root_dense).  Root construction and both copies are inside its timed region; only the K*games
+simulations are counted.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: game, mode, games/GPU, sims/move, iteration limit handed to run(), net overrides, c_puct, opening
+    "gomoku": dict(game="gomoku", mode="puct", games=16384, sims=800, limit=1200, net={}, head="softmax",
+                   c_puct_init=4.5, opening=112, label="Gomoku 15x15 self-play, PUCT 800 sims/move (x1.5 = 1200 "
+                   "iterations, Self_Play.py:99), 10-block ResNet128+SE bf16, 16384 games/GPU"),
+    "connect4": dict(game="connect4", mode="puct", games=4096, sims=800, limit=1200, net={}, head="softmax",
+                     c_puct_init=2.5, opening=None, label="Connect4 6x7 self-play, PUCT 800 sims/move, 5-block "
+                     "ResNet128 bf16, 4096 games/GPU"),
+    "gumbel": dict(game="gomoku", mode="gumbel", games=16384, sims=64, limit=64, net={}, head="stablemax",
+                   c_puct_init=4.5, opening=112, label="Gomoku 15x15 Gumbel MCTS m=16 n=64 StableMax, 10-block "
+                   "ResNet128+SE bf16, 16384 games/GPU"),
+    "tictactoe": dict(game="tictactoe", mode="puct", games=4096, sims=200, limit=300, net={}, head="softmax",
+                      c_puct_init=2.5, opening=None, label="TicTacToe 3x3 self-play, PUCT 200 sims/move, small "
+                      "ResNet, 4096 games/GPU"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def tree_caps(cfg):
+    """(node_cap, slot_cap) per tree from the oracle tree census: Gomoku <= ~1350 nodes and
+    <= ~290k child slots per tree at 1200 iterations/move with sub-tree reuse."""
+    if cfg["game"] == "gomoku":
+        if cfg["mode"] == "gumbel":
+            return 192, 192 * 225
+        return 1664, 340000
+    if cfg["game"] == "connect4":
+        return 4096, 4096 * 7
+    return 1024, 1024 * 9
+
+
+class SelfPlayBench:
+    """Drives the engine the way Self_Play.play does (two PUCT trees per game, the tree of the side to move
+    searches, both are re-rooted after the move; one fresh Gumbel tree per move)."""
+
+    def __init__(self, cfg, n_games, device):
+        from grok_alpha_zero_b200 import netspec
+        from grok_alpha_zero_b200.engine import Engine
+        from grok_alpha_zero_b200.net import Net
+        self.cfg, self.n_games = cfg, n_games
+        self.gumbel = cfg["mode"] == "gumbel"
+        self.tpg = 1 if self.gumbel else 2
+        self.spec = netspec.build_spec(cfg["game"], cfg["head"] if not self.gumbel else "linear", **cfg["net"])
+        self.weights = netspec.init_weights(self.spec, seed=0)
+        self.flops_per_eval = netspec.flops_per_eval(self.spec)
+        node_cap, slot_cap = tree_caps(cfg)
+        self.eng = Engine(cfg["game"], n_games=n_games, mode=cfg["mode"], trees_per_game=self.tpg, node_cap=node_cap,
+                          slot_cap=slot_cap, c_puct_init=cfg["c_puct_init"], m=16, c_visit=50.0, c_scale=1.0,
+                          activation_fn="stablemax" if self.gumbel else "softmax", device=device)
+        self.net = Net(self.spec, self.weights, max_batch=n_games, device=device)
+        self.net.attach(self.eng)
+        self.moves = 0
+        self.sims_done = 0       # simulations of finished runs
+        self.next_player = np.full(n_games, -1, np.int32)
+        self.alive = np.ones(n_games, bool)
+        self.launches = 0
+        self.per_round_launches = 3 + 1 + self.net.n_ops  # counter reset, select, expand + chunk count + net ops
+
+    # ---- Self_Play.play pieces -------------------------------------------------------------
+    def start(self):
+        e, cfg = self.eng, self.cfg
+        e.reset_games()
+        if cfg["opening"] is not None:  # Gomoku/Gomoku.py:47 opening book [[7,7], 0.333]: every third game
+            a = np.full(self.n_games, -1, np.int16)
+            a[::3] = cfg["opening"]
+            e.apply_actions(a)
+            self.next_player[::3] = 1
+        self._fresh_roots()
+        self._begin_run()
+
+    def _fresh_roots(self, mask=None):
+        e = self.eng
+        for k in range(self.tpg):  # one tree per game at a time keeps the batch <= n_games
+            m = np.zeros((self.n_games, self.tpg), np.uint8)
+            m[:, k] = 1 if mask is None else mask
+            if e.new_roots(m.reshape(-1)) > 0:
+                e.eval_net()
+                self.launches += 1 + self.net.n_ops
+            e.expand()
+            self.launches += 3
+
+    def _limits(self):
+        lim = np.zeros((self.n_games, self.tpg), np.int32)
+        if self.gumbel:
+            lim[:, 0] = np.where(self.alive, self.cfg["limit"], 0)
+        else:
+            lim[np.arange(self.n_games), (self.next_player > 0).astype(int)] = np.where(self.alive, self.cfg["limit"], 0)
+        return lim.reshape(-1)
+
+    def _begin_run(self):
+        self.eng.run_begin(self._limits())
+        self.launches += 1
+
+    def rounds(self, n, sync=False):
+        self.eng.rounds_net(n, sync=sync)
+        self.launches += n * self.per_round_launches
+
+    def run_finished(self):
+        return self.eng.remaining() == 0
+
+    def advance_move(self):
+        """root stats -> tau=0 move -> do_action/check_win -> prune_tree on both trees -> next run"""
+        e = self.eng
+        _, _, info = e.root_dense(want_values=False)
+        info = info.reshape(self.n_games, self.tpg, 4)
+        run_tree = 0 if self.gumbel else (self.next_player > 0).astype(int)
+        sel = info[np.arange(self.n_games), run_tree]
+        self.sims_done += int(sel[self.alive, 2].sum())
+        act = np.where(self.alive, sel[:, 1], -1).astype(np.int16)
+        winners = e.apply_actions(act)
+        self.next_player = np.where(self.alive, -self.next_player, self.next_player)
+        self.alive &= winners == -2
+        self.moves += int((act >= 0).sum())
+        pa = np.repeat(np.where(self.alive, act, -1).astype(np.int16), self.tpg)
+        if e.prune(pa, create_new_root=self.gumbel) > 0:  # Gumbel: tree rebuilt every move (Self_Play.py:151-153)
+            e.eval_net()
+            self.launches += 1 + self.net.n_ops
+        e.expand()
+        self.launches += 6
+        self._begin_run()
+
+    def sims_in_flight(self):
+        _, _, info = self.eng.root_dense(want_values=False)
+        info = info.reshape(self.n_games, self.tpg, 4)
+        run_tree = 0 if self.gumbel else (self.next_player > 0).astype(int)
+        sel = info[np.arange(self.n_games), run_tree]
+        return int(sel[self.alive, 2].sum())
+
+    def evals_total(self):
+        _, _, info = self.eng.root_dense(want_values=False)
+        return int(info[:, 3].astype(np.int64).sum())
+
+    def total_sims(self):
+        return self.sims_done + self.sims_in_flight()
+
+
+def dominant_kernel_stats(sb, leaves_per_launch, peaks):
+    """CUDA-event time of the dominant kernel (3x3 C128->C128 tcgen05 implicit-GEMM conv) inside the timed region."""
+    tot, cnt, per = sb.net.profile_read()
+    shapes = sb.net.op_shapes()
+    best = None
+    groups = {}
+    for oi, (typ, cin, cout, k) in enumerate(shapes):
+        if typ != 1 or per[oi] <= 0:
+            continue
+        groups.setdefault((cin, cout, k), [0.0, 0])
+        groups[(cin, cout, k)][0] += float(per[oi])
+        groups[(cin, cout, k)][1] += 1
+    if not groups:
+        return None, {}
+    key = max(groups, key=lambda g: groups[g][0])
+    n_ops_in_group = groups[key][1]
+    passes = cnt / max(1, sum(g[1] for g in groups.values()))
+    launches = n_ops_in_group * passes
+    avg_ms = groups[key][0] / max(1.0, launches)
+    cin, cout, k = key
+    hw = sb.spec["H"] * sb.spec["W"]
+    flops = 2.0 * leaves_per_launch * hw * k * k * cin * cout
+    achieved = flops / (avg_ms * 1e-3) / 1e12
+    share = groups[key][0] / max(tot, 1e-9)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tp):
+        try:
+            t = json.load(open(tp))
+            if t.get("kernel") == "conv3x3_%d_%d" % (cin, cout) and t.get("leaves") == int(leaves_per_launch):
+                traffic = t.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = dict(bound="tensor", kernel="conv_tc_kernel<%d> %dx%d C%d->C%d (tcgen05 implicit GEMM)" % (cout, k, k, cin, cout),
+                achieved=round(achieved, 2), peak=peaks["sustained"], unit="TFLOP/s", frac=round(achieved / peaks["sustained"], 4),
+                peak_source="%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
+                flops_per_launch=flops, avg_launch_ms=round(avg_ms, 4), launches_timed=int(launches),
+                share_of_conv_time=round(share, 4), traffic=traffic)
+    return roof, dict(conv_ms_total=tot, conv_launches=cnt)
+
+
+def run_reference(args, cfg):
+    """CPU arm: oracle port of the reference path (numba MCTS + inference server) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import __graft_entry__ as ge
+    ge.build_oracle()
+    import cpu_selfplay
+    from grok_alpha_zero_b200 import netspec
+    cores = os.cpu_count() or 1
+    workers = cores
+    spec = netspec.build_spec(cfg["game"], cfg["head"], **cfg["net"])
+    W = netspec.init_weights(spec, seed=0)
+    sims_per_step = 4
+    r = cpu_selfplay.run_sample(cfg["game"], spec, W, n_workers=workers, sims_per_step=sims_per_step, steps=args.steps,
+                                warmup=args.warmup, c_puct_init=cfg["c_puct_init"], opening=cfg["opening"],
+                                torch_threads=cores)
+    sample = ("%d worker threads x 1 game (C oracle port of MCTS.py) + 1 batching inference server (fp32 torch-CPU "
+              "restatement of the Keras net standing in for onnxruntime-CPU, mean batch %.1f); step = %d sims/game"
+              % (workers, r["mean_batch"], sims_per_step))
+    line = dict(impl="reference", metric="MCTS simulations/sec", value=r["sims_per_s"], unit="sims/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=cfg["label"], reference_sample=sample),
+                cpu_baseline=dict(value=r["sims_per_s"], unit="sims/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=r["sims_per_s"], unit="sims/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="gomoku", choices=sorted(CONFIGS))
+    ap.add_argument("--games", type=int, default=0, help="override games per GPU")
+    ap.add_argument("--presearch", type=int, default=-1,
+                    help="untimed rounds before warm-up so trees are mid-search (default: past the forced root expansion)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_games = args.games or cfg["games"]
+    peaks = load_peaks()
+
+    sb = SelfPlayBench(cfg, n_games, local)
+    sb.start()
+    presearch = args.presearch
+    if presearch < 0:
+        presearch = {"gomoku": 232, "connect4": 16, "tictactoe": 12}[cfg["game"]] if cfg["mode"] == "puct" else 20
+    done = 0
+    while done < presearch:
+        n = min(32, presearch - done)
+        sb.rounds(n, sync=True)
+        done += n
+        if sb.run_finished():
+            sb.advance_move()
+
+    def barrier():
+        sb.eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_rounds(k):
+        """k search rounds incl. move transitions; returns ms (device events on the engine stream)"""
+        sb.eng.timer_begin()
+        left = k
+        while left > 0:
+            n = min(left, 64)
+            sb.rounds(n, sync=False)
+            left -= n
+            if sb.run_finished():  # reads a counter back: synchronises
+                sb.advance_move()
+        return sb.eng.timer_end()
+
+    # ---- warm-up + timed region -------------------------------------------------------------------
+    timed_rounds(args.warmup)
+    sims0, evals0, l0 = sb.total_sims(), sb.evals_total(), sb.launches
+    sb.net.profile(min(4096, (args.steps + 2) * sb.net.n_conv_tc))
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms = timed_rounds(args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    sims1, evals1, l1 = sb.total_sims(), sb.evals_total(), sb.launches
+    sims = sims1 - sims0
+    evals = evals1 - evals0
+    leaves_per_round = evals / max(1, args.steps)
+    roof, conv = dominant_kernel_stats(sb, leaves_per_round, peaks)
+    sb.net.profile(0)
+    status = sb.eng.status()
+    if status != 0:
+        raise SystemExit("engine status %d (1 node overflow, 2 slot overflow, 4 LUT miss, 8 bad state)" % status)
+
+    # ---- e2e: host boards in, root statistics out ---------------------------------------------------------
+    H, Wd = sb.eng.H, sb.eng.W
+    boards = torch.zeros((n_games, H, Wd), dtype=torch.int8).pin_memory().numpy()
+    nxt = np.full(n_games, -1, np.int32)
+    last = np.full(n_games, -1, np.int32)
+    if cfg["opening"] is not None:
+        boards.reshape(n_games, -1)[::3, cfg["opening"]] = -1
+        nxt[::3] = 1
+        last[::3] = cfg["opening"]
+    run_mask = np.ones(n_games, np.uint8)
+    e2e_ms, e2e_sims = [], 0
+    e2e_passes = 2
+    for p in range(e2e_passes + 1):
+        barrier()
+        t0 = time.perf_counter()
+        sb.eng.set_games(boards, nxt, last_actions=last)
+        sb.next_player = nxt.copy()
+        sb.alive[:] = True
+        m = np.zeros((n_games, sb.tpg), np.uint8)
+        m[np.arange(n_games), 0 if sb.gumbel else (nxt > 0).astype(int)] = 1
+        if sb.eng.new_roots(m.reshape(-1)) > 0:
+            sb.eng.eval_net()
+        sb.eng.expand()
+        sb._begin_run()
+        sb.rounds(args.steps, sync=False)
+        vis, val, info = sb.eng.root_dense(want_values=True)
+        barrier()
+        dt = (time.perf_counter() - t0) * 1e3
+        info = info.reshape(n_games, sb.tpg, 4)
+        got = int(info[np.arange(n_games), 0 if sb.gumbel else (nxt > 0).astype(int), 2].sum())
+        if p > 0:  # first pass is warm-up
+            e2e_ms.append(dt)
+            e2e_sims += got
+        assert int(vis.sum()) > 0
+    h2d = boards.nbytes + n_games * 16 + sb.eng.n_trees * (4 + 1)   # boards + meta + limits + root mask
+    d2h = vis.nbytes + val.nbytes + info.nbytes
+    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(sims), float(evals), float(e2e_sims), float(sb.moves)], dtype=torch.float64, device="cuda")
+    mst = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_all = float(mst.item())
+    sims_all, evals_all, e2e_sims_all, moves_all = (float(x) for x in tot.tolist())
+
+    if rank == 0:
+        value = sims_all / (ms_all * 1e-3)
+        e2e_value = e2e_sims_all / (float(e2e_t.item()) * 1e-3)
+        line = dict(metric="MCTS simulations/sec", value=value, unit="sims/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_all / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload=cfg["label"], games_per_gpu=n_games, trees_per_game=sb.tpg,
+                                step="one search round = 1 simulation in every running tree (select -> network -> expand/backup)",
+                                presearch_rounds=presearch, weights="random-init he_normal, seed 0",
+                                l2="per-step working set (%.1f GB of activations + trees) is far larger than the 126 MB L2; no flush needed"
+                                   % (sb.net.bytes_allocated() / 1e9),
+                                sharding="games by index, no collective on the search path"),
+                    positions_per_s=value / cfg["limit"],
+                    nn_evals_per_s=evals_all / (ms_all * 1e-3), sims_per_eval=sims_all / max(1.0, evals_all),
+                    net_tflops=evals_all * sb.flops_per_eval / (ms_all * 1e-3) / 1e12,
+                    e2e=dict(value=e2e_value, unit="sims/s", h2d_bytes_per_step=int(h2d / args.steps),
+                             d2h_bytes_per_step=int(d2h / args.steps),
+                             what="per pass: pinned host boards -> gaz_set_games, fresh roots (1 eval each), %d rounds, "
+                                  "gaz_root_dense -> host visit counts/value sums/moves; wall clock incl. copies" % args.steps),
+                    gpu_launches=int(l1 - l0), clocks=clocks, roofline=roof,
+                    hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()))
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import cpu_selfplay
+                cores = os.cpu_count() or 1
+                spc = 4
+                csteps = 24 if cfg["game"] == "gomoku" else 200
+                r = cpu_selfplay.run_sample(cfg["game"], sb.spec, sb.weights, n_workers=cores, sims_per_step=spc,
+                                            steps=csteps, warmup=2, c_puct_init=cfg["c_puct_init"], opening=cfg["opening"],
+                                            torch_threads=cores)
+                line["cpu_baseline"] = dict(
+                    value=r["sims_per_s"], unit="sims/s", cores=cores, kind="port",
+                    sample="%d games x %d sims (%d worker threads on the C oracle port of MCTS.py + 1 batching server on the "
+                           "fp32 torch-CPU restatement of the network, mean batch %.1f), %.1f s"
+                           % (cores, spc * csteps, cores, r["mean_batch"], r["seconds"]))
+            except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+                line["cpu_baseline"] = dict(value=None, unit="sims/s", cores=os.cpu_count(), kind="port",
+                                            sample="failed: %r" % (ex,))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

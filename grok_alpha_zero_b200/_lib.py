@@ -27,6 +27,7 @@ SYMBOLS = {
     "gaz_set_puct_params": (C.c_int, [_P, C.c_float, C.c_float]),
     "gaz_set_gumbel_params": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_int]),
     "gaz_set_game": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int]),
+    "gaz_set_games": (C.c_int, [_P, _P, _P]),
     "gaz_reset_games": (C.c_int, [_P]),
     "gaz_apply_actions": (C.c_int, [_P, _P, _P]),
     "gaz_get_game": (C.c_int, [_P, C.c_int, _P, _P]),
@@ -43,6 +44,10 @@ SYMBOLS = {
     "gaz_root_stats": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gaz_gumbel_pi": (C.c_int, [_P, C.c_int, _P]),
     "gaz_set_gumbel_noise": (C.c_int, [_P, _P]),
+    "gaz_root_dense": (C.c_int, [_P, _P, _P, _P]),
+    "gaz_timer_begin": (C.c_int, [_P]),
+    "gaz_timer_end": (C.c_int, [_P, _P]),
+    "gaz_sync": (C.c_int, [_P]),
     "gaz_status": (C.c_int, [_P]),
     "gaz_bytes_allocated": (C.c_int64, [_P]),
 }

@@ -30,6 +30,7 @@ SYMBOLS = {
     "gaz_attach_net": (C.c_int, [_P, _P]),
     "gaz_eval_net": (C.c_int, [_P]),
     "gaz_rounds_net": (C.c_int, [_P, C.c_int]),
+    "gaz_rounds_net_async": (C.c_int, [_P, C.c_int]),
     "gaz_net_bytes": (C.c_int64, [_P]),
     "gaz_net_launches_per_forward": (C.c_int, [_P]),
     "gaz_net_profile": (C.c_int, [_P, C.c_int]),

@@ -110,6 +110,77 @@ GAZ_HD void apply_action_game(const View &v, int gi, int action, int32_t *winner
     if (winners) winners[gi] = g.winner;
 }
 
+
+// Root statistics of every tree as dense per-action vectors (the rows of MCTS.run, MCTS.py:591-600,
+// scattered by action id the way compute_policy_improvement does, Gomoku.py:257-262).
+template <class CG>
+GAZ_HD void root_dense_tree(const CG &cg, const View &v, int tree, uint32_t *visits, float *values, int32_t *info) {
+    const TreeState &ts = v.trees[tree];
+    uint32_t *vo = visits + (size_t)tree * v.P;
+    float *qo = values ? values + (size_t)tree * v.P : nullptr;
+    for (int i = cg.lane; i < v.P; i += cg.width()) { vo[i] = 0; if (qo) qo[i] = 0.0f; }
+    cg.sync();
+    int32_t *io = info + (size_t)tree * 4;
+    if (ts.root < 0) {
+        if (cg.lane == 0) { io[0] = 0; io[1] = -1; io[2] = ts.iter; io[3] = ts.evals; }
+        return;
+    }
+    const NodeRec r = *node_ptr(v, tree, ts.root);
+    const uint8_t *sa = slota_ptr(v, tree);
+    const int L = nr_L(r);
+    uint32_t bestv = 0;
+    int besti = L;
+    for (int i = cg.lane; i < L; i += cg.width()) {
+        int c = child_at(v, tree, r, i);
+        if (c < 0) continue;
+        const NodeRec *cr = node_ptr(v, tree, c);
+        int a = sa[r.slot_base + i];
+        vo[a] = cr->visits;
+        if (qo) qo[a] = cr->value;
+        if (cr->visits > bestv) { bestv = cr->visits; besti = i; } // first max inside the lane's stride
+    }
+    // np.argmax(child_visits): first maximum over slot order (MCTS.py:603)
+    uint32_t mx = cg.umax(bestv);
+    int cand = (bestv == mx && besti < L) ? besti : L;
+    cand = cg.imin(cand);
+    if (cg.lane == 0) {
+        io[0] = (int32_t)ts.root_visits;
+        io[1] = v.gumbel ? (ts.g_best_slot >= 0 ? sa[r.slot_base + ts.g_best_slot] : -1)
+                         : (L > 0 ? sa[r.slot_base + (cand < L ? cand : 0)] : -1);
+        io[2] = ts.iter;
+        io[3] = ts.evals;
+    }
+}
+
+// Batched upload of live games: cells int8 [n_games][ncell], meta int32 [n_games][4] =
+// next_player, hist_len, last3 (packed), last_action
+GAZ_HD void set_game_from_cells(const View &v, int gi, const int8_t *cells, const int32_t *meta) {
+    GameState g;
+    for (int w = 0; w < MAXNW; w++) g.board[w] = 0;
+    const int8_t *c = cells + (size_t)gi * v.ncell;
+    for (int i = 0; i < v.ncell; i++) {
+        if (c[i] == 0) continue;
+        int p = c[i] > 0 ? 1 : 0;
+        if (v.game == GAME_GOMOKU) {
+            int y = i / 15, x = i - y * 15;
+            g.board[p * 8 + (y >> 1)] |= 1u << (x + (y & 1) * 16);
+        } else if (v.game == GAME_C4) {
+            int y = i / 7, x = i - y * 7;
+            int bit = x * 7 + (5 - y);
+            g.board[p * 2 + (bit >> 5)] |= 1u << (bit & 31);
+        } else {
+            g.board[p] |= 1u << i;
+        }
+    }
+    g.next_player = meta[gi * 4 + 0];
+    g.hist_len = meta[gi * 4 + 1];
+    g.last3 = (uint32_t)meta[gi * 4 + 2];
+    g.winner = -2;
+    g.last_action = meta[gi * 4 + 3];
+    g.pad[0] = g.pad[1] = g.pad[2] = 0;
+    v.games[gi] = g;
+}
+
 #ifndef GAZ_EMUL
 #define WARP_PROLOGUE(count)                                          \
     const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    \
@@ -171,6 +242,17 @@ __global__ void __launch_bounds__(32) k_gumbel_pi(View v, int tree, float *out) 
     __shared__ Scratch sc;
     Coop cg;
     gumbel_final_pi(cg, v, tree, sc, out);
+}
+__global__ void __launch_bounds__(THREADS) k_root_dense(View v, uint32_t *visits, float *values, int32_t *info) {
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= v.n_trees) return;
+    Coop cg;
+    root_dense_tree(cg, v, widx, visits, values, info);
+}
+__global__ void k_set_games(View v, const int8_t *cells, const int32_t *meta) {
+    int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= v.n_games) return;
+    set_game_from_cells(v, gi, cells, meta);
 }
 static inline int grid_warps(int n) { return (n + WARPS - 1) / WARPS; }
 #endif
@@ -242,6 +324,7 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     e->cfg = *cfg;
     e->bytes = 0;
     e->net = nullptr;
+    e->leaf_bound = 0;
     View &v = e->v;
     memset(&v, 0, sizeof v);
     v.game = cfg->game;
@@ -297,6 +380,10 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     rc |= ealloc(e, &e->d_lut, (size_t)v.lut_n);
     rc |= ealloc(e, &e->d_pi, MAXL);
     e->d_noise = nullptr;
+    e->d_cells = nullptr; e->d_meta = nullptr; e->d_dense_vis = nullptr; e->d_dense_val = nullptr; e->d_dense_info = nullptr;
+#ifndef GAZ_EMUL
+    e->ev0 = nullptr; e->ev1 = nullptr;
+#endif
     if (rc != 0) { gaz_destroy(e); return g_err.empty() ? fail("allocation failed") : -1; }
     v.c_lut = e->d_lut;
     *out = e;
@@ -313,6 +400,7 @@ void gaz_destroy(gaz_engine *e) {
 #endif
     for (void *p : e->allocs) dev_free(p);
 #ifndef GAZ_EMUL
+    if (e->ev0) { cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); }
     cudaStreamDestroy(e->stream);
 #endif
     delete e;
@@ -439,13 +527,18 @@ int gaz_new_roots(gaz_engine *e, const uint8_t *tree_mask) {
     k_new_roots<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, dm);
     CK(cudaGetLastError());
 #endif
-    return read_leaf_count(e);
+    int nl = read_leaf_count(e);
+    e->leaf_bound = nl > 0 ? nl : 1;
+    return nl;
 }
 
 int gaz_run_begin(gaz_engine *e, const int32_t *limits) {
     if (!e || !limits) return fail("null argument");
     const View &v = e->v;
     if (h2d(e->d_limits, limits, (size_t)v.n_trees * sizeof(int32_t), e->stream) != 0) return -1;
+    int running = 0;
+    for (int t = 0; t < v.n_trees; t++) running += limits[t] > 0 ? 1 : 0;
+    e->leaf_bound = running > 0 ? running : 1;
 #ifdef GAZ_EMUL
     for (int t = 0; t < v.n_trees; t++) { Coop cg; run_begin_tree(cg, v, t, e->d_limits[t]); }
 #else
@@ -544,7 +637,9 @@ int gaz_prune(gaz_engine *e, const int16_t *actions, int create_new_root) {
     k_prune<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, e->d_actions, create_new_root);
     CK(cudaGetLastError());
 #endif
-    return read_leaf_count(e);
+    int nl = read_leaf_count(e);
+    e->leaf_bound = nl > 0 ? nl : 1;
+    return nl;
 }
 
 int gaz_root_stats(gaz_engine *e, int tree, int16_t *actions, uint32_t *visits, float *values, float *priors,
@@ -617,6 +712,76 @@ int gaz_set_gumbel_noise(gaz_engine *e, const double *noise) {
     if (!e->d_noise && ealloc(e, &e->d_noise, (size_t)e->v.n_trees * MAXL) != 0) return -1;
     if (h2d(e->d_noise, noise, (size_t)e->v.n_trees * MAXL * sizeof(double), e->stream) != 0) return -1;
     e->v.gumbel_noise = e->d_noise;
+    return stream_sync(e->stream);
+}
+
+int gaz_set_games(gaz_engine *e, const int8_t *boards, const int32_t *meta) {
+    if (!e || !boards || !meta) return fail("null argument");
+    const View &v = e->v;
+    if (!e->d_cells) {
+        if (ealloc(e, &e->d_cells, (size_t)v.n_games * v.ncell) != 0) return -1;
+        if (ealloc(e, &e->d_meta, (size_t)v.n_games * 4) != 0) return -1;
+    }
+    if (h2d(e->d_cells, boards, (size_t)v.n_games * v.ncell, e->stream) != 0) return -1;
+    if (h2d(e->d_meta, meta, (size_t)v.n_games * 4 * sizeof(int32_t), e->stream) != 0) return -1;
+#ifdef GAZ_EMUL
+    for (int g = 0; g < v.n_games; g++) set_game_from_cells(v, g, e->d_cells, e->d_meta);
+#else
+    k_set_games<<<(v.n_games + 127) / 128, 128, 0, e->stream>>>(v, e->d_cells, e->d_meta);
+    CK(cudaGetLastError());
+#endif
+    return 0; // stream-ordered; the next call on this engine observes the new games
+}
+
+int gaz_root_dense(gaz_engine *e, uint32_t *visits_out, float *values_out, int32_t *info_out) {
+    if (!e || !visits_out || !info_out) return fail("null argument");
+    const View &v = e->v;
+    const size_t NT = (size_t)v.n_trees;
+    if (!e->d_dense_vis) {
+        if (ealloc(e, &e->d_dense_vis, NT * v.P) != 0) return -1;
+        if (ealloc(e, &e->d_dense_val, NT * v.P) != 0) return -1;
+        if (ealloc(e, &e->d_dense_info, NT * 4) != 0) return -1;
+    }
+#ifdef GAZ_EMUL
+    for (int t = 0; t < v.n_trees; t++) { Coop cg; root_dense_tree(cg, v, t, e->d_dense_vis, e->d_dense_val, e->d_dense_info); }
+    memcpy(visits_out, e->d_dense_vis, NT * v.P * 4);
+    if (values_out) memcpy(values_out, e->d_dense_val, NT * v.P * 4);
+    memcpy(info_out, e->d_dense_info, NT * 4 * sizeof(int32_t));
+    return 0;
+#else
+    k_root_dense<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, e->d_dense_vis, e->d_dense_val, e->d_dense_info);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(visits_out, e->d_dense_vis, NT * v.P * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (values_out) CK(cudaMemcpyAsync(values_out, e->d_dense_val, NT * v.P * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(info_out, e->d_dense_info, NT * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    return stream_sync(e->stream);
+#endif
+}
+
+int gaz_timer_begin(gaz_engine *e) {
+    if (!e) return fail("null engine");
+#ifndef GAZ_EMUL
+    if (!e->ev0) { CK(cudaEventCreate(&e->ev0)); CK(cudaEventCreate(&e->ev1)); }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+#endif
+    return 0;
+}
+
+int gaz_timer_end(gaz_engine *e, float *ms_out) {
+    if (!e || !ms_out) return fail("null argument");
+    *ms_out = 0.0f;
+#ifndef GAZ_EMUL
+    if (!e->ev0) return fail("gaz_timer_begin was not called");
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
+#endif
+    return 0;
+}
+
+int gaz_sync(gaz_engine *e) {
+    if (!e) return fail("null engine");
     return stream_sync(e->stream);
 }
 

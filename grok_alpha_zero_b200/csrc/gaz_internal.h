@@ -54,6 +54,7 @@ struct gaz_engine {
     int64_t bytes;
     std::vector<void *> allocs;
     struct gaz_net *net; // attached evaluator (gaz_net.cu) or null
+    int leaf_bound;      // host-side upper bound of outstanding leaf requests (0 = n_trees)
     int32_t *d_limits;   // [n_trees]
     int16_t *d_actions;  // [n_trees]
     uint8_t *d_mask;     // [n_trees]
@@ -62,6 +63,14 @@ struct gaz_engine {
     double *d_noise;
     double *d_lut;
     float *d_pi;         // [MAXL]
+    int8_t *d_cells;     // [n_games][ncell] staging of gaz_set_games
+    int32_t *d_meta;     // [n_games][4]
+    uint32_t *d_dense_vis; // [n_trees][P] staging of gaz_root_dense
+    float *d_dense_val;
+    int32_t *d_dense_info; // [n_trees][4]
+#ifndef GAZ_EMUL
+    cudaEvent_t ev0, ev1; // gaz_timer_begin / gaz_timer_end
+#endif
 };
 
 

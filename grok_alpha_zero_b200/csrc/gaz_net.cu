@@ -483,6 +483,11 @@ __global__ void __launch_bounds__(128) policy_out_kernel(const int32_t *count, i
 }
 
 __global__ void set_count_kernel(int32_t *c, int v) { *c = v; }
+// leaves [offset, offset + max) of the request list form one forward chunk
+__global__ void chunk_count_kernel(const int32_t *total, int offset, int max, int32_t *out) {
+    int c = *total - offset;
+    *out = c < 0 ? 0 : (c > max ? max : c);
+}
 
 // ====================================================================== executor ==
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -508,6 +513,7 @@ struct gaz_net {
     // own I/O buffers for the host path
     int8_t *d_states;
     int32_t *d_count;
+    int32_t *d_chunk_count; // [16] per-chunk leaf counts of an engine-driven forward
     float *d_policy, *d_value;
     int logits_buf; // id of the flat buffer holding the policy logits
     // profiling of the tcgen05 conv launches
@@ -685,6 +691,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     }
     rc |= alloc((void **)&n->d_states, (size_t)n->max_batch * n->H * n->W * n->Cin);
     rc |= alloc((void **)&n->d_count, 16);
+    rc |= alloc((void **)&n->d_chunk_count, 16 * 4);
     rc |= alloc((void **)&n->d_policy, (size_t)n->max_batch * n->P * 4);
     rc |= alloc((void **)&n->d_value, (size_t)n->max_batch * 4);
     if (rc != 0) { gaz_net_destroy(n); return -1; }
@@ -722,7 +729,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_policy); cudaFree(n->d_value);
+    cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
     delete n;
@@ -748,25 +755,53 @@ int gaz_attach_net(gaz_engine *e, gaz_net *n) {
     if (!e) return gaz_fail("null engine");
     if (n) {
         if (n->game != e->cfg.game) return gaz_fail("network game %d != engine game %d", n->game, e->cfg.game);
-        if (n->max_batch < e->v.n_trees) return gaz_fail("network max_batch %d < engine trees %d", n->max_batch, e->v.n_trees);
     }
     e->net = n;
     return 0;
 }
 
+// Serves the engine's outstanding leaf requests; the request list is cut into chunks of max_batch
+// leaves (the host-side bound e->leaf_bound says how many chunks can be non-empty).
+static int engine_forward(gaz_engine *e) {
+    gaz_net *n = e->net;
+    const gaz::View &v = e->v;
+    int bound = e->leaf_bound > 0 ? e->leaf_bound : v.n_trees;
+    int chunks = (bound + n->max_batch - 1) / n->max_batch;
+    if (chunks > 16) return gaz_fail("leaf bound %d needs more than 16 chunks of %d", bound, n->max_batch);
+    const size_t ss = (size_t)v.ncell * v.C;
+    for (int c = 0; c < chunks; c++) {
+        const int off = c * n->max_batch;
+        chunk_count_kernel<<<1, 1, 0, e->stream>>>(v.leaf_count, off, n->max_batch, n->d_chunk_count + c);
+        if (net_forward(n, v.leaf_state + (size_t)off * ss, n->d_chunk_count + c, v.policy + (size_t)off * v.P,
+                        v.value + off, e->stream) != 0) return -1;
+    }
+    return 0;
+}
+
 int gaz_eval_net(gaz_engine *e) {
     if (!e || !e->net) return gaz_fail("no network attached");
-    return net_forward(e->net, e->v.leaf_state, e->v.leaf_count, e->v.policy, e->v.value, e->stream);
+    return engine_forward(e);
 }
 
 int gaz_rounds_net(gaz_engine *e, int n_rounds) {
     if (!e || !e->net) return gaz_fail("no network attached");
     for (int r = 0; r < n_rounds; r++) {
         if (gaz_internal_launch_select(e) != 0) return -1;
-        if (net_forward(e->net, e->v.leaf_state, e->v.leaf_count, e->v.policy, e->v.value, e->stream) != 0) return -1;
+        if (engine_forward(e) != 0) return -1;
         if (gaz_internal_launch_expand(e) != 0) return -1;
     }
     CKN(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// same without the trailing synchronise (bench: events bracket many calls)
+int gaz_rounds_net_async(gaz_engine *e, int n_rounds) {
+    if (!e || !e->net) return gaz_fail("no network attached");
+    for (int r = 0; r < n_rounds; r++) {
+        if (gaz_internal_launch_select(e) != 0) return -1;
+        if (engine_forward(e) != 0) return -1;
+        if (gaz_internal_launch_expand(e) != 0) return -1;
+    }
     return 0;
 }
 

@@ -81,6 +81,17 @@ class Engine:
         tail = np.array(list(reversed(history[-3:])) + [0, 0, 0], dtype=np.int16)
         self._ck(self.lib.gaz_set_game(self._h, g, _p(b), int(next_player), _p(tail), len(history)))
 
+    def set_games(self, boards, next_players, hist_lens=None, last3=None, last_actions=None):
+        """Upload every live game at once: boards int8 (n_games, H, W) (pinned memory welcome)."""
+        b = np.ascontiguousarray(boards, dtype=np.int8).reshape(self.n_games, self.H * self.W)
+        meta = np.zeros((self.n_games, 4), dtype=np.int32)
+        meta[:, 0] = next_players
+        meta[:, 1] = (b != 0).sum(1) if hist_lens is None else hist_lens
+        meta[:, 2] = 0 if last3 is None else last3
+        meta[:, 3] = -1 if last_actions is None else last_actions
+        self._keep = (b, meta)  # the copy is asynchronous
+        self._ck(self.lib.gaz_set_games(self._h, _p(b), _p(meta)))
+
     def reset_games(self):
         self._ck(self.lib.gaz_reset_games(self._h))
 
@@ -162,6 +173,26 @@ class Engine:
                     best_slot=int(info[3]), n_nodes=int(info[4]), n_slots=int(info[5]), iter=int(info[6]),
                     evals=int(info[7]))
 
+    def root_dense(self, want_values=True):
+        """Visit counts / value sums of every tree scattered by action id + per-tree info
+        (root_visits, tau=0 move, iterations, evals)."""
+        vis = np.zeros((self.n_trees, self.P), np.uint32)
+        val = np.zeros((self.n_trees, self.P), np.float32) if want_values else None
+        info = np.zeros((self.n_trees, 4), np.int32)
+        self._ck(self.lib.gaz_root_dense(self._h, _p(vis), _p(val), _p(info)))
+        return vis, val, info
+
+    def timer_begin(self):
+        self._ck(self.lib.gaz_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._ck(self.lib.gaz_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        self._ck(self.lib.gaz_sync(self._h))
+
     def gumbel_pi(self, tree=0):
         pi = np.zeros(256, dtype=np.float32)
         self._ck(self.lib.gaz_gumbel_pi(self._h, tree, _p(pi)))
@@ -170,8 +201,9 @@ class Engine:
     def eval_net(self):
         self._ck(self.lib.gaz_eval_net(self._h))
 
-    def rounds_net(self, n):
-        self._ck(self.lib.gaz_rounds_net(self._h, int(n)))
+    def rounds_net(self, n, sync=True):
+        fn = self.lib.gaz_rounds_net if sync else self.lib.gaz_rounds_net_async
+        self._ck(fn(self._h, int(n)))
 
     def status(self):
         return self._ck(self.lib.gaz_status(self._h))

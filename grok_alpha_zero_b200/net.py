@@ -228,6 +228,7 @@ class Net:
         self.n_ops = len(b.ops)
         self.n_conv_tc = sum(1 for o in b.ops if o["type"] == OP_CONV_TC)
         self.conv_shapes = [(o["cin"], o["cout"], o["ksize"]) for o in b.ops if o["type"] == OP_CONV_TC]
+        self._op_shapes = [(o["type"], o["cin"], o["cout"], o["ksize"]) for o in b.ops]
         bufs = (GazNetBuf * len(b.bufs))(*[GazNetBuf(k, w) for k, w in b.bufs])
         ops = (GazNetOp * len(b.ops))(*[GazNetOp(**o) for o in b.ops])
         wf = np.concatenate(b.wf) if b.wf else np.zeros(4, np.float32)
@@ -272,6 +273,10 @@ class Net:
     def attach(self, engine):
         self._ck(self.lib.gaz_attach_net(engine._h, self._h))
         engine._net = self  # keep alive
+
+    def op_shapes(self):
+        """(op type, cin, cout, ksize) of every op in launch order"""
+        return list(self._op_shapes)
 
     def bytes_allocated(self):
         return int(self.lib.gaz_net_bytes(self._h))

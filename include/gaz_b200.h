@@ -60,6 +60,12 @@ int gaz_set_gumbel_params(gaz_engine *e, int m, double c_visit, double c_scale, 
  * hist_tail = the last <=3 actions, most recent first. */
 int gaz_set_game(gaz_engine *e, int game, const int8_t *board, int next_player, const int16_t *hist_tail,
                  int hist_len);
+/* the same for every game at once (Self_Play.py:346-363 starts one process per game; here one call uploads
+ * all live `game` objects).  boards = n_games * H*W int8 cells; meta = n_games * 4 int32:
+ * next_player, len(action_history), last three actions packed 3 bits each (most recent in bits 0-2;
+ * only Connect4's input-state encoding reads them, Connect4.py:327-346), last action (-1 = none).
+ * Stream-ordered: returns after enqueueing the copy + scatter kernel. */
+int gaz_set_games(gaz_engine *e, const int8_t *boards, const int32_t *meta);
 int gaz_reset_games(gaz_engine *e);
 /* game.do_action + game.check_win for every game (Self_Play.py:142-144); actions[g] < 0 = skip.
  * winners_out[g] = -2 running / -1,0,1 (may be NULL). */
@@ -100,11 +106,21 @@ int gaz_prune(gaz_engine *e, const int16_t *actions, int create_new_root);
  * [5] n_slots, [6] iter, [7] evals */
 int gaz_root_stats(gaz_engine *e, int tree, int16_t *actions, uint32_t *visits, float *values, float *priors,
                    float *raws, int8_t *term, int8_t *expanded, int64_t *info_out);
+/* Root statistics of EVERY tree in one call, scattered by action id like compute_policy_improvement
+ * (Gomoku.py:257-262, Connect4.py:414-419): visits_out / values_out = n_trees * P (0 where illegal or
+ * unexpanded; values_out may be NULL); info_out = n_trees * 4 int32: root.visits, the move MCTS.run would
+ * return for tau = 0 (np.argmax over child_visits, first maximum; Gumbel: the sequential-halving survivor),
+ * iterations done in the current run, evaluator calls so far. */
+int gaz_root_dense(gaz_engine *e, uint32_t *visits_out, float *values_out, int32_t *info_out);
 /* final pi' of MCTS_Gumbel.run (:653-662) for one tree, L floats in slot order */
 int gaz_gumbel_pi(gaz_engine *e, int tree, float *pi_out);
 /* injected Gumbel(0,1) noise for parity runs: n_trees * 256 doubles or NULL to clear */
 int gaz_set_gumbel_noise(gaz_engine *e, const double *noise);
 
+/* CUDA-event stopwatch on the engine's stream (bench.py; torch events cannot see this stream) */
+int gaz_timer_begin(gaz_engine *e);
+int gaz_timer_end(gaz_engine *e, float *ms_out);
+int gaz_sync(gaz_engine *e);
 int gaz_status(gaz_engine *e); /* sticky error bits: 1 node overflow, 2 slot overflow, 4 LUT miss, 8 bad state */
 int64_t gaz_bytes_allocated(gaz_engine *e);
 

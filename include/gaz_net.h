@@ -71,6 +71,8 @@ int gaz_attach_net(gaz_engine *e, gaz_net *net);
 int gaz_eval_net(gaz_engine *e);
 /* n_rounds x (select -> network -> expand), stream-ordered, no host sync inside; returns 0 */
 int gaz_rounds_net(gaz_engine *e, int n_rounds);
+/* same without the trailing stream synchronise */
+int gaz_rounds_net_async(gaz_engine *e, int n_rounds);
 
 /* timing / introspection for bench.py */
 /* Bracket every tcgen05 conv launch with CUDA events on the launching stream (max_launches = event

@@ -561,15 +561,11 @@ static int puct_select(const Tree *t) {
     }
 }
 
-/* MCTS.run: MCTS.py:528-587.  Returns the effective iteration count. */
-int orc_puct_run(Tree *t, int iteration_limit) {
-    Node *root = &t->nodes[t->root];
-    int16_t tmp[ORC_MAXP];
-    int n_legal = legal_actions(&t->g, root->board, tmp);
-    if (n_legal == 1) iteration_limit = 1;
-    else if (iteration_limit < n_legal) iteration_limit = n_legal * 3;
+/* n iterations of the MCTS.run loop body (MCTS.py:560-587) */
+static void puct_iterations(Tree *t, int n) {
+    Node *root;
     int fully = 0;
-    for (int it = 0; it < iteration_limit; it++) {
+    for (int it = 0; it < n; it++) {
         root = &t->nodes[t->root];
         if (!fully) {
             int zero = 0;
@@ -587,7 +583,24 @@ int orc_puct_run(Tree *t, int iteration_limit) {
         back_propagate(t, node, value, visits);
         t->n_sims++;
     }
+}
+
+/* MCTS.run: MCTS.py:528-587.  Returns the effective iteration count. */
+int orc_puct_run(Tree *t, int iteration_limit) {
+    Node *root = &t->nodes[t->root];
+    int16_t tmp[ORC_MAXP];
+    int n_legal = legal_actions(&t->g, root->board, tmp);
+    if (n_legal == 1) iteration_limit = 1;
+    else if (iteration_limit < n_legal) iteration_limit = n_legal * 3;
+    puct_iterations(t, iteration_limit);
     return iteration_limit;
+}
+
+/* A slice of a longer run for bench.py's bounded CPU sample: n more iterations of the same loop body,
+ * without re-applying the budget rule of MCTS.py:543-546 (the caller holds the run's limit). */
+int orc_puct_iterate(Tree *t, int n) {
+    puct_iterations(t, n);
+    return n;
 }
 
 /* --------------------------------------------------------------- Gumbel -- */

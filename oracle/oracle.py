@@ -41,6 +41,8 @@ def lib():
         L.orc_new_root.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_puct_run.argtypes = [C.c_void_p, C.c_int]
         L.orc_puct_run.restype = C.c_int
+        L.orc_puct_iterate.argtypes = [C.c_void_p, C.c_int]
+        L.orc_puct_iterate.restype = C.c_int
         L.orc_gumbel_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_gumbel_run.restype = C.c_int
         L.orc_prune.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -143,6 +145,11 @@ class OracleTree:
         a = self.L.orc_gumbel_run(self.t, iteration_limit, noise, _p(pi))
         self.pi = pi[: self.L.orc_root_L(self.t)].copy()
         return a
+
+    def iterate(self, n):
+        """n more iterations of the PUCT run loop (a slice of a longer run; bench.py's CPU sample)."""
+        assert not self.gumbel
+        return self.L.orc_puct_iterate(self.t, int(n))
 
     def prune(self, action, create_new_root=False):
         self.L.orc_prune(self.t, int(action), int(create_new_root))
