@@ -1,0 +1,350 @@
+// gaz_conv.cuh -- board-tile implicit-GEMM convolution on tcgen05 (v2 of the trunk convolution).
+//
+// One persistent CTA walks 256-row tiles of the padded-row activation tensor (Gomoku: 256 rows = exactly one
+// board).  Compared with v1 (one TMA tile per filter tap) this kernel is built around the shared-memory port,
+// which is what bounds an M=128 x N=128 cta_group::1 MMA (8 KB of operand reads per 64-cycle MMA = 128 B/clk):
+//   * the activation SLAB of a tile (24 halo rows + 256 rows + 24 halo rows, 64 channels, SWIZZLE_128B) is
+//     loaded ONCE per 64-channel K-block and all 9 filter taps read it through row-shifted UMMA descriptors
+//     (start address + shift*128 B; measured on B200: the MMA unit applies the 128B swizzle to ABSOLUTE shared-
+//     memory address bits exactly like TMA does, so a row-shifted start needs matrix-base-offset = 0 - setting it
+//     to (addr >> 7) & 7 gives wrong results), so A is written to SMEM once, not 9x;
+//   * every weight tile (tap, K-block) is used by both 128-row halves of the tile (8 MMAs per 16 KB tile);
+//   * TMEM holds 2 stages x 2 accumulators (4 x BN columns) so the epilogue of tile i overlaps the MMAs of i+1.
+// Warp roles (256 threads): 0 = slab TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+TMEM alloc),
+// 3 = idle, 4..7 = epilogue (TMEM lane quarter = warp & 3).
+// Epilogue modes: plain (bias [+ fp32 residual] -> fp32 stream and/or relu(BN(.)) bf16 operands) and fused
+// Squeeze-Excitation (Net/SE/SE_Block.py:15-23 + the block's skip add, Net/ResNet/ResNet_Block.py:27-41):
+// pass 1 folds the accumulators into per-channel board means (halving butterfly over the 32 rows of a warp),
+// the 128 epilogue threads run the two tiny dense layers + sigmoid, pass 2 re-reads TMEM and writes
+// gate*(conv+bias) + residual.  fp32 row tensors use a 32x32-blocked layout (f32_blk_index) so that the
+// row-per-lane accesses of the epilogue are 1 KB-contiguous 256-bit vectors instead of 32 separate lines.
+#pragma once
+#include "gaz_tc.cuh"
+#include <cuda_bf16.h>
+
+namespace gaz_conv {
+using namespace gaz_tc;
+
+// ---- blocked fp32 row tensor: element (row, c) of a [rows][C] tensor, rows % 32 == 0, C % 32 == 0 ----
+// 32x32 blocks; inside a block 8-float pieces of a row are interleaved across the 32 rows so that lane r reading
+// piece j of its row touches block + j*256 + r*8 floats: one warp instruction = 1 KB contiguous.
+__host__ __device__ __forceinline__ size_t f32_blk_index(long long row, int c, int C) {
+    const long long g = row >> 5;
+    const int r = (int)(row & 31);
+    const int cb = c >> 5, ci = c & 31;
+    return ((size_t)(g * (C >> 5) + cb) << 10) + (size_t)((ci >> 3) << 8) + (size_t)(r << 3) + (size_t)(ci & 7);
+}
+
+__device__ __forceinline__ void ldg256(const float *p, float (&r)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float *p, const float (&r)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]) : "memory");
+}
+__device__ __forceinline__ void stg256u(void *p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+// K-major SWIZZLE_128B descriptor whose start row is NOT aligned to the 8-row (1024 B) swizzle pattern.  The slab
+// base is 1024 B aligned and was written by TMA, so the swizzle phase of every row is a function of its absolute
+// address; base_offset_mode = 0 (default, parity-tested) leaves the matrix-base-offset field (bits 49..51) zero,
+// mode 1 (debug) fills it with the phase of the start address.
+__device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, int base_offset_mode) {
+    uint64_t d = umma_desc_sw128(smem_addr);
+    if (base_offset_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+    return d;
+}
+
+struct BoardConvArgs {
+    const int32_t *count;
+    int max_count;
+    int P_pad, Wp;
+    int taps, kpt;            // filter taps (1 or 9), 64-channel K-blocks per tap
+    int base_offset_mode;     // 0 = base offset field zero (correct on B200), 1 = phase of the start address (debug)
+    const float *bias;
+    const float *res;         // blocked fp32 residual stream (optional)
+    float *out_raw;           // blocked fp32 output (optional)
+    __nv_bfloat16 *out_a;     // relu(scale_a * v + shift_a) as bf16 rows (optional)
+    const float *scale_a, *shift_a;
+    __nv_bfloat16 *out_b;
+    const float *scale_b, *shift_b;
+    // fused Squeeze-Excitation (tile == board, P_pad == 256): dense1 [C][R], dense2 [R][C]
+    int se, se_r, n_cells;
+    const float *se_w1, *se_b1, *se_w2, *se_b2;
+};
+
+constexpr int HALO = 24;                       // >= Wp + 1 for every game, multiple of 8
+constexpr int TILE_ROWS = 256;
+constexpr int SLAB_ROWS = TILE_ROWS + 2 * HALO; // 304 rows = 2 TMA boxes of 152 rows
+constexpr int SLAB_BYTES = SLAB_ROWS * 128;     // 38912 = 38 * 1024
+constexpr int SLAB_BOX_ROWS = SLAB_ROWS / 2;
+
+template <int BN> struct BoardCfg {
+    static constexpr int NSLAB = 4;
+    static constexpr int NB = 4;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;
+    static constexpr int PAR_FLOATS = 5 * BN;
+    static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [4 warps][2 halves][BN], mean, hidden, gate
+    static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                                (PAR_FLOATS + SE_FLOATS) * 4;
+};
+
+struct Ring {
+    int idx;
+    uint32_t phase;
+    __device__ Ring() : idx(0), phase(0) {}
+    __device__ void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, BoardConvArgs p) {
+    using Cfg = BoardCfg<BN>;
+    constexpr int NSLAB = Cfg::NSLAB, NB = Cfg::NB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;
+    uint8_t *sB = base + NSLAB * SLAB_BYTES;
+    uint64_t *bars = (uint64_t *)(sB + NB * Cfg::B_BYTES);
+    uint64_t *a_full = bars, *a_empty = bars + NSLAB, *b_full = bars + 2 * NSLAB, *b_empty = bars + 2 * NSLAB + NB;
+    uint64_t *tfull = bars + 2 * NSLAB + 2 * NB, *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    float *s_par = (float *)(bars + 32); // bias | scale_a | shift_a | scale_b | shift_b
+    float *s_se = s_par + Cfg::PAR_FLOATS;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const long long valid_rows = (long long)cnt * p.P_pad;
+    const int n_tiles = (int)((valid_rows + TILE_ROWS - 1) / TILE_ROWS);
+
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+        s_par[i] = p.bias ? p.bias[i] : 0.0f;
+        s_par[BN + i] = p.scale_a ? p.scale_a[i] : 1.0f;
+        s_par[2 * BN + i] = p.shift_a ? p.shift_a[i] : 0.0f;
+        s_par[3 * BN + i] = p.scale_b ? p.scale_b[i] : 1.0f;
+        s_par[4 * BN + i] = p.shift_b ? p.shift_b[i] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLAB; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) { // ---------------- activation-slab TMA producer
+            Ring r;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int row0 = t * TILE_ROWS - HALO;
+                for (int kc = 0; kc < p.kpt; kc++) {
+                    mbar_wait(&a_empty[r.idx], r.phase ^ 1);
+                    mbar_expect_tx(&a_full[r.idx], SLAB_BYTES);
+                    uint8_t *dst = sA + r.idx * SLAB_BYTES;
+                    tma_load_2d(dst, &tmA, &a_full[r.idx], kc * 64, row0);
+                    tma_load_2d(dst + SLAB_BYTES / 2, &tmA, &a_full[r.idx], kc * 64, row0 + SLAB_BOX_ROWS);
+                    r.advance(NSLAB);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) { // ---------------- weight-tile TMA producer: order (K-block, tap)
+            Ring r;
+            const int cin = p.kpt * 64;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+                for (int kc = 0; kc < p.kpt; kc++)
+                    for (int tap = 0; tap < p.taps; tap++) {
+                        mbar_wait(&b_empty[r.idx], r.phase ^ 1);
+                        mbar_expect_tx(&b_full[r.idx], Cfg::B_BYTES);
+                        tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, 0);
+                        r.advance(NB);
+                    }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) { // ---------------- MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+            Ring ra, rb;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
+                for (int kc = 0; kc < p.kpt; kc++) {
+                    mbar_wait(&a_full[ra.idx], ra.phase);
+                    const uint32_t slab = smem_u32(sA + ra.idx * SLAB_BYTES);
+                    for (int tap = 0; tap < p.taps; tap++) {
+                        mbar_wait(&b_full[rb.idx], rb.phase);
+                        tc_fence_after();
+                        int shift = 0;
+                        if (p.taps == 9) shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+                        const uint32_t b_addr = smem_u32(sB + rb.idx * Cfg::B_BYTES);
+#pragma unroll
+                        for (int sub = 0; sub < 2; sub++) {
+                            const uint32_t a_addr = slab + (uint32_t)((HALO + sub * 128 + shift) * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                umma_bf16(d0 + (uint32_t)(sub * BN), umma_desc_sw128_shifted(a_addr + k * 32, p.base_offset_mode),
+                                          umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kc | tap | k) != 0));
+                        }
+                        umma_commit(&b_empty[rb.idx]);
+                        rb.advance(NB);
+                    }
+                    umma_commit(&a_empty[ra.idx]);
+                    ra.advance(NSLAB);
+                }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) { // ---------------- epilogue warps (TMEM lane quarter q)
+        const int q = warp & 3;
+        const int et = threadIdx.x - 128; // 0..127
+        float *s_part = s_se, *s_mean = s_se + 8 * BN, *s_hid = s_mean + BN, *s_gate = s_hid + BN;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
+            if (p.se) {
+                // ---- pass 1: per-channel sums over the board's live cells
+#pragma unroll 1
+                for (int sub = 0; sub < 2; sub++) {
+                    const int pos = sub * 128 + q * 32 + lane; // tile == board
+                    const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
+                    const bool live = yy != 0 && xx != p.Wp - 1;
+#pragma unroll 1
+                    for (int ch = 0; ch < BN / 32; ch++) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_acc + (uint32_t)(sub * BN + ch * 32), r);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = live ? __uint_as_float(r[j]) : 0.0f;
+                        // halving butterfly: 31 shuffles leave lane l with the column sum of column f(l)
+                        int col = 0;
+#pragma unroll
+                        for (int m = 16, h = 16; m >= 1; m >>= 1, h >>= 1) {
+                            const bool up = (lane & m) != 0;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                if (i < h) {
+                                    const float send = up ? v[i] : v[i + h];
+                                    const float keep = up ? v[i + h] : v[i];
+                                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                                }
+                            }
+                            col += up ? h : 0;
+                        }
+                        s_part[(q * 2 + sub) * BN + ch * 32 + col] = v[0];
+                    }
+                }
+                named_bar_sync(1, 128);
+                if (et < BN) {
+                    float s = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) s += s_part[i * BN + et];
+                    s_mean[et] = s / (float)p.n_cells + s_par[et];
+                }
+                named_bar_sync(1, 128);
+                if (et < p.se_r) {
+                    float hsum = p.se_b1[et];
+                    for (int i = 0; i < BN; i++) hsum = fmaf(s_mean[i], p.se_w1[i * p.se_r + et], hsum);
+                    s_hid[et] = fmaxf(hsum, 0.0f);
+                }
+                named_bar_sync(1, 128);
+                if (et < BN) {
+                    float g = p.se_b2[et];
+                    for (int i = 0; i < p.se_r; i++) g = fmaf(s_hid[i], p.se_w2[i * BN + et], g);
+                    s_gate[et] = 1.0f / (1.0f + expf(-g));
+                }
+                named_bar_sync(1, 128);
+            }
+            // ---- output pass
+#pragma unroll 1
+            for (int sub = 0; sub < 2; sub++) {
+                const long long row = (long long)t * TILE_ROWS + sub * 128 + q * 32 + lane;
+                const int pos = (int)(row % p.P_pad);
+                const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
+                const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_acc + (uint32_t)(sub * BN + ch * 32), r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + s_par[ch * 32 + j];
+                    if (p.se) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] *= s_gate[ch * 32 + j];
+                    }
+                    const size_t blk = f32_blk_index(row, ch * 32, BN); // this lane's first piece of the 32x32 block
+                    if (p.res) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            float tt[8];
+                            ldg256(p.res + blk + j * 256, tt);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[8 * j + i] += tt[i];
+                        }
+                    }
+                    if (p.out_raw) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            float tt[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) tt[i] = live ? v[8 * j + i] : 0.0f;
+                            stg256(p.out_raw + blk + j * 256, tt);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 2; o++) {
+                        __nv_bfloat16 *outp = o == 0 ? p.out_a : p.out_b;
+                        if (!outp) continue;
+                        const float *sc = s_par + (1 + 2 * o) * BN + ch * 32, *sh = s_par + (2 + 2 * o) * BN + ch * 32;
+                        uint8_t *op = reinterpret_cast<uint8_t *>(outp + (size_t)row * BN + ch * 32);
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const int c = 16 * j + 2 * i;
+                                const float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
+                                const float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
+                                __nv_bfloat162 hh = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
+                                w[i] = *reinterpret_cast<uint32_t *>(&hh);
+                            }
+                            stg256u(op + j * 32, w);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+} // namespace gaz_conv

@@ -14,12 +14,14 @@
 #include "../../include/gaz_net.h"
 #include "gaz_internal.h"
 #include "gaz_tc.cuh"
+#include "gaz_conv.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdio.h>
 
 using namespace gaz_tc;
+using gaz_conv::f32_blk_index;
 
 #define CKN(x)                                                                                             \
     do {                                                                                                   \
@@ -149,20 +151,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + s_par[ch * 32 + j];
+                const size_t blk = f32_blk_index(row, ch * 32, BN); // blocked fp32 row tensor (gaz_conv.cuh)
                 if (p.res) {
-                    const float4 *rp = reinterpret_cast<const float4 *>(p.res + (size_t)row * BN + ch * 32);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        float4 t = rp[j];
+                        float4 t = *reinterpret_cast<const float4 *>(p.res + blk + (j >> 1) * 256 + (j & 1) * 4);
                         v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                     }
                 }
                 if (p.out_raw) {
-                    float4 *op = reinterpret_cast<float4 *>(p.out_raw + (size_t)row * BN + ch * 32);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
-                        op[j] = live ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(p.out_raw + blk + (j >> 1) * 256 + (j & 1) * 4) =
+                            live ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int o = 0; o < 2; o++) {
@@ -212,61 +214,82 @@ struct StemArgs {
     const float *scale_a, *shift_a;
 };
 
-// one warp per padded row; lane owns Cout/32 consecutive channels
-template <int CPL> __global__ void __launch_bounds__(256) stem_kernel(StemArgs p) {
-    extern __shared__ float s_w[];
-    const int nW = p.K * p.K * p.Cin * p.Cout;
-    for (int i = threadIdx.x; i < nW; i += blockDim.x) s_w[i] = p.w[i];
-    __syncthreads();
+// One CTA per board at a time (state bytes staged in shared memory); a thread owns 4 consecutive output
+// channels with their K*K*Cin x 4 weights in REGISTERS and walks the board's padded rows, so the inner loop is
+// warp-uniform broadcast LDS of the int8 inputs + FMAs; outputs leave as 8/16-byte vectors.
+template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(StemArgs p) {
+    constexpr int TAPS_CIN = K * K * CIN;
+    __shared__ int8_t s_in[1024];
+    const int cpr = p.Cout >> 2;                 // threads per row
+    const int rows_par = blockDim.x / cpr;       // rows processed in parallel
+    const int tc = threadIdx.x % cpr, tr = threadIdx.x / cpr;
+    const int c0 = tc * 4;
+    float4 w[TAPS_CIN];
+#pragma unroll
+    for (int i = 0; i < TAPS_CIN; i++) w[i] = *reinterpret_cast<const float4 *>(p.w + (size_t)i * p.Cout + c0);
+    const float4 bias = *reinterpret_cast<const float4 *>(p.bias + c0);
+    const float4 sc = *reinterpret_cast<const float4 *>(p.scale + c0), sh = *reinterpret_cast<const float4 *>(p.shift + c0);
+    float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), ta = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.out_a) { sa = *reinterpret_cast<const float4 *>(p.scale_a + c0); ta = *reinterpret_cast<const float4 *>(p.shift_a + c0); }
     int cnt = *p.count;
     if (cnt > p.max_count) cnt = p.max_count;
-    const int total_rows = ((cnt * p.P_pad + 127) >> 7) << 7;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kh = p.K >> 1;
-    const int c0 = lane * CPL;
-    for (int row = blockIdx.x * 8 + warp; row < total_rows; row += gridDim.x * 8) {
-        const int b = row / p.P_pad, pos = row - b * p.P_pad;
-        const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
-        const bool live = b < cnt && yy >= 0 && xx < p.W;
-        float acc[CPL];
+    const long long total_rows = ((long long)cnt * p.P_pad + 255) / 256 * 256;
+    const int n_boards_pad = (int)((total_rows + p.P_pad - 1) / p.P_pad);
+    constexpr int kh = K >> 1;
+    const int nin = p.H * p.W * CIN;
+    for (int b = blockIdx.x; b < n_boards_pad; b += gridDim.x) {
+        __syncthreads();
+        if (b < cnt)
+            for (int i = threadIdx.x; i < nin; i += blockDim.x) s_in[i] = p.states[(size_t)b * nin + i];
+        __syncthreads();
+        for (int pos = tr; pos < p.P_pad; pos += rows_par) {
+            const long long row = (long long)b * p.P_pad + pos;
+            if (row >= total_rows) break;
+            const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
+            const bool live = b < cnt && yy >= 0 && xx < p.W;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
 #pragma unroll
-        for (int j = 0; j < CPL; j++) acc[j] = 0.0f;
-        if (live) {
-            const int8_t *st = p.states + (size_t)b * p.H * p.W * p.Cin;
-            for (int ky = 0; ky < p.K; ky++) {
-                const int iy = yy + ky - kh;
-                if (iy < 0 || iy >= p.H) continue;
-                for (int kx = 0; kx < p.K; kx++) {
-                    const int ix = xx + kx - kh;
-                    if (ix < 0 || ix >= p.W) continue;
-                    const int8_t *sp = st + (iy * p.W + ix) * p.Cin;
-                    const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * p.Cout + c0;
-                    for (int ci = 0; ci < p.Cin; ci++) {
-                        const int s = sp[ci];
-                        if (s == 0) continue;
-                        const float fs = (float)s;
+                for (int ky = 0; ky < K; ky++) {
+                    const int iy = yy + ky - kh;
 #pragma unroll
-                        for (int j = 0; j < CPL; j++) acc[j] = fmaf(fs, wp[ci * p.Cout + j], acc[j]);
+                    for (int kx = 0; kx < K; kx++) {
+                        const int ix = xx + kx - kh;
+                        const bool inb = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        const int8_t *sp = s_in + (inb ? (iy * p.W + ix) * CIN : 0);
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ci++) {
+                            const int sv = inb ? (int)sp[ci] : 0;
+                            if (sv != 0) { // warp-uniform: the whole warp works on one row
+                                const float fs = (float)sv;
+                                const float4 ww = w[(ky * K + kx) * CIN + ci];
+                                acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
+                                acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
+                            }
+                        }
                     }
                 }
             }
-        }
-        float v[CPL];
+            float v[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+            const float sav[4] = {sa.x, sa.y, sa.z, sa.w}, tav[4] = {ta.x, ta.y, ta.z, ta.w};
+            float a[4];
 #pragma unroll
-        for (int j = 0; j < CPL; j++) {
-            float t = acc[j] + p.bias[c0 + j];
-            t = fmaf(p.scale[c0 + j], t, p.shift[c0 + j]);
-            t = p.act == GAZ_ACT_RELU ? fmaxf(t, 0.0f) : (p.act == GAZ_ACT_GELU ? gelu_exact(t) : t);
-            v[j] = live ? t : 0.0f;
-        }
-        const size_t o = (size_t)row * p.Cout + c0;
-#pragma unroll
-        for (int j = 0; j < CPL; j++) {
-            if (p.out_raw) p.out_raw[o + j] = v[j];
-            if (p.out_q) p.out_q[o + j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < 4; j++) {
+                float t = fmaf(scv[j], v[j], shv[j]);
+                t = p.act == GAZ_ACT_RELU ? fmaxf(t, 0.0f) : (p.act == GAZ_ACT_GELU ? gelu_exact(t) : t);
+                v[j] = live ? t : 0.0f;
+                a[j] = live ? fmaxf(fmaf(sav[j], t, tav[j]), 0.0f) : 0.0f;
+            }
+            const size_t o = (size_t)row * p.Cout + c0;
+            if (p.out_raw) *reinterpret_cast<float4 *>(p.out_raw + f32_blk_index(row, c0, p.Cout)) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.out_q) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2 *>(p.out_q + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+            }
             if (p.out_a) {
-                float a = fmaxf(fmaf(p.scale_a[c0 + j], v[j], p.shift_a[c0 + j]), 0.0f);
-                p.out_a[o + j] = __float2bfloat16_rn(live ? a : 0.0f);
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
+                *reinterpret_cast<uint2 *>(p.out_a + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
             }
         }
     }
@@ -283,17 +306,18 @@ struct SeArgs {
     const float *scale_a, *shift_a, *scale_b, *shift_b;
 };
 
-// Net/SE/SE_Block.py:15-23 + the block's skip add; one CTA per board, thread = channel
+// Net/SE/SE_Block.py:15-23 + the block's skip add; one CTA per board, thread = channel.  Fallback for geometries
+// where a board is not one 256-row tile (the fused epilogue of conv_board_kernel handles Gomoku).
 __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
     __shared__ float s_mean[128], s_hid[64], s_gate[128];
     int cnt = *p.count;
     if (cnt > p.max_count) cnt = p.max_count;
     const int c = threadIdx.x;
     for (int b = blockIdx.x; b < cnt; b += gridDim.x) {
-        const size_t base = (size_t)b * p.P_pad * p.C;
+        const long long row0 = (long long)b * p.P_pad;
         float s = 0.0f;
         for (int y = 0; y < p.H; y++)
-            for (int x = 0; x < p.W; x++) s += p.c2[base + (size_t)((y + 1) * p.Wp + x) * p.C + c];
+            for (int x = 0; x < p.W; x++) s += p.c2[f32_blk_index(row0 + (y + 1) * p.Wp + x, c, p.C)];
         s_mean[c] = s / (float)(p.H * p.W);
         __syncthreads();
         if (c < p.R) {
@@ -311,9 +335,10 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
         for (int pos = 0; pos < p.P_pad; pos++) {
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
             const bool live = yy != 0 && xx != p.Wp - 1;
-            const size_t o = base + (size_t)pos * p.C + c;
-            float v = live ? fmaf(p.c2[o], gate, p.res[o]) : 0.0f;
-            if (p.out_raw) p.out_raw[o] = v;
+            const size_t ob = f32_blk_index(row0 + pos, c, p.C);
+            const size_t o = (size_t)(row0 + pos) * p.C + c;
+            float v = live ? fmaf(p.c2[ob], gate, p.res[ob]) : 0.0f;
+            if (p.out_raw) p.out_raw[ob] = v;
             if (p.out_a) p.out_a[o] = __float2bfloat16_rn(live ? fmaxf(fmaf(p.scale_a[c], v, p.shift_a[c]), 0.0f) : 0.0f);
             if (p.out_b) p.out_b[o] = __float2bfloat16_rn(live ? fmaxf(fmaf(p.scale_b[c], v, p.shift_b[c]), 0.0f) : 0.0f);
         }
@@ -355,9 +380,8 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
                 if (r < 0 || r >= p.in_rows) continue;
                 const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * p.Cout;
                 if (p.in_f32) {
-                    const float *ip = (const float *)p.in + r * p.Cin;
                     for (int ci = 0; ci < p.Cin; ci++) {
-                        const float a = ip[ci];
+                        const float a = ((const float *)p.in)[f32_blk_index(r, ci, p.Cin)];
 #pragma unroll
                         for (int j = 0; j < 16; j++) if (j < p.Cout) acc[j] = fmaf(a, wp[ci * p.Cout + j], acc[j]);
                     }
@@ -373,6 +397,76 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
         float *op = p.out + (size_t)b * ncell * p.Cout + (size_t)cell * p.Cout;
 #pragma unroll
         for (int j = 0; j < 16; j++) if (j < p.Cout) op[j] = acc[j];
+    }
+}
+
+// Head convolutions with few taps*channels: one warp per output cell, lane = input channel (CPL channels per
+// lane, coalesced row loads), weights in registers, COUT partial sums folded across the warp with a halving
+// butterfly (COUT-1 + log2(32/COUT) shuffles instead of 5*COUT).
+template <int CPL, int COUT, int K, bool IN_F32>
+__global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
+    constexpr int TAPS = K * K, kh = K >> 1;
+    const int lane = threadIdx.x & 31;
+    float w[TAPS][CPL][COUT];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+#pragma unroll
+        for (int j = 0; j < CPL; j++)
+#pragma unroll
+            for (int co = 0; co < COUT; co++) w[t][j][co] = p.w[(size_t)(t * p.Cin + lane + 32 * j) * COUT + co];
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int ncell = p.H * p.W;
+    const long long total = (long long)cnt * ncell;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long idx = warp0; idx < total; idx += nwarps) {
+        const int b = (int)(idx / ncell), cell = (int)(idx - (long long)b * ncell);
+        const int y = cell / p.W, x = cell - y * p.W;
+        const long long r0 = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; co++) acc[co] = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < K; ky++)
+#pragma unroll
+            for (int kx = 0; kx < K; kx++) {
+                const long long r = r0 + (ky - kh) * p.Wp + (kx - kh);
+                if (r < 0 || r >= p.in_rows) continue;
+#pragma unroll
+                for (int j = 0; j < CPL; j++) {
+                    float a;
+                    if (IN_F32) a = ((const float *)p.in)[f32_blk_index(r, lane + 32 * j, p.Cin)];
+                    else a = __bfloat162float(((const __nv_bfloat16 *)p.in)[r * p.Cin + lane + 32 * j]);
+#pragma unroll
+                    for (int co = 0; co < COUT; co++) acc[co] = fmaf(a, w[ky * K + kx][j][co], acc[co]);
+                }
+            }
+        // halving butterfly: after the step with mask m a lane keeps the half of its values selected by (lane & m)
+        int n = COUT;
+        int co_base = 0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            if (n > 1) {
+                const int h = n >> 1;
+                const bool up = (lane & m) != 0;
+#pragma unroll
+                for (int i = 0; i < COUT / 2; i++) {
+                    if (i < h) {
+                        const float send = up ? acc[i] : acc[i + h];
+                        const float keep = up ? acc[i + h] : acc[i];
+                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                    }
+                }
+                co_base += up ? h : 0;
+                n = h;
+            } else {
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], m);
+            }
+        }
+        // lanes whose low log2(32/COUT) bits are zero hold output channel co_base
+        constexpr int REP = 32 / COUT;
+        if ((lane & (REP - 1)) == 0) p.out[(size_t)idx * COUT + co_base] = acc[0] + p.bias[co_base];
     }
 }
 
@@ -497,7 +591,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 struct NetBuf { int kind, width; void *ptr; size_t bytes; };
 struct NetOp {
     gaz_net_op d;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB; // v1: 128-row activation box
+    CUtensorMap tmA2;     // v2 (conv_board_kernel): 152-row half-slab box
+    int fused_se;         // this conv carries the following SE op in its epilogue
+    gaz_net_op se;        // ... whose parameters are here
+    int skip;             // SE op folded into the previous conv
 };
 
 struct gaz_net {
@@ -518,6 +616,9 @@ struct gaz_net {
     int logits_buf; // id of the flat buffer holding the policy logits
     // profiling of the tcgen05 conv launches
     int profile;
+    int conv_v1;           // GAZ_CONV_V1=1: use the v1 per-tap kernel (A/B comparison)
+    int base_offset_mode;  // GAZ_DESC_BASE_OFFSET (default 0, see gaz_conv.cuh)
+    int fuse_se;           // GAZ_FUSE_SE (default 1)
     std::vector<cudaEvent_t> ev;
     size_t ev_used;
     std::vector<int> ev_op;
@@ -545,6 +646,17 @@ template <int BN> static int launch_conv(gaz_net *n, NetOp &op, const ConvArgs &
     return 0;
 }
 
+template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_conv::BoardConvArgs &a, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CKN(cudaFuncSetAttribute(gaz_conv::conv_board_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gaz_conv::BoardCfg<BN>::SMEM));
+        attr_set = true;
+    }
+    gaz_conv::conv_board_kernel<BN><<<n->n_sm, 256, gaz_conv::BoardCfg<BN>::SMEM, s>>>(op.tmA2, op.tmB, a);
+    return 0;
+}
+
 static const float *wfp(gaz_net *n, int64_t off) { return off < 0 ? nullptr : n->wf + off; }
 
 static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, float *policy, float *value, cudaStream_t s) {
@@ -561,32 +673,55 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.scale = wfp(n, d.scale_b); a.shift = wfp(n, d.shift_b);
             a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
             a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
-            size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
-            int grid = n->n_sm * 8;
-            if (d.cout == 256) stem_kernel<8><<<grid, 256, sm, s>>>(a);
-            else if (d.cout == 128) stem_kernel<4><<<grid, 256, sm, s>>>(a);
-            else if (d.cout == 64) stem_kernel<2><<<grid, 256, sm, s>>>(a);
-            else return gaz_fail("stem cout %d unsupported", d.cout);
+            const int tc = d.ksize * d.ksize * d.cin;
+            if (d.cout % 4 != 0 || 256 % (d.cout / 4) != 0 || d.cin > 4 || n->H * n->W * d.cin > 1024)
+                return gaz_fail("stem shape unsupported (cin %d cout %d)", d.cin, d.cout);
+            int grid = n->n_sm * 4;
+            (void)tc;
+            if (d.ksize == 3 && d.cin == 2) stem_kernel<3, 2><<<grid, 256, 0, s>>>(a);        // Gomoku
+            else if (d.ksize == 3 && d.cin == 4) stem_kernel<3, 4><<<grid, 256, 0, s>>>(a);   // Connect4
+            else if (d.ksize == 5 && d.cin == 2) stem_kernel<5, 2><<<grid, 256, 0, s>>>(a);   // TicTacToe
+            else return gaz_fail("stem k=%d cin=%d unsupported", d.ksize, d.cin);
             break;
         }
         case GAZ_OP_CONV_TC: {
-            ConvArgs a;
-            a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
-            a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64;
-            a.bias = wfp(n, d.bias); a.res = (const float *)buf(d.res_buf); a.out_raw = (float *)buf(d.out_raw);
-            a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
-            a.out_b = (__nv_bfloat16 *)buf(d.out_b); a.scale_b = wfp(n, d.scale_b); a.shift_b = wfp(n, d.shift_b);
             if (n->profile && n->ev_used + 2 <= n->ev.size()) {
                 n->ev_op.push_back((int)oi);
                 CKN(cudaEventRecord(n->ev[n->ev_used++], s));
             }
-            int rc = d.cout == 128 ? launch_conv<128>(n, op, a, s) : d.cout == 64 ? launch_conv<64>(n, op, a, s)
+            int rc;
+            if (n->conv_v1) {
+                ConvArgs a;
+                a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
+                a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64;
+                a.bias = wfp(n, d.bias); a.res = (const float *)buf(d.res_buf); a.out_raw = (float *)buf(d.out_raw);
+                a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
+                a.out_b = (__nv_bfloat16 *)buf(d.out_b); a.scale_b = wfp(n, d.scale_b); a.shift_b = wfp(n, d.shift_b);
+                rc = d.cout == 128 ? launch_conv<128>(n, op, a, s) : d.cout == 64 ? launch_conv<64>(n, op, a, s)
                      : d.cout == 32 ? launch_conv<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
+            } else {
+                gaz_conv::BoardConvArgs a;
+                memset(&a, 0, sizeof a);
+                a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
+                a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->base_offset_mode;
+                a.bias = wfp(n, d.bias);
+                const gaz_net_op &o = op.fused_se ? op.se : d; // outputs / residual of the fused SE op
+                a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
+                a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.scale_a = wfp(n, o.scale_a); a.shift_a = wfp(n, o.shift_a);
+                a.out_b = (__nv_bfloat16 *)buf(o.out_b); a.scale_b = wfp(n, o.scale_b); a.shift_b = wfp(n, o.shift_b);
+                if (op.fused_se) {
+                    a.se = 1; a.se_r = op.se.cin; a.n_cells = n->H * n->W;
+                    a.se_w1 = wfp(n, op.se.w2); a.se_b1 = wfp(n, op.se.bias2); a.se_w2 = wfp(n, op.se.w3); a.se_b2 = wfp(n, op.se.bias3);
+                }
+                rc = d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
+                     : d.cout == 32 ? launch_conv_board<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
+            }
             if (rc != 0) return rc;
             if (n->profile && (n->ev_used & 1)) CKN(cudaEventRecord(n->ev[n->ev_used++], s));
             break;
         }
         case GAZ_OP_SE: {
+            if (op.skip) break;
             SeArgs a;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.C = d.cout; a.R = d.cin;
             a.P_pad = n->P_pad; a.Wp = n->Wp;
@@ -604,6 +739,20 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32;
             a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
             size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
+            const int cpl = d.cin / 32;
+            const int g2 = n->n_sm * 8;
+            bool done = true;
+#define HC(CPL_, CO_, K_) \
+    (a.in_f32 ? (void)(headconv_warp_kernel<CPL_, CO_, K_, true><<<g2, 256, 0, s>>>(a)) \
+              : (void)(headconv_warp_kernel<CPL_, CO_, K_, false><<<g2, 256, 0, s>>>(a)))
+            if (d.cin % 32 != 0) done = false;
+            else if (cpl == 1 && d.cout == 8 && d.ksize == 3) HC(1, 8, 3);
+            else if (cpl == 1 && d.cout == 4 && d.ksize == 1) HC(1, 4, 1);
+            else if (cpl == 2 && d.cout == 8 && d.ksize == 1) HC(2, 8, 1);
+            else if (cpl == 2 && d.cout == 4 && d.ksize == 1) HC(2, 4, 1);
+            else done = false;
+#undef HC
+            if (done) break;
             if (d.cout > 16 || sm > 48 * 1024) return gaz_fail("headconv shape unsupported (cout %d, %zu B weights)", d.cout, sm);
             headconv_kernel<<<n->n_sm * 16, 128, sm, s>>>(a);
             break;
@@ -658,8 +807,14 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     n->max_batch = desc->max_batch;
     n->policy_mode = desc->policy_mode;
     n->device = desc->device;
-    n->rows_alloc = (((long long)n->max_batch * n->P_pad + 127) / 128) * 128;
+    n->rows_alloc = (((long long)n->max_batch * n->P_pad + 255) / 256) * 256;
     n->bytes = 0;
+    {
+        const char *e1 = getenv("GAZ_CONV_V1"), *e2 = getenv("GAZ_DESC_BASE_OFFSET"), *e3 = getenv("GAZ_FUSE_SE");
+        n->conv_v1 = e1 && atoi(e1) != 0;
+        n->base_offset_mode = e2 ? atoi(e2) : 0;
+        n->fuse_se = e3 ? atoi(e3) : 1;
+    }
     n->profile = 0;
     n->ev_used = 0;
     n->logits_buf = -1;
@@ -700,6 +855,10 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.d = desc->ops[i];
         memset(&op.tmA, 0, sizeof op.tmA);
         memset(&op.tmB, 0, sizeof op.tmB);
+        memset(&op.tmA2, 0, sizeof op.tmA2);
+        op.fused_se = 0;
+        op.skip = 0;
+        memset(&op.se, 0, sizeof op.se);
         const gaz_net_op &d = op.d;
         if (d.type == GAZ_OP_CONV_TC) {
             if (d.cin % 64 != 0 || (d.cout != 32 && d.cout != 64 && d.cout != 128) || (d.ksize != 1 && d.ksize != 3)) {
@@ -711,13 +870,24 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
                 gaz_net_destroy(n);
                 return gaz_fail("conv_tc op %d: input buffer must be bf16 rows of width cin", i);
             }
-            if (make_map(enc, &op.tmA, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, 128) != 0 ||
+            if (make_map(enc, &op.tmA2, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, gaz_conv::SLAB_BOX_ROWS) != 0 ||
+                make_map(enc, &op.tmA, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, 128) != 0 ||
                 make_map(enc, &op.tmB, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout) != 0) {
                 gaz_net_destroy(n);
                 return -1;
             }
         }
         if (d.type == GAZ_OP_POLICY_OUT) n->logits_buf = d.in_buf;
+        // fold an SE op into the epilogue of the convolution that feeds it (tile == board geometries only)
+        if (d.type == GAZ_OP_SE && !n->conv_v1 && n->fuse_se && n->P_pad == gaz_conv::TILE_ROWS && !n->ops.empty()) {
+            NetOp &prev = n->ops.back();
+            if (prev.d.type == GAZ_OP_CONV_TC && prev.d.out_raw == d.in_buf && prev.d.out_a < 0 && prev.d.out_b < 0 &&
+                prev.d.res_buf < 0 && prev.d.cout == d.cout && d.cout <= 128 && d.cin <= d.cout) {
+                prev.fused_se = 1;
+                prev.se = d;
+                op.skip = 1;
+            }
+        }
         n->ops.push_back(op);
     }
     CKN(cudaDeviceSynchronize());
