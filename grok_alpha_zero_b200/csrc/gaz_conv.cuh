@@ -10,8 +10,9 @@
 //     to (addr >> 7) & 7 gives wrong results), so A is written to SMEM once, not 9x;
 //   * every weight tile (tap, K-block) is used by both 128-row halves of the tile (8 MMAs per 16 KB tile);
 //   * TMEM holds 2 stages x 2 accumulators (4 x BN columns) so the epilogue of tile i overlaps the MMAs of i+1.
-// Warp roles (256 threads): 0 = slab TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+TMEM alloc),
-// 3 = idle, 4..7 = epilogue (TMEM lane quarter = warp & 3).
+// Warp roles (384 threads): 0 = slab TMA producer, 1 = weight TMA producer, 2 = MMA issuer (+TMEM alloc),
+// 3 = idle, 4..11 = epilogue (TMEM lane quarter = warp & 3, 128-row half = (warp - 4) >> 2): two epilogue warps
+// per scheduler so their TMEM / global / shuffle latencies overlap.
 // Epilogue modes: plain (bias [+ fp32 residual] -> fp32 stream and/or relu(BN(.)) bf16 operands) and fused
 // Squeeze-Excitation (Net/SE/SE_Block.py:15-23 + the block's skip add, Net/ResNet/ResNet_Block.py:27-41):
 // pass 1 folds the accumulators into per-channel board means (halving butterfly over the 32 rows of a warp),
@@ -54,7 +55,7 @@ __device__ __forceinline__ void stg256u(void *p, const uint32_t (&r)[8]) {
 // mode 1 (debug) fills it with the phase of the start address.
 __device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, int base_offset_mode) {
     uint64_t d = umma_desc_sw128(smem_addr);
-    if (base_offset_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+    if (base_offset_mode & 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
     return d;
 }
 
@@ -63,14 +64,15 @@ struct BoardConvArgs {
     int max_count;
     int P_pad, Wp;
     int taps, kpt;            // filter taps (1 or 9), 64-channel K-blocks per tap
-    int base_offset_mode;     // 0 = base offset field zero (correct on B200), 1 = phase of the start address (debug)
-    const float *bias;
+    int base_offset_mode;     // debug bits: 4 = skip the output stores (timing experiment)
+    // per-channel parameters travel in the kernel-argument (constant) bank: bias | scale_a | shift_a | scale_b |
+    // shift_b, 128 floats each.  The epilogue reads them with uniform LDC, which keeps them off the shared-memory
+    // port that the MMAs saturate (a broadcast LDS per value cost 25 % of the port in v2.0, ncu r01).
+    float par[5 * 128];
     const float *res;         // blocked fp32 residual stream (optional)
     float *out_raw;           // blocked fp32 output (optional)
     __nv_bfloat16 *out_a;     // relu(scale_a * v + shift_a) as bf16 rows (optional)
-    const float *scale_a, *shift_a;
     __nv_bfloat16 *out_b;
-    const float *scale_b, *shift_b;
     // fused Squeeze-Excitation (tile == board, P_pad == 256): dense1 [C][R], dense2 [R][C]
     int se, se_r, n_cells;
     const float *se_w1, *se_b1, *se_w2, *se_b2;
@@ -82,15 +84,15 @@ constexpr int SLAB_ROWS = TILE_ROWS + 2 * HALO; // 304 rows = 2 TMA boxes of 152
 constexpr int SLAB_BYTES = SLAB_ROWS * 128;     // 38912 = 38 * 1024
 constexpr int SLAB_BOX_ROWS = SLAB_ROWS / 2;
 
-template <int BN> struct BoardCfg {
+template <int BN, bool PAIR> struct BoardCfg {
     static constexpr int NSLAB = 4;
-    static constexpr int NB = 4;
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int NB = PAIR ? 6 : 4;
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN; // weight rows (output channels) this CTA stages per tile
+    static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;
-    static constexpr int PAR_FLOATS = 5 * BN;
-    static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [4 warps][2 halves][BN], mean, hidden, gate
+    static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [8 warps][BN], mean, hidden, gate
     static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                                (PAR_FLOATS + SE_FLOATS) * 4;
+                                SE_FLOATS * 4;
 };
 
 struct Ring {
@@ -104,10 +106,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
-conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, BoardConvArgs p) {
-    using Cfg = BoardCfg<BN>;
+// PAIR = true: two CTAs of a cluster (one TPC) issue every MMA jointly (cta_group::2, M = 256 = one 128-row half of
+// each CTA's own board tile); each CTA stages only half of every weight tile, which takes the shared-memory
+// operand traffic per CTA from 8 KB to 6 KB per 64-cycle MMA - below the 128 B/clk port limit that caps the
+// single-CTA form near 55 % of the tensor pipe (ncu r01).  Everything else (slab, TMEM, epilogue) stays per CTA.
+template <int BN, bool PAIR>
+__global__ void __launch_bounds__(384, 1)
+conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ BoardConvArgs p) {
+    using Cfg = BoardCfg<BN, PAIR>;
     constexpr int NSLAB = Cfg::NSLAB, NB = Cfg::NB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -117,47 +124,51 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t *a_full = bars, *a_empty = bars + NSLAB, *b_full = bars + 2 * NSLAB, *b_empty = bars + 2 * NSLAB + NB;
     uint64_t *tfull = bars + 2 * NSLAB + 2 * NB, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
-    float *s_par = (float *)(bars + 32); // bias | scale_a | shift_a | scale_b | shift_b
-    float *s_se = s_par + Cfg::PAR_FLOATS;
+    float *s_se = (float *)(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0; // 0 = leader (issues the MMAs, owns the full/tempty barriers)
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     int cnt = *p.count;
     if (cnt > p.max_count) cnt = p.max_count;
     const long long valid_rows = (long long)cnt * p.P_pad;
     const int n_tiles = (int)((valid_rows + TILE_ROWS - 1) / TILE_ROWS);
+    // loop index space: single CTA = tiles; pair = pair-tiles (tile 2*pt + rank; the last one may be a dummy)
+    const int n_loop = PAIR ? (n_tiles + 1) / 2 : n_tiles;
 
-    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-        s_par[i] = p.bias ? p.bias[i] : 0.0f;
-        s_par[BN + i] = p.scale_a ? p.scale_a[i] : 1.0f;
-        s_par[2 * BN + i] = p.shift_a ? p.shift_a[i] : 0.0f;
-        s_par[3 * BN + i] = p.scale_b ? p.scale_b[i] : 1.0f;
-        s_par[4 * BN + i] = p.shift_b ? p.shift_b[i] : 0.0f;
-    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLAB; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], PAIR ? 16 : 8); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg::TMEM_COLS); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) { // ---------------- activation-slab TMA producer
             Ring r;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int lt = tile0; lt < n_loop; lt += tile_step) {
+                const int t = PAIR ? 2 * lt + rank : lt;
                 const int row0 = t * TILE_ROWS - HALO;
                 for (int kc = 0; kc < p.kpt; kc++) {
                     mbar_wait(&a_empty[r.idx], r.phase ^ 1);
-                    mbar_expect_tx(&a_full[r.idx], SLAB_BYTES);
                     uint8_t *dst = sA + r.idx * SLAB_BYTES;
-                    tma_load_2d(dst, &tmA, &a_full[r.idx], kc * 64, row0);
-                    tma_load_2d(dst + SLAB_BYTES / 2, &tmA, &a_full[r.idx], kc * 64, row0 + SLAB_BOX_ROWS);
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(&a_full[r.idx], 2 * SLAB_BYTES);
+                        tma_load_2d_pair(dst, &tmA, &a_full[r.idx], kc * 64, row0);
+                        tma_load_2d_pair(dst + SLAB_BYTES / 2, &tmA, &a_full[r.idx], kc * 64, row0 + SLAB_BOX_ROWS);
+                    } else {
+                        mbar_expect_tx(&a_full[r.idx], SLAB_BYTES);
+                        tma_load_2d(dst, &tmA, &a_full[r.idx], kc * 64, row0);
+                        tma_load_2d(dst + SLAB_BYTES / 2, &tmA, &a_full[r.idx], kc * 64, row0 + SLAB_BOX_ROWS);
+                    }
                     r.advance(NSLAB);
                 }
             }
@@ -166,185 +177,232 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) { // ---------------- weight-tile TMA producer: order (K-block, tap)
             Ring r;
             const int cin = p.kpt * 64;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+            for (int lt = tile0; lt < n_loop; lt += tile_step)
                 for (int kc = 0; kc < p.kpt; kc++)
                     for (int tap = 0; tap < p.taps; tap++) {
                         mbar_wait(&b_empty[r.idx], r.phase ^ 1);
-                        mbar_expect_tx(&b_full[r.idx], Cfg::B_BYTES);
-                        tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, 0);
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(&b_full[r.idx], 2 * Cfg::B_BYTES);
+                            tma_load_2d_pair(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, rank * Cfg::B_ROWS);
+                        } else {
+                            mbar_expect_tx(&b_full[r.idx], Cfg::B_BYTES);
+                            tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, 0);
+                        }
                         r.advance(NB);
                     }
         }
     } else if (warp == 2) {
-        if (lane == 0) { // ---------------- MMA issuer
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+        if (rank == 0) { // ---------------- MMA issuer: whole warp, uniform control flow, one elected lane per instruction
+            constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN);
             Ring ra, rb;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int lt = tile0; lt < n_loop; lt += tile_step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
                 for (int kc = 0; kc < p.kpt; kc++) {
                     mbar_wait(&a_full[ra.idx], ra.phase);
-                    const uint32_t slab = smem_u32(sA + ra.idx * SLAB_BYTES);
+                    const uint32_t slab_lo = umma_desc_lo(smem_u32(sA + ra.idx * SLAB_BYTES) + (uint32_t)(HALO * 128));
+                    int dy = -1, dx = -1; // tap = (dy + 1) * 3 + (dx + 1)
                     for (int tap = 0; tap < p.taps; tap++) {
                         mbar_wait(&b_full[rb.idx], rb.phase);
                         tc_fence_after();
-                        int shift = 0;
-                        if (p.taps == 9) shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
-                        const uint32_t b_addr = smem_u32(sB + rb.idx * Cfg::B_BYTES);
+                        const int shift = p.taps == 9 ? dy * p.Wp + dx : 0;
+                        const uint32_t b_lo = umma_desc_lo(smem_u32(sB + rb.idx * Cfg::B_BYTES));
+                        const uint32_t a_lo = slab_lo + (uint32_t)(shift * 8); // 128 B per row = 8 descriptor units
+                        const uint32_t accf = (uint32_t)((kc | tap) != 0); // the first MMA into each accumulator overwrites
 #pragma unroll
                         for (int sub = 0; sub < 2; sub++) {
-                            const uint32_t a_addr = slab + (uint32_t)((HALO + sub * 128 + shift) * 128);
 #pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                umma_bf16(d0 + (uint32_t)(sub * BN), umma_desc_sw128_shifted(a_addr + k * 32, p.base_offset_mode),
-                                          umma_desc_sw128(b_addr + k * 32), idesc, (uint32_t)((kc | tap | k) != 0));
+                            for (int k = 0; k < 4; k++) {
+                                umma_bf16_elect<PAIR>(d0 + (uint32_t)(sub * BN), a_lo + (uint32_t)(sub * 128 * 8 + k * 2),
+                                                      b_lo + (uint32_t)(k * 2), idesc, k == 0 ? accf : 1u);
+                            }
                         }
-                        umma_commit(&b_empty[rb.idx]);
+                        umma_commit_elect<PAIR>(&b_empty[rb.idx]);
                         rb.advance(NB);
+                        if (++dx == 2) { dx = -1; dy++; }
                     }
-                    umma_commit(&a_empty[ra.idx]);
+                    umma_commit_elect<PAIR>(&a_empty[ra.idx]);
                     ra.advance(NSLAB);
                 }
-                umma_commit(&tfull[acc]);
+                umma_commit_elect<PAIR>(&tfull[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) { // ---------------- epilogue warps (TMEM lane quarter q)
-        const int q = warp & 3;
-        const int et = threadIdx.x - 128; // 0..127
+    } else if (warp >= 4) { // ---------------- epilogue warps: TMEM lane quarter q, 128-row half `sub`
+        const int q = warp & 3, sub = (warp - 4) >> 2;
+        const int et = threadIdx.x - 128; // 0..255
         float *s_part = s_se, *s_mean = s_se + 8 * BN, *s_hid = s_mean + BN, *s_gate = s_hid + BN;
+        constexpr int NCH = BN / 32;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int lt = tile0; lt < n_loop; lt += tile_step) {
+            const int t = PAIR ? 2 * lt + rank : lt;
+            if (t >= n_tiles) { // dummy half of the last pair-tile: keep the barrier phases in step, touch nothing
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+            const long long row = (long long)t * TILE_ROWS + sub * 128 + q * 32 + lane;
+            const int pos = (int)(row % p.P_pad);
+            const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
+            const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
+            float rnext[32]; // residual of the first output chunk: issued before the accumulator is even ready
+            if (p.res) {
+#pragma unroll 1
+                for (int ch = 1; ch < NCH; ch++) { // pull the rest of this row's residual into L2 meanwhile
+                    const float *pp = p.res + f32_blk_index(row, ch * 32, BN);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + j * 256));
+                }
+                const size_t blk0 = f32_blk_index(row, 0, BN);
+#pragma unroll
+                for (int j = 0; j < 4; j++) ldg256(p.res + blk0 + j * 256, *reinterpret_cast<float(*)[8]>(&rnext[8 * j]));
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN);
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + sub) * BN);
             if (p.se) {
-                // ---- pass 1: per-channel sums over the board's live cells
+                // ---- pass 1: per-channel sums over the board's live cells (tile == board)
 #pragma unroll 1
-                for (int sub = 0; sub < 2; sub++) {
-                    const int pos = sub * 128 + q * 32 + lane; // tile == board
-                    const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-                    const bool live = yy != 0 && xx != p.Wp - 1;
-#pragma unroll 1
-                    for (int ch = 0; ch < BN / 32; ch++) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(t_acc + (uint32_t)(sub * BN + ch * 32), r);
-                        tmem_ld_wait();
-                        float v[32];
+                for (int ch = 0; ch < NCH; ch++) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_acc + (uint32_t)(ch * 32), r);
+                    tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = live ? __uint_as_float(r[j]) : 0.0f;
-                        // halving butterfly: 31 shuffles leave lane l with the column sum of column f(l)
-                        int col = 0;
+                    for (int j = 0; j < 32; j++) v[j] = live ? __uint_as_float(r[j]) : 0.0f;
+                    // halving butterfly: 31 shuffles leave lane l with the column sum of column f(l)
+                    int col = 0;
 #pragma unroll
-                        for (int m = 16, h = 16; m >= 1; m >>= 1, h >>= 1) {
-                            const bool up = (lane & m) != 0;
+                    for (int m = 16, h = 16; m >= 1; m >>= 1, h >>= 1) {
+                        const bool up = (lane & m) != 0;
 #pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                if (i < h) {
-                                    const float send = up ? v[i] : v[i + h];
-                                    const float keep = up ? v[i + h] : v[i];
-                                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-                                }
+                        for (int i = 0; i < 16; i++) {
+                            if (i < h) {
+                                const float send = up ? v[i] : v[i + h];
+                                const float keep = up ? v[i + h] : v[i];
+                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
                             }
-                            col += up ? h : 0;
                         }
-                        s_part[(q * 2 + sub) * BN + ch * 32 + col] = v[0];
+                        col += up ? h : 0;
                     }
+                    s_part[(sub * 4 + q) * BN + ch * 32 + col] = v[0];
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
                 if (et < BN) {
                     float s = 0.0f;
 #pragma unroll
                     for (int i = 0; i < 8; i++) s += s_part[i * BN + et];
-                    s_mean[et] = s / (float)p.n_cells + s_par[et];
+                    s_mean[et] = s / (float)p.n_cells + p.par[et];
                 }
-                named_bar_sync(1, 128);
-                if (et < p.se_r) {
-                    float hsum = p.se_b1[et];
-                    for (int i = 0; i < BN; i++) hsum = fmaf(s_mean[i], p.se_w1[i * p.se_r + et], hsum);
-                    s_hid[et] = fmaxf(hsum, 0.0f);
+                named_bar_sync(1, 256);
+                if (et < p.se_r) { // 4 independent accumulators hide the FMA / load latency of the 128-long dot product
+                    float h0 = p.se_b1[et], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+                    const float *w1 = p.se_w1 + et;
+#pragma unroll 8
+                    for (int i = 0; i < BN; i += 4) {
+                        h0 = fmaf(s_mean[i], w1[(i) * p.se_r], h0);
+                        h1 = fmaf(s_mean[i + 1], w1[(i + 1) * p.se_r], h1);
+                        h2 = fmaf(s_mean[i + 2], w1[(i + 2) * p.se_r], h2);
+                        h3 = fmaf(s_mean[i + 3], w1[(i + 3) * p.se_r], h3);
+                    }
+                    s_hid[et] = fmaxf((h0 + h1) + (h2 + h3), 0.0f);
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
                 if (et < BN) {
-                    float g = p.se_b2[et];
-                    for (int i = 0; i < p.se_r; i++) g = fmaf(s_hid[i], p.se_w2[i * BN + et], g);
-                    s_gate[et] = 1.0f / (1.0f + expf(-g));
+                    float g0 = p.se_b2[et], g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+                    const float *w2 = p.se_w2 + et;
+#pragma unroll 8
+                    for (int i = 0; i < p.se_r; i += 4) {
+                        g0 = fmaf(s_hid[i], w2[(i) * BN], g0);
+                        g1 = fmaf(s_hid[i + 1], w2[(i + 1) * BN], g1);
+                        g2 = fmaf(s_hid[i + 2], w2[(i + 2) * BN], g2);
+                        g3 = fmaf(s_hid[i + 3], w2[(i + 3) * BN], g3);
+                    }
+                    s_gate[et] = 1.0f / (1.0f + expf(-((g0 + g1) + (g2 + g3))));
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
             }
-            // ---- output pass
+            // ---- output pass over the 32-column chunks of this warp's 32 rows; the residual of chunk i+1 is
+            // loaded while chunk i is processed (register double buffer)
 #pragma unroll 1
-            for (int sub = 0; sub < 2; sub++) {
-                const long long row = (long long)t * TILE_ROWS + sub * 128 + q * 32 + lane;
-                const int pos = (int)(row % p.P_pad);
-                const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-                const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch++) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_acc + (uint32_t)(sub * BN + ch * 32), r);
-                    tmem_ld_wait();
-                    float v[32];
+            for (int ch = 0; ch < NCH; ch++) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_acc + (uint32_t)(ch * 32), r);
+                float rcur[32];
+                if (p.res) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + s_par[ch * 32 + j];
-                    if (p.se) {
+                    for (int j = 0; j < 32; j++) rcur[j] = rnext[j];
+                    if (ch + 1 < NCH) {
+                        const size_t blk2 = f32_blk_index(row, (ch + 1) * 32, BN);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] *= s_gate[ch * 32 + j];
+                        for (int j = 0; j < 4; j++) ldg256(p.res + blk2 + j * 256, *reinterpret_cast<float(*)[8]>(&rnext[8 * j]));
                     }
-                    const size_t blk = f32_blk_index(row, ch * 32, BN); // this lane's first piece of the 32x32 block
-                    if (p.res) {
+                }
+                tmem_ld_wait();
+                float v[32];
+                const float *pb = p.par + ch * 32; // constant bank, uniform index: no shared-memory traffic
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            float tt[8];
-                            ldg256(p.res + blk + j * 256, tt);
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + pb[j];
+                if (p.se) {
+                    const float4 *g4 = reinterpret_cast<const float4 *>(s_gate + ch * 32);
 #pragma unroll
-                            for (int i = 0; i < 8; i++) v[8 * j + i] += tt[i];
-                        }
+                    for (int j = 0; j < 8; j++) {
+                        const float4 g = g4[j];
+                        v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
                     }
-                    if (p.out_raw) {
+                }
+                if (p.res) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            float tt[8];
+                    for (int j = 0; j < 32; j++) v[j] += rcur[j];
+                }
+                const size_t blk = f32_blk_index(row, ch * 32, BN); // this lane's first piece of the 32x32 block
+                if (p.base_offset_mode & 4) continue; // timing experiment only: no output stores
+                if (p.out_raw) {
 #pragma unroll
-                            for (int i = 0; i < 8; i++) tt[i] = live ? v[8 * j + i] : 0.0f;
-                            stg256(p.out_raw + blk + j * 256, tt);
-                        }
+                    for (int j = 0; j < 4; j++) {
+                        float tt[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) tt[i] = live ? v[8 * j + i] : 0.0f;
+                        stg256(p.out_raw + blk + j * 256, tt);
                     }
+                }
 #pragma unroll
-                    for (int o = 0; o < 2; o++) {
-                        __nv_bfloat16 *outp = o == 0 ? p.out_a : p.out_b;
-                        if (!outp) continue;
-                        const float *sc = s_par + (1 + 2 * o) * BN + ch * 32, *sh = s_par + (2 + 2 * o) * BN + ch * 32;
-                        uint8_t *op = reinterpret_cast<uint8_t *>(outp + (size_t)row * BN + ch * 32);
+                for (int o = 0; o < 2; o++) {
+                    __nv_bfloat16 *outp = o == 0 ? p.out_a : p.out_b;
+                    if (!outp) continue;
+                    const float *sc = p.par + (1 + 2 * o) * 128 + ch * 32, *sh = p.par + (2 + 2 * o) * 128 + ch * 32;
+                    uint8_t *op = reinterpret_cast<uint8_t *>(outp + (size_t)row * BN + ch * 32);
 #pragma unroll
-                        for (int j = 0; j < 2; j++) {
-                            uint32_t w[8];
+                    for (int j = 0; j < 2; j++) {
+                        uint32_t w[8];
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const int c = 16 * j + 2 * i;
-                                const float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
-                                const float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
-                                __nv_bfloat162 hh = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
-                                w[i] = *reinterpret_cast<uint32_t *>(&hh);
-                            }
-                            stg256u(op + j * 32, w);
+                        for (int i = 0; i < 8; i++) {
+                            const int c = 16 * j + 2 * i;
+                            const float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
+                            const float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
+                            w[i] = *reinterpret_cast<uint32_t *>(&hh);
                         }
+                        stg256u(op + j * 32, w);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) { if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 } // namespace gaz_conv

@@ -219,7 +219,10 @@ struct StemArgs {
 // warp-uniform broadcast LDS of the int8 inputs + FMAs; outputs leave as 8/16-byte vectors.
 template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(StemArgs p) {
     constexpr int TAPS_CIN = K * K * CIN;
-    __shared__ int8_t s_in[1024];
+    constexpr int kh = K >> 1;
+    __shared__ float s_in[18 * 18 * CIN]; // board with a zero border of kh cells, as floats: no bounds checks, no I2F
+    const int pitch = (p.W + 2 * kh) * CIN;
+    const int npad = (p.H + 2 * kh) * pitch;
     const int cpr = p.Cout >> 2;                 // threads per row
     const int rows_par = blockDim.x / cpr;       // rows processed in parallel
     const int tc = threadIdx.x % cpr, tr = threadIdx.x / cpr;
@@ -235,12 +238,16 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
     if (cnt > p.max_count) cnt = p.max_count;
     const long long total_rows = ((long long)cnt * p.P_pad + 255) / 256 * 256;
     const int n_boards_pad = (int)((total_rows + p.P_pad - 1) / p.P_pad);
-    constexpr int kh = K >> 1;
     const int nin = p.H * p.W * CIN;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) s_in[i] = 0.0f;
     for (int b = blockIdx.x; b < n_boards_pad; b += gridDim.x) {
         __syncthreads();
         if (b < cnt)
-            for (int i = threadIdx.x; i < nin; i += blockDim.x) s_in[i] = p.states[(size_t)b * nin + i];
+            for (int i = threadIdx.x; i < nin; i += blockDim.x) {
+                const int cell = i / CIN, ci = i - cell * CIN;
+                const int y = cell / p.W, x = cell - y * p.W;
+                s_in[(y + kh) * pitch + (x + kh) * CIN + ci] = (float)p.states[(size_t)b * nin + i];
+            }
         __syncthreads();
         for (int pos = tr; pos < p.P_pad; pos += rows_par) {
             const long long row = (long long)b * p.P_pad + pos;
@@ -249,25 +256,19 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
             const bool live = b < cnt && yy >= 0 && xx < p.W;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live) {
+                const float *wp0 = s_in + yy * pitch + xx * CIN; // top-left of the receptive field (padded coords)
 #pragma unroll
                 for (int ky = 0; ky < K; ky++) {
-                    const int iy = yy + ky - kh;
+                    const float *wp = wp0 + ky * pitch;
 #pragma unroll
-                    for (int kx = 0; kx < K; kx++) {
-                        const int ix = xx + kx - kh;
-                        const bool inb = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                        const int8_t *sp = s_in + (inb ? (iy * p.W + ix) * CIN : 0);
+                    for (int kx = 0; kx < K; kx++)
 #pragma unroll
                         for (int ci = 0; ci < CIN; ci++) {
-                            const int sv = inb ? (int)sp[ci] : 0;
-                            if (sv != 0) { // warp-uniform: the whole warp works on one row
-                                const float fs = (float)sv;
-                                const float4 ww = w[(ky * K + kx) * CIN + ci];
-                                acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
-                                acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
-                            }
+                            const float fs = wp[kx * CIN + ci]; // warp-uniform broadcast load
+                            const float4 ww = w[(ky * K + kx) * CIN + ci];
+                            acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
+                            acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
                         }
-                    }
                 }
             }
             float v[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
@@ -427,21 +428,26 @@ __global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
         float acc[COUT];
 #pragma unroll
         for (int co = 0; co < COUT; co++) acc[co] = 0.0f;
+        float a[TAPS][CPL]; // all loads issued before the first FMA (rows outside the buffer are padding: weight 0)
 #pragma unroll
-        for (int ky = 0; ky < K; ky++)
+        for (int t = 0; t < TAPS; t++) {
+            long long r = r0 + (t / K - kh) * p.Wp + (t % K - kh);
+            const bool ok = r >= 0 && r < p.in_rows;
+            r = ok ? r : r0;
 #pragma unroll
-            for (int kx = 0; kx < K; kx++) {
-                const long long r = r0 + (ky - kh) * p.Wp + (kx - kh);
-                if (r < 0 || r >= p.in_rows) continue;
-#pragma unroll
-                for (int j = 0; j < CPL; j++) {
-                    float a;
-                    if (IN_F32) a = ((const float *)p.in)[f32_blk_index(r, lane + 32 * j, p.Cin)];
-                    else a = __bfloat162float(((const __nv_bfloat16 *)p.in)[r * p.Cin + lane + 32 * j]);
-#pragma unroll
-                    for (int co = 0; co < COUT; co++) acc[co] = fmaf(a, w[ky * K + kx][j][co], acc[co]);
-                }
+            for (int j = 0; j < CPL; j++) {
+                float x_;
+                if (IN_F32) x_ = ((const float *)p.in)[f32_blk_index(r, lane + 32 * j, p.Cin)];
+                else x_ = __bfloat162float(((const __nv_bfloat16 *)p.in)[r * p.Cin + lane + 32 * j]);
+                a[t][j] = ok ? x_ : 0.0f;
             }
+        }
+#pragma unroll
+        for (int t = 0; t < TAPS; t++)
+#pragma unroll
+            for (int j = 0; j < CPL; j++)
+#pragma unroll
+                for (int co = 0; co < COUT; co++) acc[co] = fmaf(a[t][j], w[t][j][co], acc[co]);
         // halving butterfly: after the step with mask m a lane keeps the half of its values selected by (lane & m)
         int n = COUT;
         int co_base = 0;
@@ -593,9 +599,11 @@ struct NetOp {
     gaz_net_op d;
     CUtensorMap tmA, tmB; // v1: 128-row activation box
     CUtensorMap tmA2;     // v2 (conv_board_kernel): 152-row half-slab box
+    CUtensorMap tmB2;     // v2 pair mode: half of the output channels per CTA
     int fused_se;         // this conv carries the following SE op in its epilogue
     gaz_net_op se;        // ... whose parameters are here
     int skip;             // SE op folded into the previous conv
+    float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
 };
 
 struct gaz_net {
@@ -619,6 +627,7 @@ struct gaz_net {
     int conv_v1;           // GAZ_CONV_V1=1: use the v1 per-tap kernel (A/B comparison)
     int base_offset_mode;  // GAZ_DESC_BASE_OFFSET (default 0, see gaz_conv.cuh)
     int fuse_se;           // GAZ_FUSE_SE (default 1)
+    int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
     std::vector<cudaEvent_t> ev;
     size_t ev_used;
     std::vector<int> ev_op;
@@ -649,11 +658,29 @@ template <int BN> static int launch_conv(gaz_net *n, NetOp &op, const ConvArgs &
 template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_conv::BoardConvArgs &a, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        CKN(cudaFuncSetAttribute(gaz_conv::conv_board_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gaz_conv::BoardCfg<BN>::SMEM));
+        CKN(cudaFuncSetAttribute(gaz_conv::conv_board_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gaz_conv::BoardCfg<BN, false>::SMEM));
+        CKN(cudaFuncSetAttribute(gaz_conv::conv_board_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gaz_conv::BoardCfg<BN, true>::SMEM));
         attr_set = true;
     }
-    gaz_conv::conv_board_kernel<BN><<<n->n_sm, 256, gaz_conv::BoardCfg<BN>::SMEM, s>>>(op.tmA2, op.tmB, a);
+    if (!n->conv_pair) {
+        gaz_conv::conv_board_kernel<BN, false><<<n->n_sm, 384, gaz_conv::BoardCfg<BN, false>::SMEM, s>>>(op.tmA2, op.tmB, a);
+        return 0;
+    }
+    // CTA pairs: clusters of 2 (one TPC), the leader issues cta_group::2 MMAs for both
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(n->n_sm & ~1), 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = gaz_conv::BoardCfg<BN, true>::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CKN(cudaLaunchKernelEx(&cfg, gaz_conv::conv_board_kernel<BN, true>, op.tmA2, op.tmB2, a));
     return 0;
 }
 
@@ -674,7 +701,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
             a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
             const int tc = d.ksize * d.ksize * d.cin;
-            if (d.cout % 4 != 0 || 256 % (d.cout / 4) != 0 || d.cin > 4 || n->H * n->W * d.cin > 1024)
+            if (d.cout % 4 != 0 || 256 % (d.cout / 4) != 0 || d.cin > 4 || (n->H + 2 * (d.ksize / 2)) > 18 || (n->W + 2 * (d.ksize / 2)) > 18)
                 return gaz_fail("stem shape unsupported (cin %d cout %d)", d.cin, d.cout);
             int grid = n->n_sm * 4;
             (void)tc;
@@ -704,11 +731,10 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 memset(&a, 0, sizeof a);
                 a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
                 a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->base_offset_mode;
-                a.bias = wfp(n, d.bias);
                 const gaz_net_op &o = op.fused_se ? op.se : d; // outputs / residual of the fused SE op
+                memcpy(a.par, op.par, sizeof a.par);
                 a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
-                a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.scale_a = wfp(n, o.scale_a); a.shift_a = wfp(n, o.shift_a);
-                a.out_b = (__nv_bfloat16 *)buf(o.out_b); a.scale_b = wfp(n, o.scale_b); a.shift_b = wfp(n, o.shift_b);
+                a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.out_b = (__nv_bfloat16 *)buf(o.out_b);
                 if (op.fused_se) {
                     a.se = 1; a.se_r = op.se.cin; a.n_cells = n->H * n->W;
                     a.se_w1 = wfp(n, op.se.w2); a.se_b1 = wfp(n, op.se.bias2); a.se_w2 = wfp(n, op.se.w3); a.se_b2 = wfp(n, op.se.bias3);
@@ -814,6 +840,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         n->conv_v1 = e1 && atoi(e1) != 0;
         n->base_offset_mode = e2 ? atoi(e2) : 0;
         n->fuse_se = e3 ? atoi(e3) : 1;
+        const char *e4 = getenv("GAZ_CONV_PAIR");
+        n->conv_pair = e4 ? atoi(e4) : 1;
     }
     n->profile = 0;
     n->ev_used = 0;
@@ -856,6 +884,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         memset(&op.tmA, 0, sizeof op.tmA);
         memset(&op.tmB, 0, sizeof op.tmB);
         memset(&op.tmA2, 0, sizeof op.tmA2);
+        memset(&op.tmB2, 0, sizeof op.tmB2);
         op.fused_se = 0;
         op.skip = 0;
         memset(&op.se, 0, sizeof op.se);
@@ -872,7 +901,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             }
             if (make_map(enc, &op.tmA2, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, gaz_conv::SLAB_BOX_ROWS) != 0 ||
                 make_map(enc, &op.tmA, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, 128) != 0 ||
-                make_map(enc, &op.tmB, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout) != 0) {
+                make_map(enc, &op.tmB, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout) != 0 ||
+                make_map(enc, &op.tmB2, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout / 2) != 0) {
                 gaz_net_destroy(n);
                 return -1;
             }
@@ -889,6 +919,15 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             }
         }
         n->ops.push_back(op);
+    }
+    for (auto &op : n->ops) { // per-channel epilogue parameters of the tensor-core convolutions (host copies)
+        if (op.d.type != GAZ_OP_CONV_TC) continue;
+        const gaz_net_op &o = op.fused_se ? op.se : op.d;
+        const int64_t offs[5] = {op.d.bias, o.scale_a, o.shift_a, o.scale_b, o.shift_b};
+        const float dflt[5] = {0.0f, 1.0f, 0.0f, 1.0f, 0.0f};
+        for (int k = 0; k < 5; k++)
+            for (int c = 0; c < 128; c++)
+                op.par[k * 128 + c] = (offs[k] >= 0 && c < op.d.cout) ? desc->wf[offs[k] + c] : dflt[k];
     }
     CKN(cudaDeviceSynchronize());
     *out = n;

@@ -100,4 +100,89 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// ---- CTA pair (cta_group::2) variants ------------------------------------------------------------------
+// Shared-memory window addresses of the two CTAs of a pair differ in bit 24; clearing it names the even
+// (leader) CTA's copy of the same offset.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load executed by either CTA of the pair; the transaction bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) { // arrive on the leader CTA's copy of `bar`
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_result, uint32_t ncols) { // same warp id in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 across the pair (128 rows from each CTA's A tile), B split by N between the CTAs; leader issues
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier at this offset in BOTH CTAs when all previously issued pair-MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+
+// ---- warp-uniform issue helpers ------------------------------------------------------------------------
+// The MMA warp runs its loops with all 32 lanes (uniform control flow, descriptors in uniform registers) and
+// elects one lane only for the tcgen05 instruction itself.  Issuing from an `if (lane == 0)` region instead makes
+// the compiler shuttle every descriptor through R2UR/ELECT loops: ~27 SASS instructions per MMA, which capped the
+// tensor pipe at ~54 % (ncu + SASS, r01).
+// SWIZZLE_128B K-major descriptor split in two words: hi is constant, lo = (addr >> 4) | LBO(1) << 16.
+constexpr uint32_t UMMA_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    if (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128) : "memory");
+    }
+}
+template <bool PAIR> __device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
+    if (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+            ::"r"(smem_u32(bar)) : "memory");
+    }
+}
+
 } // namespace gaz_tc

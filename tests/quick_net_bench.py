@@ -17,4 +17,5 @@ ms = net.time_forward(B, 1)
 import ctypes
 tot, cnt, per = net.profile_read()
 print("conv launches", cnt, "conv total ms (last passes)", tot)
+print("per conv op ms:", [round(float(x), 3) for x in per if x > 0])
 print("net bytes GB", net.bytes_allocated() / 1e9)
