@@ -232,43 +232,53 @@ class SelfPlayBench:
 
 
 def dominant_kernel_stats(sb, leaves_per_launch, peaks):
-    """CUDA-event time of the dominant kernel (3x3 C128->C128 tcgen05 implicit-GEMM conv) inside the timed region."""
+    """CUDA-event time of the dominant kernel group inside the timed region.  Groups = tensor-core convolutions of
+    one shape; the 3x3 C128->C128 launches are split into plain ones (block conv1) and those whose epilogue carries
+    the Squeeze-Excitation + skip add (block conv2)."""
     tot, cnt, per = sb.net.profile_read()
     shapes = sb.net.op_shapes()
-    best = None
     groups = {}
-    for oi, (typ, cin, cout, k) in enumerate(shapes):
+    for oi, (typ, cin, cout, k, tag) in enumerate(shapes):
         if typ != 1 or per[oi] <= 0:
             continue
-        groups.setdefault((cin, cout, k), [0.0, 0])
-        groups[(cin, cout, k)][0] += float(per[oi])
-        groups[(cin, cout, k)][1] += 1
+        g = groups.setdefault((cin, cout, k, tag), [0.0, 0])
+        g[0] += float(per[oi])
+        g[1] += 1
     if not groups:
         return None, {}
-    key = max(groups, key=lambda g: groups[g][0])
-    n_ops_in_group = groups[key][1]
-    passes = cnt / max(1, sum(g[1] for g in groups.values()))
-    launches = n_ops_in_group * passes
-    avg_ms = groups[key][0] / max(1.0, launches)
-    cin, cout, k = key
+    n_tc_ops = sum(g[1] for g in groups.values())
+    passes = cnt / max(1, n_tc_ops)
     hw = sb.spec["H"] * sb.spec["W"]
+    detail = {}
+    for (cin, cout, k, tag), (ms, nops) in groups.items():
+        launches = nops * passes
+        avg_ms = ms / max(1.0, launches)
+        flops = 2.0 * leaves_per_launch * hw * k * k * cin * cout
+        detail["%dx%d C%d->C%d%s" % (k, k, cin, cout, "+SE" if tag else "")] = dict(
+            launches=int(launches), avg_launch_ms=round(avg_ms, 4), tflops=round(flops / (avg_ms * 1e-3) / 1e12, 1),
+            share_of_conv_time=round(ms / max(tot, 1e-9), 4))
+    key = max(groups, key=lambda g: groups[g][0])
+    cin, cout, k, tag = key
+    launches = groups[key][1] * passes
+    avg_ms = groups[key][0] / max(1.0, launches)
     flops = 2.0 * leaves_per_launch * hw * k * k * cin * cout
     achieved = flops / (avg_ms * 1e-3) / 1e12
-    share = groups[key][0] / max(tot, 1e-9)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tp):
         try:
-            t = json.load(open(tp))
-            if t.get("kernel") == "conv3x3_%d_%d" % (cin, cout) and t.get("leaves") == int(leaves_per_launch):
+            t = json.load(open(tp)).get("%dx%d_C%d_C%d%s" % (k, k, cin, cout, "_se" if tag else ""))
+            if t and t.get("leaves") == int(round(leaves_per_launch)):
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = dict(bound="tensor", kernel="conv_tc_kernel<%d> %dx%d C%d->C%d (tcgen05 implicit GEMM)" % (cout, k, k, cin, cout),
+    roof = dict(bound="tensor",
+                kernel="gaz_conv::conv_board_kernel<%d, pair> %dx%d C%d->C%d%s (tcgen05 cta_group::2 implicit GEMM)"
+                       % (cout, k, k, cin, cout, " + fused SE/skip epilogue" if tag else ""),
                 achieved=round(achieved, 2), peak=peaks["sustained"], unit="TFLOP/s", frac=round(achieved / peaks["sustained"], 4),
                 peak_source="%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
                 flops_per_launch=flops, avg_launch_ms=round(avg_ms, 4), launches_timed=int(launches),
-                share_of_conv_time=round(share, 4), traffic=traffic)
+                share_of_conv_time=round(groups[key][0] / max(tot, 1e-9), 4), traffic=traffic, groups=detail)
     return roof, dict(conv_ms_total=tot, conv_launches=cnt)
 
 

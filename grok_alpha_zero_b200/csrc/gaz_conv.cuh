@@ -85,13 +85,15 @@ constexpr int SLAB_BYTES = SLAB_ROWS * 128;     // 38912 = 38 * 1024
 constexpr int SLAB_BOX_ROWS = SLAB_ROWS / 2;
 
 template <int BN, bool PAIR> struct BoardCfg {
-    static constexpr int NSLAB = 4;
-    static constexpr int NB = PAIR ? 6 : 4;
+    static constexpr int NSLAB = PAIR ? 4 : 3;
+    static constexpr int NB = 4;
+    static constexpr int NSTAGE = PAIR ? 2 : 1; // 32-row x 32-channel bf16 staging tiles per epilogue warp (TMA store source)
+    static constexpr int STAGE_BYTES = 8 * NSTAGE * 2048;
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN; // weight rows (output channels) this CTA stages per tile
     static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;
     static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [8 warps][BN], mean, hidden, gate
-    static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+    static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                                 SE_FLOATS * 4;
 };
 
@@ -113,6 +115,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(384, 1)
 conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOa, const __grid_constant__ CUtensorMap tmOb,
                   const __grid_constant__ BoardConvArgs p) {
     using Cfg = BoardCfg<BN, PAIR>;
     constexpr int NSLAB = Cfg::NSLAB, NB = Cfg::NB;
@@ -120,7 +123,8 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;
     uint8_t *sB = base + NSLAB * SLAB_BYTES;
-    uint64_t *bars = (uint64_t *)(sB + NB * Cfg::B_BYTES);
+    uint8_t *sStage = sB + NB * Cfg::B_BYTES; // [8 epilogue warps][NSTAGE][2 KB], 1024 B aligned
+    uint64_t *bars = (uint64_t *)(sStage + Cfg::STAGE_BYTES);
     uint64_t *a_full = bars, *a_empty = bars + NSLAB, *b_full = bars + 2 * NSLAB, *b_empty = bars + 2 * NSLAB + NB;
     uint64_t *tfull = bars + 2 * NSLAB + 2 * NB, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
@@ -136,6 +140,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int n_tiles = (int)((valid_rows + TILE_ROWS - 1) / TILE_ROWS);
     // loop index space: single CTA = tiles; pair = pair-tiles (tile 2*pt + rank; the last one may be a dummy)
     const int n_loop = PAIR ? (n_tiles + 1) / 2 : n_tiles;
+    const int dbg = p.base_offset_mode; // timing experiments: 8 no residual loads, 16 no fp32 stores, 32 no bf16 stores, 64 no SE passes
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLAB; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -144,6 +149,8 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.out_a) tma_prefetch_desc(&tmOa);
+        if (p.out_b) tma_prefetch_desc(&tmOb);
     }
     if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); else tmem_alloc(tmem_slot, Cfg::TMEM_COLS); }
     tc_fence_before();
@@ -236,6 +243,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int et = threadIdx.x - 128; // 0..255
         float *s_part = s_se, *s_mean = s_se + 8 * BN, *s_hid = s_mean + BN, *s_gate = s_hid + BN;
         constexpr int NCH = BN / 32;
+        uint32_t stage_i = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int lt = tile0; lt < n_loop; lt += tile_step) {
@@ -253,7 +261,8 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
             const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
             float rnext[32]; // residual of the first output chunk: issued before the accumulator is even ready
-            if (p.res) {
+            const bool use_res = p.res && !(dbg & 8);
+            if (use_res) {
 #pragma unroll 1
                 for (int ch = 1; ch < NCH; ch++) { // pull the rest of this row's residual into L2 meanwhile
                     const float *pp = p.res + f32_blk_index(row, ch * 32, BN);
@@ -267,7 +276,8 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + sub) * BN);
-            if (p.se) {
+            if (p.se && (dbg & 64)) { if (et < BN) s_gate[et] = 1.0f; named_bar_sync(1, 256); }
+            if (p.se && !(dbg & 64)) {
                 // ---- pass 1: per-channel sums over the board's live cells (tile == board)
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ch++) {
@@ -336,7 +346,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint32_t r[32];
                 tmem_ld_32x32(t_acc + (uint32_t)(ch * 32), r);
                 float rcur[32];
-                if (p.res) {
+                if (use_res) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) rcur[j] = rnext[j];
                     if (ch + 1 < NCH) {
@@ -358,13 +368,13 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
                     }
                 }
-                if (p.res) {
+                if (use_res) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] += rcur[j];
                 }
                 const size_t blk = f32_blk_index(row, ch * 32, BN); // this lane's first piece of the 32x32 block
-                if (p.base_offset_mode & 4) continue; // timing experiment only: no output stores
-                if (p.out_raw) {
+                if (dbg & 4) continue; // timing experiment only: no output stores
+                if (p.out_raw && !(dbg & 16)) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         float tt[8];
@@ -373,24 +383,37 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         stg256(p.out_raw + blk + j * 256, tt);
                     }
                 }
+                // bf16 operands of the next layer: the 32 x 32 tile of this warp goes through a 2 KB SWIZZLE_64B
+                // staging tile and leaves with ONE TMA store - a row-per-lane STG touches 32 lines per instruction
+                // and made the epilogue LSU-bound (ncu r01)
 #pragma unroll
                 for (int o = 0; o < 2; o++) {
-                    __nv_bfloat16 *outp = o == 0 ? p.out_a : p.out_b;
-                    if (!outp) continue;
+                    if (!(o == 0 ? p.out_a : p.out_b) || (dbg & 32)) continue;
                     const float *sc = p.par + (1 + 2 * o) * 128 + ch * 32, *sh = p.par + (2 + 2 * o) * 128 + ch * 32;
-                    uint8_t *op = reinterpret_cast<uint8_t *>(outp + (size_t)row * BN + ch * 32);
+                    uint8_t *st = sStage + ((warp - 4) * Cfg::NSTAGE + (stage_i % Cfg::NSTAGE)) * 2048;
+                    stage_i++;
+                    // at most NSTAGE - 1 earlier stores of this warp may still be reading their staging tiles
+                    if (lane == 0) { if (Cfg::NSTAGE == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        uint32_t w[8];
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t w[4];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int c = 16 * j + 2 * i;
+                        for (int i = 0; i < 4; i++) {
+                            const int c = 8 * j + 2 * i;
                             const float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
                             const float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
                             __nv_bfloat162 hh = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
                             w[i] = *reinterpret_cast<uint32_t *>(&hh);
                         }
-                        stg256u(op + j * 32, w);
+                        // row = lane (64 B), 16-byte chunk j XOR-swizzled with address bits 7..8 (= (lane >> 1) & 3)
+                        *reinterpret_cast<uint4 *>(st + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(o == 0 ? &tmOa : &tmOb, st, ch * 32, (int)(row - lane));
+                        tma_store_commit();
                     }
                 }
             }
@@ -400,6 +423,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (warp >= 4 && lane == 0) tma_store_wait_all(); // bulk stores must complete before the CTA's shared memory goes away
     tc_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();
     if (warp == 2) { if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }

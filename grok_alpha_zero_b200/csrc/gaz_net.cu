@@ -600,6 +600,7 @@ struct NetOp {
     CUtensorMap tmA, tmB; // v1: 128-row activation box
     CUtensorMap tmA2;     // v2 (conv_board_kernel): 152-row half-slab box
     CUtensorMap tmB2;     // v2 pair mode: half of the output channels per CTA
+    CUtensorMap tmOa, tmOb; // v2 epilogue: bf16 outputs as 32-row x 32-channel SWIZZLE_64B store boxes
     int fused_se;         // this conv carries the following SE op in its epilogue
     gaz_net_op se;        // ... whose parameters are here
     int skip;             // SE op folded into the previous conv
@@ -633,16 +634,20 @@ struct gaz_net {
     std::vector<int> ev_op;
 };
 
-static int make_map(PFN_encodeTiled enc, CUtensorMap *m, void *ptr, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+static int make_map_ex(PFN_encodeTiled enc, CUtensorMap *m, void *ptr, uint64_t inner, uint64_t rows, uint32_t box_inner,
+                       uint32_t box_rows, CUtensorMapSwizzle sw) {
     cuuint64_t dims[2] = {inner, rows};
     cuuint64_t strides[1] = {inner * 2};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return gaz_fail("cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu box=%u", (int)r,
-                                           (unsigned long long)inner, (unsigned long long)rows, box_rows);
+                     sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gaz_fail("cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu box=%ux%u", (int)r,
+                                           (unsigned long long)inner, (unsigned long long)rows, box_inner, box_rows);
     return 0;
+}
+static int make_map(PFN_encodeTiled enc, CUtensorMap *m, void *ptr, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    return make_map_ex(enc, m, ptr, inner, rows, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int BN> static int launch_conv(gaz_net *n, NetOp &op, const ConvArgs &a, cudaStream_t s) {
@@ -665,7 +670,7 @@ template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_
         attr_set = true;
     }
     if (!n->conv_pair) {
-        gaz_conv::conv_board_kernel<BN, false><<<n->n_sm, 384, gaz_conv::BoardCfg<BN, false>::SMEM, s>>>(op.tmA2, op.tmB, a);
+        gaz_conv::conv_board_kernel<BN, false><<<n->n_sm, 384, gaz_conv::BoardCfg<BN, false>::SMEM, s>>>(op.tmA2, op.tmB, op.tmOa, op.tmOb, a);
         return 0;
     }
     // CTA pairs: clusters of 2 (one TPC), the leader issues cta_group::2 MMAs for both
@@ -680,7 +685,7 @@ template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CKN(cudaLaunchKernelEx(&cfg, gaz_conv::conv_board_kernel<BN, true>, op.tmA2, op.tmB2, a));
+    CKN(cudaLaunchKernelEx(&cfg, gaz_conv::conv_board_kernel<BN, true>, op.tmA2, op.tmB2, op.tmOa, op.tmOb, a));
     return 0;
 }
 
@@ -923,6 +928,16 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     for (auto &op : n->ops) { // per-channel epilogue parameters of the tensor-core convolutions (host copies)
         if (op.d.type != GAZ_OP_CONV_TC) continue;
         const gaz_net_op &o = op.fused_se ? op.se : op.d;
+        memset(&op.tmOa, 0, sizeof op.tmOa);
+        memset(&op.tmOb, 0, sizeof op.tmOb);
+        for (int k = 0; k < 2; k++) {
+            const int id = k == 0 ? o.out_a : o.out_b;
+            if (id < 0) continue;
+            const NetBuf &ob = n->bufs[(size_t)id];
+            if (ob.kind != GAZ_BUF_ROWS_BF16 || ob.width != op.d.cout) { gaz_net_destroy(n); return gaz_fail("conv_tc output buffer must be bf16 rows of width cout"); }
+            if (make_map_ex(enc, k == 0 ? &op.tmOa : &op.tmOb, ob.ptr, (uint64_t)ob.width, (uint64_t)n->rows_alloc, 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_64B) != 0) { gaz_net_destroy(n); return -1; }
+        }
         const int64_t offs[5] = {op.d.bias, o.scale_a, o.shift_a, o.scale_b, o.shift_b};
         const float dflt[5] = {0.0f, 1.0f, 0.0f, 1.0f, 0.0f};
         for (int k = 0; k < 5; k++)

@@ -228,7 +228,14 @@ class Net:
         self.n_ops = len(b.ops)
         self.n_conv_tc = sum(1 for o in b.ops if o["type"] == OP_CONV_TC)
         self.conv_shapes = [(o["cin"], o["cout"], o["ksize"]) for o in b.ops if o["type"] == OP_CONV_TC]
-        self._op_shapes = [(o["type"], o["cin"], o["cout"], o["ksize"]) for o in b.ops]
+        # (type, cin, cout, ksize, tag): tag "se" = convolution whose epilogue carries the following SE op
+        self._op_shapes = []
+        for i, o in enumerate(b.ops):
+            tag = ""
+            if o["type"] == OP_CONV_TC and i + 1 < len(b.ops) and b.ops[i + 1]["type"] == OP_SE and \
+                    (spec["H"] + 1) * (spec["W"] + 1) == 256:
+                tag = "se"
+            self._op_shapes.append((o["type"], o["cin"], o["cout"], o["ksize"], tag))
         bufs = (GazNetBuf * len(b.bufs))(*[GazNetBuf(k, w) for k, w in b.bufs])
         ops = (GazNetOp * len(b.ops))(*[GazNetOp(**o) for o in b.ops])
         wf = np.concatenate(b.wf) if b.wf else np.zeros(4, np.float32)
@@ -275,7 +282,7 @@ class Net:
         engine._net = self  # keep alive
 
     def op_shapes(self):
-        """(op type, cin, cout, ksize) of every op in launch order"""
+        """(op type, cin, cout, ksize, tag) of every op in launch order"""
         return list(self._op_shapes)
 
     def bytes_allocated(self):
