@@ -1,0 +1,60 @@
+"""Build-container-only checks against the UNMODIFIED reference tree (skipped where /root/reference is absent,
+i.e. on the GPU box): the reference's own Game_Tester must accept our game classes, and our game classes must
+agree with the reference's numba `*_MCTS` functions on random play-outs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import ref_shim  # noqa: E402
+from grok_alpha_zero_b200 import games  # noqa: E402
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")]
+
+OURS = {"gomoku": games.Gomoku, "connect4": games.Connect4, "tictactoe": games.TicTacToe}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_shim.load()
+
+
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "gomoku"])
+def test_static_functions_match_reference_numba(ref, name):
+    rng = np.random.RandomState(5)
+    R = ref.games[name]
+    for trial in range(6 if name != "gomoku" else 3):
+        g, r = OURS[name](), R()
+        w = -2
+        while w == -2 and len(g.get_legal_actions()) > 0:
+            la, lr = g.get_legal_actions(), r.get_legal_actions()
+            assert np.array_equal(np.asarray(la), np.asarray(lr)) and np.asarray(la).dtype == np.asarray(lr).dtype
+            pol = rng.rand(g.policy_shape[0]).astype(np.float32)
+            hist = np.array(g.action_history, dtype=la.dtype) if len(g.action_history) else np.zeros((0,), la.dtype)
+            a1, p1 = g.get_legal_actions_policy_MCTS(g.board, -g.next_player, hist, pol.copy())
+            a2, p2 = r.get_legal_actions_policy_MCTS(r.board, -r.next_player, hist, pol.copy())
+            assert np.array_equal(a1, a2) and np.array_equal(p1.view(np.uint32), p2.view(np.uint32))   # bit-exact priors
+            a = la[rng.randint(len(la))]
+            g.do_action(a); r.do_action(a)
+            assert np.array_equal(g.board, r.board)
+            s1, s2 = g.get_input_state(), r.get_input_state()
+            assert s1.shape == s2.shape and np.array_equal(s1, s2)
+            w = g.check_win()
+            assert w == r.check_win()
+        T = min(4, len(g.action_history))
+        states = np.stack([g.get_input_state()] * T)
+        pols = rng.rand(T, g.policy_shape[0]).astype(np.float32)
+        b1, q1 = g.augment_sample(states, pols)
+        b2, q2 = r.augment_sample(states, pols)
+        assert np.array_equal(np.asarray(b1), np.asarray(b2)) and np.array_equal(np.asarray(q1), np.asarray(q2))
+
+
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "gomoku"])
+def test_reference_game_tester_accepts_our_game_classes(ref, name, capsys):
+    from Game_Tester import Game_Tester   # the reference's only executable conformance check (Game_Tester.py:9-576)
+    ok = Game_Tester(OURS[name]).test()
+    out = capsys.readouterr().out
+    assert ok is not False, out[-2000:]
