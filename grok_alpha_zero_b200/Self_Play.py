@@ -1,0 +1,438 @@
+"""Batched self-play on the B200 engine: the drop-in for `Self_Play.run_self_play` (Self_Play.py:259-413).
+
+The reference runs one OS process per game (Self_Play.py:346-363), each looping `Self_Play.play` (:71-208).  Here
+every GPU keeps thousands of games resident and advances them together, one move per outer iteration:
+
+    get_input_state of every game  ->  MCTS.run / MCTS_Gumbel.run for every game (rounds of select -> network ->
+    expand on the device)  ->  root statistics  ->  tau / opening-book move choice  ->  do_action + check_win  ->
+    prune_tree on both trees (or a fresh Gumbel tree)  ->  finished games leave, queued games take their slots.
+
+What is kept from `Self_Play.play`: two PUCT trees per game with the side to move searching `int(limit * 1.5)`
+iterations (:97-106) or one Gumbel tree rebuilt every move (:110-112,151-153); tau = 1 for the first
+`num_explore_actions_first/second` own moves, else 0 (:87-95); the opening book on move 0 (:130-140); the policy
+target = scattered `[action, prob]` rows (:114), q target = win-rate of the played move (:117-125), z target and its
+sign / draw rules (:127,159-170), value = 0.5 * (z + q) (:172), `max_actions` cut-off as a draw (:155-157), the
+game's own `augment_sample` (:174), the dataset naming `boards_k / policies_k / values_k` and the six `game_stats`
+counters (:181-208).  Games shard over ranks by index (game g -> rank g mod world); the search path has no
+collective, finished trajectories are gathered to rank 0 (the single writer) with `torch.distributed`.
+Randomness: tau sampling and the opening book use one numpy Generator per GLOBAL game id and the device Dirichlet
+noise is keyed by the global game id, so a game's trajectory does not depend on the number of GPUs.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import games as G
+from .engine import DIMS, Engine
+
+try:  # the reference writes HDF5; h5py is not part of this image, so the same schema goes into an .npz otherwise
+    import h5py as _h5
+except Exception:  # noqa: BLE001
+    _h5 = None
+
+
+# ---------------------------------------------------------------------------------------------- replay writer --
+class ReplayWriter:
+    """`Self_Play_Data` with the reference schema (Self_Play.py:178-208): `game_stats` uint32[6] =
+    [max game length, total positions, games, wins(-1), draws, wins(+1)] and per game and augmentation
+    `boards_k` (T,H,W,C), `policies_k` (T,P) f32, `values_k` (T,1) f32.  HDF5 when h5py is importable, else
+    `Self_Play_Data.npz` holding the same names."""
+
+    def __init__(self, folder_path):
+        self.folder = folder_path
+        os.makedirs(folder_path, exist_ok=True)
+        self.h5_path = os.path.join(folder_path, "Self_Play_Data.h5")
+        self.npz_path = os.path.join(folder_path, "Self_Play_Data.npz")
+        self.use_h5 = _h5 is not None
+        self.data = {}
+        if not self.use_h5 and os.path.exists(self.npz_path):
+            with np.load(self.npz_path) as z:
+                self.data = {k: z[k] for k in z.files}
+        if not self.use_h5 and "game_stats" not in self.data:
+            self.data["game_stats"] = np.zeros(6, dtype=np.uint32)
+
+    def games_done(self):
+        if self.use_h5:
+            if not os.path.exists(self.h5_path):
+                return 0
+            with _h5.File(self.h5_path, "r") as f:
+                return int(f["game_stats"][2])
+        return int(self.data["game_stats"][2])
+
+    def add_game(self, boards_aug, policies_aug, values_aug, game_length, winner):
+        """boards_aug (A,T,H,W,C), policies_aug (A,T,P), values_aug (A,T,1)"""
+        if self.use_h5:
+            with _h5.File(self.h5_path, "a") as f:
+                if "game_stats" not in f:
+                    f.create_dataset("game_stats", data=np.zeros(6, dtype=np.uint32))
+                self._add(f, boards_aug, policies_aug, values_aug, game_length, winner, h5=True)
+        else:
+            self._add(self.data, boards_aug, policies_aug, values_aug, game_length, winner, h5=False)
+
+    @staticmethod
+    def _add(f, boards_aug, policies_aug, values_aug, game_length, winner, h5):
+        st = f["game_stats"]
+        if st[0] < game_length:
+            st[0] = game_length
+        st[1] += boards_aug.shape[1]
+        st[2] += 1
+        st[winner + 4] += 1
+        k0 = (len(f.keys()) - 1) // 3
+        for inc in range(policies_aug.shape[0]):
+            for name, arr, dt in (("boards", boards_aug[inc], boards_aug.dtype), ("policies", policies_aug[inc], np.float32),
+                                  ("values", values_aug[inc], np.float32)):
+                key = "%s_%d" % (name, k0 + inc)
+                if h5:
+                    f.create_dataset(key, maxshape=(None, *arr.shape[1:]), dtype=dt, data=arr, chunks=None)
+                else:
+                    f[key] = np.ascontiguousarray(arr, dtype=dt)
+
+    def flush(self):
+        if not self.use_h5:
+            np.savez(self.npz_path, **self.data)
+
+
+def finalize_game(game_obj, states, policies, q, z, winner):
+    """Self_Play.py:159-176: z sign / draw rules, value = 0.5 * (z + q), the game's own augmentation."""
+    states = np.asarray(states, dtype=game_obj.board.dtype)
+    policies = np.asarray(policies, dtype=np.float32)
+    q = np.asarray(q, dtype=np.float32).reshape((-1, 1))
+    z = np.asarray(z, dtype=np.float32).reshape((-1, 1)).copy()
+    if winner == z[-1][0] == -1:
+        z *= -1.0
+    elif winner == 0:
+        z[:] = 0.0
+    values = 0.5 * (z + q)
+    b_aug, p_aug = game_obj.augment_sample(states, policies)
+    b_aug, p_aug = np.asarray(b_aug), np.asarray(p_aug)
+    v_aug = np.repeat(np.expand_dims(values, 0), repeats=p_aug.shape[0], axis=0)
+    return b_aug, p_aug, v_aug
+
+
+# ---------------------------------------------------------------------------------------- the batched driver --
+class BatchedSelfPlay:
+    """Plays the games `game_ids` (global ids) on one device, `n_slots` at a time."""
+
+    def __init__(self, game_class, build_config, train_config, game_ids, n_slots, device=0, evaluator="net",
+                 spec=None, weights=None, seed=0, lib=None, hash_salt=0, node_cap=None, slot_cap=None,
+                 use_noise=True):
+        self.game_class = game_class
+        self.proto = game_class()
+        self.name = G.game_name_of(self.proto)
+        self.H, self.W, self.C, self.P = DIMS[self.name]
+        self.tc, self.bc = train_config, build_config
+        self.gumbel = bool(train_config.get("use_gumbel", False))
+        self.tpg = 1 if self.gumbel else 2
+        self.queue = list(game_ids)
+        self.n_slots = max(1, min(n_slots, len(self.queue))) if self.queue else 1
+        self.seed = seed
+        self.evaluator = evaluator
+        self.hash_salt = hash_salt
+        limit = train_config["MCTS_iteration_limit"]
+        self.limit = int(limit) if self.gumbel else int(limit * 1.5)          # Self_Play.py:99
+        self.max_actions = int(train_config["max_actions"])
+        stablemax = bool(build_config.get("use_stablemax"))
+        if node_cap is None:
+            L = 7 if self.name == "connect4" else self.P
+            node_cap = int(self.limit * (1.4 if self.name == "gomoku" else 3.5)) + 4 * L + 64
+            if self.gumbel:
+                node_cap = int(self.limit * 1.5) + 2 * L + 64
+            slot_cap = node_cap * min(L, 225) + 256 if slot_cap is None else slot_cap
+        self.eng = Engine(self.name, n_games=self.n_slots, mode="gumbel" if self.gumbel else "puct",
+                          trees_per_game=self.tpg, node_cap=node_cap, slot_cap=slot_cap,
+                          c_puct_init=float(train_config.get("c_puct_init", 2.5)), m=int(train_config.get("m", 16)),
+                          c_visit=float(train_config.get("c_visit", 50.0)), c_scale=float(train_config.get("c_scale", 1.0)),
+                          activation_fn="stablemax" if stablemax else "softmax", device=device, lib=lib)
+        self.net = None
+        if evaluator == "net":
+            from .net import Net
+            self.net = Net(spec, weights, max_batch=self.n_slots, device=device)  # larger request lists are served in chunks
+            self.net.attach(self.eng)
+        if not self.gumbel and use_noise:
+            self.eng.set_noise(float(train_config.get("dirichlet_alpha", 0.3)), 0.25, seed)   # Self_Play.py:38-46
+        self.use_gumbel_noise = self.gumbel and use_noise
+        # per-slot host state
+        self.slot_game = np.full(self.n_slots, -1, np.int64)      # global game id or -1 (idle)
+        self.rngs = [None] * self.n_slots
+        self.traj = [None] * self.n_slots
+        self.finished = []
+        self.sims = 0
+        self.moves = 0
+
+    # ---- evaluator plumbing --------------------------------------------------------------------------------
+    def _serve(self, n):
+        if n > 0:
+            if self.evaluator == "net":
+                self.eng.eval_net()
+            else:
+                self.eng.eval_hash(self.hash_salt, self.gumbel)
+        self.eng.expand()
+
+    def _rounds(self, n):
+        if self.evaluator == "net":
+            self.eng.rounds_net(n)
+        else:
+            self.eng.rounds_hash(n, self.hash_salt, self.gumbel)
+
+    # ---- slots ---------------------------------------------------------------------------------------------
+    def _seat(self, slots):
+        """put queued games into `slots` (empty boards, fresh roots)"""
+        seated = []
+        for s in slots:
+            if not self.queue:
+                self.slot_game[s] = -1
+                continue
+            gid = self.queue.pop(0)
+            self.slot_game[s] = gid
+            self.rngs[s] = np.random.Generator(np.random.PCG64([self.seed, int(gid)]))
+            self.traj[s] = dict(states=[], policies=[], q=[], z=[])
+            self.eng.set_game(int(s), np.zeros((self.H, self.W), np.int8), -1, [])
+            seated.append(s)
+        keys = np.repeat(np.where(self.slot_game >= 0, self.slot_game, 0).astype(np.uint64), self.tpg)
+        self.eng.set_tree_keys(keys * np.uint64(2) + np.tile(np.arange(self.tpg, dtype=np.uint64), self.n_slots))
+        if seated:
+            mask = np.zeros((self.n_slots, self.tpg), np.uint8)
+            mask[seated] = 1
+            for k in range(self.tpg):   # one tree per game at a time keeps the evaluation batch <= n_slots
+                m = np.zeros_like(mask)
+                m[:, k] = mask[:, k]
+                self._serve(self.eng.new_roots(m.reshape(-1)))
+
+    def live(self):
+        return self.slot_game >= 0
+
+    # ---- one move of every live game -------------------------------------------------------------------
+    def step(self):
+        e = self.eng
+        live = self.live()
+        if not live.any():
+            return False
+        states, ginfo = e.get_states()
+        mover = ginfo[:, 0]
+        hist_len = ginfo[:, 1]
+        run_tree = np.zeros(self.n_slots, np.int64) if self.gumbel else (mover > 0).astype(np.int64)
+        limits = np.zeros((self.n_slots, self.tpg), np.int32)
+        limits[np.arange(self.n_slots), run_tree] = np.where(live, self.limit, 0)
+        if self.use_gumbel_noise:   # MCTS_Gumbel.py:592-594: Gumbel(0,1) on the root logits, one stream per game
+            noise = np.zeros((self.n_slots, 256), np.float64)
+            for s in np.nonzero(live)[0]:
+                noise[s] = self.rngs[s].gumbel(size=256)
+            e.set_gumbel_noise(noise)
+        e.run_begin(limits.reshape(-1))
+        while e.remaining() > 0:
+            self._rounds(32)
+        vis, val, tinfo = e.root_dense(want_values=True)
+        vis = vis.reshape(self.n_slots, self.tpg, self.P)[np.arange(self.n_slots), run_tree]
+        val = val.reshape(self.n_slots, self.tpg, self.P)[np.arange(self.n_slots), run_tree]
+        tinfo = tinfo.reshape(self.n_slots, self.tpg, 4)[np.arange(self.n_slots), run_tree]
+        self.sims += int(tinfo[live, 2].sum())
+        if self.gumbel:
+            pi = e.gumbel_pi_dense().reshape(self.n_slots, self.P)
+        actions = np.full(self.n_slots, -1, np.int16)
+        for s in np.nonzero(live)[0]:
+            v = vis[s].astype(np.float64)
+            if self.gumbel:
+                policy = pi[s]
+                a = int(tinfo[s, 1])
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    q = val[s, a] / vis[s, a] if vis[s, a] > 0 else pi[s, a]     # MCTS_Gumbel.py:648-666
+            else:
+                policy = (v / v.sum()).astype(np.float32)
+                move_no = int(hist_len[s])
+                first = move_no % 2 == 0
+                explore = (move_no // 2 < self.tc.get("num_explore_actions_first", 0)) if first else \
+                    ((move_no + 1) // 2 < self.tc.get("num_explore_actions_second", 0))       # Self_Play.py:87-95
+                if explore:  # tau = 1: weights visits / root.visits, renormalised (MCTS.py:605-610)
+                    w = v / float(tinfo[s, 0]) if tinfo[s, 0] > 0 else v
+                    w = w / w.sum()
+                    a = int(self.rngs[s].choice(self.P, p=w))
+                else:
+                    a = int(tinfo[s, 1])
+                q = np.float32(val[s, a]) / np.float32(vis[s, a]) if vis[s, a] > 0 else np.float32(0.0)
+            t = self.traj[s]
+            t["states"].append(states[s].copy())
+            t["policies"].append(policy)
+            t["q"].append(np.float32(q))
+            t["z"].append(float(mover[s]))
+            if hist_len[s] == 0 and self.tc.get("opening_actions", False):               # Self_Play.py:130-140
+                acts, weights = zip(*self.tc["opening_actions"])
+                acts = [G.action_to_id(self.name, x) for x in acts]
+                weights = list(weights)
+                if sum(weights) < 1.0:
+                    acts.append(a)
+                    weights.append(1.0 - sum(weights))
+                a = int(acts[int(self.rngs[s].choice(len(acts), p=np.asarray(weights) / sum(weights)))])
+            actions[s] = a
+        winners = e.apply_actions(actions)
+        self.moves += int(live.sum())
+        done = []
+        for s in np.nonzero(live)[0]:
+            w = int(winners[s])
+            n_act = len(self.traj[s]["z"])
+            if w == -2 and n_act >= self.max_actions:
+                w = 0                                                                      # Self_Play.py:155-157
+            if w != -2:
+                done.append((s, w))
+        done_slots = [s for s, _ in done]
+        cont = live.copy()
+        cont[done_slots] = False
+        pa = np.repeat(np.where(cont, actions, -1).astype(np.int16), self.tpg)
+        create_new = True if self.gumbel else bool(self.tc.get("create_new_root", False))
+        self._serve(e.prune(pa, create_new_root=create_new))
+        for s, w in done:
+            t = self.traj[s]
+            self.finished.append(dict(game_id=int(self.slot_game[s]), winner=w, length=len(t["z"]),
+                                      states=np.asarray(t["states"], dtype=np.int8),
+                                      policies=np.asarray(t["policies"], dtype=np.float32),
+                                      q=np.asarray(t["q"], dtype=np.float32), z=np.asarray(t["z"], dtype=np.float32)))
+            self.traj[s] = None
+        if done_slots:
+            self._seat(done_slots)
+        return True
+
+    def play(self, progress=None):
+        self._seat(list(range(self.n_slots)))
+        while self.step():
+            if progress is not None:
+                progress(self)
+        st = self.eng.status()
+        if st != 0:
+            raise RuntimeError("engine status %d (1 node overflow, 2 slot overflow): raise node_cap / slot_cap" % st)
+        return self.finished
+
+    def close(self):
+        self.eng.close()
+        if self.net is not None:
+            self.net.close()
+
+
+# ------------------------------------------------------------------------------------------- trajectory gather --
+def pack_games(finished):
+    """list of finished-game dicts -> one uint8 buffer (JSON index + raw arrays)"""
+    index, blobs, off = [], [], 0
+    for g in finished:
+        rec = dict(game_id=g["game_id"], winner=g["winner"], length=g["length"], arrays={})
+        for k in ("states", "policies", "q", "z"):
+            a = np.ascontiguousarray(g[k])
+            rec["arrays"][k] = dict(dtype=str(a.dtype), shape=list(a.shape), offset=off, nbytes=a.nbytes)
+            blobs.append(a.reshape(-1).view(np.uint8))
+            off += a.nbytes
+        index.append(rec)
+    head = np.frombuffer(json.dumps(index).encode(), dtype=np.uint8)
+    body = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
+    return np.concatenate([np.array([len(head)], dtype=np.int64).view(np.uint8), head, body])
+
+
+def unpack_games(buf):
+    buf = np.asarray(buf, dtype=np.uint8)
+    n = int(buf[:8].view(np.int64)[0])
+    index = json.loads(bytes(buf[8:8 + n]).decode())
+    body = buf[8 + n:]
+    out = []
+    for rec in index:
+        g = dict(game_id=rec["game_id"], winner=rec["winner"], length=rec["length"])
+        for k, a in rec["arrays"].items():
+            g[k] = body[a["offset"]:a["offset"] + a["nbytes"]].view(np.dtype(a["dtype"])).reshape(a["shape"]).copy()
+        out.append(g)
+    return out
+
+
+def gather_games(finished, device=None):
+    """All ranks -> rank 0: lengths by all_gather, then one padded byte buffer per rank by gather (NCCL over NVLink when
+    the process group is NCCL and `device` is a CUDA device, gloo on CPU).  Returns the merged list on rank 0, [] elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return sorted(finished, key=lambda g: g["game_id"])
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    buf = torch.from_numpy(pack_games(finished).copy()).to(dev)
+    size = torch.tensor([buf.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    mx = int(max(int(s.item()) for s in sizes))
+    padded = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    padded[:buf.numel()] = buf
+    outs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, gather_list=outs, dst=0)
+    if rank != 0:
+        return []
+    merged = []
+    for r in range(world):
+        merged += unpack_games(outs[r][:int(sizes[r].item())].cpu().numpy())
+    merged.sort(key=lambda g: g["game_id"])
+    return merged
+
+
+# ------------------------------------------------------------------------------------------------ entry point --
+def net_spec_from_configs(game_name, build_config, train_config):
+    from . import netspec
+    gumbel = bool(train_config.get("use_gumbel", False))
+    head = "linear" if gumbel else ("stablemax" if build_config.get("use_stablemax") else "softmax")
+    over = {}
+    if "num_resnet_layers" in build_config:
+        over["num_blocks"] = int(build_config["num_resnet_layers"])
+    if "num_filters" in build_config:
+        over["filters"] = int(build_config["num_filters"])
+    if "use_se" in build_config:
+        over["use_se"] = bool(build_config["use_se"])
+    return netspec.build_spec(game_name, head, **over)
+
+
+def run_self_play(game_class, configs, folder_path, per_process_wait_time=1e-3, weights=None, seed=0, evaluator="net",
+                  lib=None):
+    """Same call as the reference's `run_self_play(game_class, configs, folder_path, per_process_wait_time)`; plays
+    `games_per_generation - game_stats[2]` games (resume rule of Self_Play.py:267-272) on this rank's share of the
+    game ids and appends them to `folder_path/Self_Play_Data` on rank 0.  Extra keys read from train_config:
+    `games_per_gpu` (concurrent games per GPU, default 4096).  `weights`: Keras-layout dict or a checkpoint path
+    (default `folder_path/model.npz`, else random init - generation 0 of the reference plays with a random policy)."""
+    build_config, train_config = configs[0], configs[1]
+    rank, world, device = 0, 1, 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+            device = int(os.environ.get("LOCAL_RANK", rank))
+    except Exception:  # noqa: BLE001
+        pass
+    writer = ReplayWriter(folder_path) if rank == 0 else None
+    done = writer.games_done() if rank == 0 else 0
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([done], dtype=torch.int64)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        dist.broadcast(t, src=0)
+        done = int(t.item())
+    games_left = int(train_config["games_per_generation"]) - done
+    if games_left <= 0:
+        print(f"Finished generating {train_config['games_per_generation']} games!")
+        return []
+    ids = [g for g in range(done, done + games_left) if g % world == rank]
+    spec = w = None
+    name = G.game_name_of(game_class())
+    if evaluator == "net":
+        from . import netspec, session
+        if isinstance(weights, str) or (weights is None and os.path.exists(os.path.join(folder_path, "model.npz"))):
+            spec, w = session.load_checkpoint(weights if isinstance(weights, str) else os.path.join(folder_path, "model.npz"))
+        else:
+            spec = net_spec_from_configs(name, build_config, train_config)
+            w = weights if weights is not None else netspec.init_weights(spec, seed=seed)
+    sp = BatchedSelfPlay(game_class, build_config, train_config, ids, int(train_config.get("games_per_gpu", 4096)),
+                         device=device, evaluator=evaluator, spec=spec, weights=w, seed=seed, lib=lib)
+    finished = sp.play()
+    sp.close()
+    dev = None
+    if world > 1:
+        import torch.distributed as dist
+        dev = ("cuda:%d" % device) if dist.get_backend() == "nccl" else None
+    merged = gather_games(finished, device=dev)
+    if rank == 0:
+        proto = game_class()
+        for g in merged:
+            b, p, v = finalize_game(proto, g["states"], g["policies"], g["q"], g["z"], g["winner"])
+            writer.add_game(b, p, v, g["length"], g["winner"])
+        writer.flush()
+    return merged

@@ -31,6 +31,10 @@ SYMBOLS = {
     "gaz_reset_games": (C.c_int, [_P]),
     "gaz_apply_actions": (C.c_int, [_P, _P, _P]),
     "gaz_get_game": (C.c_int, [_P, C.c_int, _P, _P]),
+    "gaz_get_states": (C.c_int, [_P, _P, _P]),
+    "gaz_set_noise": (C.c_int, [_P, C.c_float, C.c_float, C.c_uint64]),
+    "gaz_set_tree_keys": (C.c_int, [_P, _P]),
+    "gaz_gumbel_pi_dense": (C.c_int, [_P, _P]),
     "gaz_new_roots": (C.c_int, [_P, _P]),
     "gaz_run_begin": (C.c_int, [_P, _P]),
     "gaz_select": (C.c_int, [_P]),

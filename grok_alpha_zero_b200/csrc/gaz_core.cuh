@@ -102,7 +102,7 @@ struct GameState {       // live game mirrored on the device (board = the root p
     uint32_t last3;
     int32_t winner;      // -2 running, -1/0/1 finished
     int32_t last_action;
-    int32_t pad[3];
+    int32_t pad[3];      // [0], [1]: Dirichlet-noise stream positions of the game's trees
 };
 
 struct LeafRec {         // one outstanding evaluation request
@@ -144,6 +144,9 @@ struct View {
     double c_visit_d, c_scale_d;
     int use_softmax;
     const double *gumbel_noise; // optional injected noise [n_trees][MAXL] or null
+    float dir_alpha, dir_eps;   // Dirichlet exploration noise at every evaluated node (MCTS.py:243-245,481); eps 0 = off
+    uint64_t noise_seed;
+    const uint64_t *tree_keys;  // optional per-tree stream keys (global game id based); null = seed ^ tree
 };
 
 // -------------------------------------------------------------------- coop ---
@@ -177,6 +180,10 @@ struct Coop {
         for (int o = 16; o > 0; o >>= 1) { float w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
         return v;
     }
+    __device__ float fsum_(float v) const {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
     __device__ float fmin_(float v) const {
         for (int o = 16; o > 0; o >>= 1) { float w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
         return v;
@@ -208,6 +215,7 @@ struct Coop {
     int imin(int v) const { return v; }
     uint32_t umax(uint32_t v) const { return v; }
     float fmax_(float v) const { return v; }
+    float fsum_(float v) const { return v; }
     float fmin_(float v) const { return v; }
     double dmax_(double v) const { return v; }
     void argmax_first(double &, int &) const {}
@@ -241,6 +249,46 @@ struct Scratch {
     uint8_t act2[MAXL];
     uint32_t w[2 * MAXNW];
 };
+
+
+// ------------------------------------------------------------------- noise ---
+// Counter-based RNG (Philox-4x32-10) keyed by (seed, tree) with counter (evaluation serial, child index, draw):
+// the noise a node receives depends only on which game/tree it belongs to and on how many evaluations that tree
+// has made, never on the GPU count or on scheduling.  Production mode only - parity runs keep dir_eps = 0.
+GAZ_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+GAZ_HD void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+GAZ_HD float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); } // (0, 1)
+
+// Gamma(alpha, 1) by Marsaglia-Tsang (alpha < 1 boosted with U^(1/alpha)); np.random.dirichlet normalises such draws.
+GAZ_HD float gamma_sample(float alpha, uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1) {
+    const float a = alpha < 1.0f ? alpha + 1.0f : alpha;
+    const float d = a - 1.0f / 3.0f, c = 1.0f / sqrtf(9.0f * d);
+    float g = d;
+    uint32_t r[4];
+    for (uint32_t it = 0; it < 16; it++) {
+        philox4x32(c0, c1, it, 0x47414d4du, k0, k1, r);
+        const float u1 = u01(r[0]), u2 = u01(r[1]), u3 = u01(r[2]);
+        const float x = sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2); // Box-Muller
+        float v = 1.0f + c * x;
+        if (v <= 0.0f) continue;
+        v = v * v * v;
+        if (logf(u3) < 0.5f * x * x + d - d * v + d * logf(v)) { g = d * v; break; }
+    }
+    if (alpha < 1.0f) {
+        philox4x32(c0, c1, 0xffffu, 0x424f4f53u, k0, k1, r);
+        g *= powf(u01(r[0]), 1.0f / alpha);
+    }
+    return g;
+}
 
 // ------------------------------------------------------------------- games ---
 // Boards are two bitboards: words [0, NW/2) = stones of player -1, [NW/2, NW) = player +1.
@@ -750,8 +798,27 @@ template <class CG> GAZ_HD void expand_finish(const CG &cg, const View &v, int l
     if (!v.gumbel) {
         float s = 0.0f; // sequential float32 sum, every lane redundantly (bit-exact order)
         for (int i = 0; i < n; i++) s = s + sc.f2[i];
+        float gsum = 0.0f;
+        const bool noisy = v.dir_eps > 0.0f;
+        if (noisy) { // _apply_dirichlet (MCTS.py:243-245): (1 - eps) * p + eps * Dirichlet(alpha)
+            // stream position = noisy expansions this tree has made in the CURRENT game (GameState::pad, zeroed when
+            // a game is seated), so the draw does not depend on which slot / GPU the game lives on
+            GameState &gs = v.games[tree / v.trees_per_game];
+            const uint32_t serial = (uint32_t)gs.pad[tree % v.trees_per_game];
+            cg.sync();
+            if (cg.lane == 0) gs.pad[tree % v.trees_per_game] = (int32_t)(serial + 1u);
+            for (int i = cg.lane; i < n; i += cg.width()) {
+                const uint64_t key = v.tree_keys ? v.tree_keys[tree] ^ v.noise_seed : v.noise_seed ^ (uint64_t)(uint32_t)tree;
+                float g = gamma_sample(v.dir_alpha, (uint32_t)key, (uint32_t)(key >> 32), serial, (uint32_t)i);
+                sc.f3[i] = g;
+                gsum += g;
+            }
+            gsum = cg.fsum_(gsum);
+            if (!(gsum > 0.0f)) gsum = 1.0f;
+        }
         for (int i = cg.lane; i < n; i += cg.width()) {
             float p = sc.f2[i] / s;
+            if (noisy) p = (1.0f - v.dir_eps) * p + v.dir_eps * (sc.f3[i] / gsum);
             sc.f2[i] = p;
             sc.key[i] = ((uint64_t)sortable_bits(p) << 8) | (uint64_t)i;
         }
@@ -1245,6 +1312,24 @@ template <class CG> GAZ_HD void gumbel_final_pi(const CG &cg, const View &v, int
     int L = nr_L(r);
     compute_pi_warp(cg, v, L, nb, sv, true, true, sc);
     for (int i = cg.lane; i < L; i += cg.width()) out[i] = sc.f4[i];
+    cg.sync();
+}
+
+// Final pi' of every tree scattered by action id (0 where illegal) - the `prob` column of MCTS_Gumbel.run's rows
+// as compute_policy_improvement lays it out.
+template <class CG> GAZ_HD void gumbel_final_pi_dense(const CG &cg, const View &v, int tree, Scratch &sc, float *out) {
+    TreeState &ts = v.trees[tree];
+    float *o = out + (size_t)tree * v.P;
+    for (int i = cg.lane; i < v.P; i += cg.width()) o[i] = 0.0f;
+    cg.sync();
+    if (ts.root < 0) return;
+    NodeRec r = *node_ptr(v, tree, ts.root);
+    uint64_t sv;
+    uint32_t nb = gumbel_load(cg, v, tree, r, sc, &sv);
+    int L = nr_L(r);
+    compute_pi_warp(cg, v, L, nb, sv, true, true, sc);
+    const uint8_t *sa = slota_ptr(v, tree);
+    for (int i = cg.lane; i < L; i += cg.width()) o[sa[r.slot_base + i]] = sc.f4[i];
     cg.sync();
 }
 

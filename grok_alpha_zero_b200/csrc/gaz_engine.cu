@@ -249,10 +249,26 @@ __global__ void __launch_bounds__(THREADS) k_root_dense(View v, uint32_t *visits
     Coop cg;
     root_dense_tree(cg, v, widx, visits, values, info);
 }
+// get_input_state of every live game (Self_Play.py:77: board_states.append(game.get_input_state()))
+__global__ void __launch_bounds__(THREADS) k_game_states(View v, int8_t *states, int32_t *info) {
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= v.n_games) return;
+    Coop cg;
+    const GameState &g = v.games[widx];
+    encode_state(cg, v, g.board, -g.next_player, g.hist_len, g.last3, states + (size_t)widx * v.ncell * v.C);
+    if (cg.lane == 0) {
+        info[widx * 4 + 0] = g.next_player; info[widx * 4 + 1] = g.hist_len;
+        info[widx * 4 + 2] = g.winner; info[widx * 4 + 3] = g.last_action;
+    }
+}
 __global__ void k_set_games(View v, const int8_t *cells, const int32_t *meta) {
     int gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= v.n_games) return;
     set_game_from_cells(v, gi, cells, meta);
+}
+__global__ void __launch_bounds__(THREADS) k_gumbel_pi_dense(View v, float *out) {
+    WARP_PROLOGUE(v.n_trees)
+    gumbel_final_pi_dense(cg, v, widx, sc, out);
 }
 static inline int grid_warps(int n) { return (n + WARPS - 1) / WARPS; }
 #endif
@@ -380,6 +396,7 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     rc |= ealloc(e, &e->d_lut, (size_t)v.lut_n);
     rc |= ealloc(e, &e->d_pi, MAXL);
     e->d_noise = nullptr;
+    e->d_states = nullptr; e->d_ginfo = nullptr; e->d_keys = nullptr;
     e->d_cells = nullptr; e->d_meta = nullptr; e->d_dense_vis = nullptr; e->d_dense_val = nullptr; e->d_dense_info = nullptr;
 #ifndef GAZ_EMUL
     e->ev0 = nullptr; e->ev1 = nullptr;
@@ -737,11 +754,9 @@ int gaz_root_dense(gaz_engine *e, uint32_t *visits_out, float *values_out, int32
     if (!e || !visits_out || !info_out) return fail("null argument");
     const View &v = e->v;
     const size_t NT = (size_t)v.n_trees;
-    if (!e->d_dense_vis) {
-        if (ealloc(e, &e->d_dense_vis, NT * v.P) != 0) return -1;
-        if (ealloc(e, &e->d_dense_val, NT * v.P) != 0) return -1;
-        if (ealloc(e, &e->d_dense_info, NT * 4) != 0) return -1;
-    }
+    if (!e->d_dense_vis && ealloc(e, &e->d_dense_vis, NT * v.P) != 0) return -1;
+    if (!e->d_dense_val && ealloc(e, &e->d_dense_val, NT * v.P) != 0) return -1;
+    if (!e->d_dense_info && ealloc(e, &e->d_dense_info, NT * 4) != 0) return -1;
 #ifdef GAZ_EMUL
     for (int t = 0; t < v.n_trees; t++) { Coop cg; root_dense_tree(cg, v, t, e->d_dense_vis, e->d_dense_val, e->d_dense_info); }
     memcpy(visits_out, e->d_dense_vis, NT * v.P * 4);
@@ -756,6 +771,70 @@ int gaz_root_dense(gaz_engine *e, uint32_t *visits_out, float *values_out, int32
     CK(cudaMemcpyAsync(info_out, e->d_dense_info, NT * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     return stream_sync(e->stream);
 #endif
+}
+
+int gaz_get_states(gaz_engine *e, int8_t *states_out, int32_t *info_out) {
+    if (!e || !states_out || !info_out) return fail("null argument");
+    const View &v = e->v;
+    const size_t ss = (size_t)v.ncell * v.C;
+    if (!e->d_states) {
+        if (ealloc(e, &e->d_states, (size_t)v.n_games * ss) != 0) return -1;
+        if (ealloc(e, &e->d_ginfo, (size_t)v.n_games * 4) != 0) return -1;
+    }
+#ifdef GAZ_EMUL
+    for (int g = 0; g < v.n_games; g++) {
+        Coop cg;
+        const GameState &gs = v.games[g];
+        encode_state(cg, v, gs.board, -gs.next_player, gs.hist_len, gs.last3, e->d_states + (size_t)g * ss);
+        e->d_ginfo[g * 4 + 0] = gs.next_player; e->d_ginfo[g * 4 + 1] = gs.hist_len;
+        e->d_ginfo[g * 4 + 2] = gs.winner; e->d_ginfo[g * 4 + 3] = gs.last_action;
+    }
+    memcpy(states_out, e->d_states, (size_t)v.n_games * ss);
+    memcpy(info_out, e->d_ginfo, (size_t)v.n_games * 4 * sizeof(int32_t));
+    return 0;
+#else
+    k_game_states<<<grid_warps(v.n_games), THREADS, 0, e->stream>>>(v, e->d_states, e->d_ginfo);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(states_out, e->d_states, (size_t)v.n_games * ss, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(info_out, e->d_ginfo, (size_t)v.n_games * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    return stream_sync(e->stream);
+#endif
+}
+
+int gaz_gumbel_pi_dense(gaz_engine *e, float *pi_out) {
+    if (!e || !pi_out) return fail("null argument");
+    const View &v = e->v;
+    if (!v.gumbel) return fail("engine is not in Gumbel mode");
+    const size_t NT = (size_t)v.n_trees;
+    if (!e->d_dense_val && ealloc(e, &e->d_dense_val, NT * v.P) != 0) return -1;
+#ifdef GAZ_EMUL
+    for (int t = 0; t < v.n_trees; t++) { Coop cg; Scratch sc; gumbel_final_pi_dense(cg, v, t, sc, e->d_dense_val); }
+    memcpy(pi_out, e->d_dense_val, NT * v.P * 4);
+    return 0;
+#else
+    k_gumbel_pi_dense<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, e->d_dense_val);
+    CK(cudaGetLastError());
+    return d2h(pi_out, e->d_dense_val, NT * v.P * 4, e->stream);
+#endif
+}
+
+int gaz_set_tree_keys(gaz_engine *e, const uint64_t *keys) {
+    if (!e) return fail("null engine");
+    if (!keys) { e->v.tree_keys = nullptr; return 0; }
+    if (!e->d_keys && ealloc(e, &e->d_keys, (size_t)e->v.n_trees) != 0) return -1;
+    if (h2d(e->d_keys, keys, (size_t)e->v.n_trees * sizeof(uint64_t), e->stream) != 0) return -1;
+    e->v.tree_keys = e->d_keys;
+    return stream_sync(e->stream);
+}
+
+int gaz_set_noise(gaz_engine *e, float dirichlet_alpha, float dirichlet_epsilon, uint64_t seed) {
+    if (!e) return fail("null engine");
+    if (dirichlet_epsilon < 0.0f || dirichlet_epsilon >= 1.0f) return fail("dirichlet_epsilon must be in [0, 1)");
+    if (dirichlet_epsilon > 0.0f && !(dirichlet_alpha > 0.0f)) return fail("dirichlet_alpha must be positive");
+    e->v.dir_alpha = dirichlet_alpha;
+    e->v.dir_eps = dirichlet_epsilon;
+    e->v.noise_seed = seed;
+    return 0;
 }
 
 int gaz_timer_begin(gaz_engine *e) {

@@ -63,6 +63,9 @@ struct gaz_engine {
     double *d_noise;
     double *d_lut;
     float *d_pi;         // [MAXL]
+    int8_t *d_states;    // [n_games][H*W*C] staging of gaz_get_states
+    int32_t *d_ginfo;    // [n_games][4]
+    uint64_t *d_keys;    // [n_trees] noise stream keys
     int8_t *d_cells;     // [n_games][ncell] staging of gaz_set_games
     int32_t *d_meta;     // [n_games][4]
     uint32_t *d_dense_vis; // [n_trees][P] staging of gaz_root_dense

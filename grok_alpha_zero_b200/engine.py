@@ -101,6 +101,26 @@ class Engine:
         self._ck(self.lib.gaz_apply_actions(self._h, _p(a), _p(w)))
         return w
 
+    def get_states(self):
+        """get_input_state() of every live game: (states int8 (n_games, H, W, C), info int32 (n_games, 4) =
+        next_player, len(action_history), winner (-2 running), last action id)"""
+        st = np.zeros((self.n_games, self.H, self.W, self.C), dtype=np.int8)
+        info = np.zeros((self.n_games, 4), dtype=np.int32)
+        self._ck(self.lib.gaz_get_states(self._h, _p(st), _p(info)))
+        return st, info
+
+    def set_noise(self, dirichlet_alpha, dirichlet_epsilon, seed=0):
+        self._ck(self.lib.gaz_set_noise(self._h, float(dirichlet_alpha), float(dirichlet_epsilon), int(seed)))
+
+    def set_tree_keys(self, keys):
+        k = None if keys is None else np.ascontiguousarray(keys, dtype=np.uint64)
+        self._ck(self.lib.gaz_set_tree_keys(self._h, _p(k)))
+
+    def gumbel_pi_dense(self):
+        pi = np.zeros((self.n_trees, self.P), dtype=np.float32)
+        self._ck(self.lib.gaz_gumbel_pi_dense(self._h, _p(pi)))
+        return pi
+
     def get_game(self, g):
         b = np.zeros(self.H * self.W, dtype=np.int8)
         info = np.zeros(3, dtype=np.int32)

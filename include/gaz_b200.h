@@ -71,6 +71,20 @@ int gaz_reset_games(gaz_engine *e);
  * winners_out[g] = -2 running / -1,0,1 (may be NULL). */
 int gaz_apply_actions(gaz_engine *e, const int16_t *actions, int32_t *winners_out);
 int gaz_get_game(gaz_engine *e, int game, int8_t *board_out, int32_t *info_out /* next_player, hist_len, winner */);
+/* game.get_input_state() of EVERY live game (Self_Play.py:77; layouts of Gomoku.py:173-177, Connect4.py:327-346,
+ * Tictactoe.py:229-235): states_out = n_games * H*W*C int8 (HWC); info_out = n_games * 4 int32:
+ * next_player, len(action_history), winner (-2 running), last action id. */
+int gaz_get_states(gaz_engine *e, int8_t *states_out, int32_t *info_out);
+/* Dirichlet exploration noise applied on the device to the renormalised priors of every evaluated node
+ * (MCTS._apply_dirichlet, MCTS.py:243-245,357,481-482): p = (1-eps)*p + eps*Dirichlet(alpha).  Counter-based
+ * Philox streams keyed by (seed, tree), so a game's noise does not depend on the number of GPUs.  eps = 0 (the
+ * default, used by every parity test) switches it off. */
+int gaz_set_noise(gaz_engine *e, float dirichlet_alpha, float dirichlet_epsilon, uint64_t seed);
+/* optional per-tree stream keys (n_trees values, e.g. the GLOBAL game id of the game a tree belongs to) so that the
+ * noise of a game is the same however games are laid out over slots and GPUs; NULL = seed ^ tree index */
+int gaz_set_tree_keys(gaz_engine *e, const uint64_t *keys);
+/* final pi' (MCTS_Gumbel.py:653-662) of EVERY tree scattered by action id: n_trees * P floats */
+int gaz_gumbel_pi_dense(gaz_engine *e, float *pi_out);
 
 /* create_expand_root (MCTS.py:296-365): tree_mask[t] != 0 selects trees (NULL = all).
  * Returns the number of evaluation requests produced (terminal roots need none). */
