@@ -69,6 +69,7 @@ struct BoardConvArgs {
     // shift_b, 128 floats each.  The epilogue reads them with uniform LDC, which keeps them off the shared-memory
     // port that the MMAs saturate (a broadcast LDS per value cost 25 % of the port in v2.0, ncu r01).
     float par[5 * 128];
+    const float *d_par;       // the same 640 floats in global memory (v3 reads them per lane: a lane-indexed LDC serialises)
     const float *res;         // blocked fp32 residual stream (optional)
     float *out_raw;           // blocked fp32 output (optional)
     __nv_bfloat16 *out_a;     // relu(scale_a * v + shift_a) as bf16 rows (optional)
@@ -280,7 +281,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.se && !(dbg & 64)) {
                 // ---- pass 1: per-channel sums over the board's live cells (tile == board)
 #pragma unroll 1
-                for (int ch = 0; ch < NCH; ch++) {
+                for (int ch = 0; ch < ((dbg & 256) ? 0 : NCH); ch++) {
                     uint32_t r[32];
                     tmem_ld_32x32(t_acc + (uint32_t)(ch * 32), r);
                     tmem_ld_wait();
@@ -305,38 +306,56 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     s_part[(sub * 4 + q) * BN + ch * 32 + col] = v[0];
                 }
                 named_bar_sync(1, 256);
-                if (et < BN) {
-                    float s = 0.0f;
+                if (!(dbg & 128)) {
+                    // dense1 (C -> R) spread over all 256 epilogue threads: output j, quarter `part` of the inputs, all
+                    // 32 weight loads in flight at once (the weights live in L2: with 64 / 128 threads and 128 / 64
+                    // dependent steps the two tiny layers cost 0.38 ms per launch, ncu + ablation r01).  The conv bias
+                    // is folded into the dense bias on the host (se_b1 = b1 + W1^T bias).
+                    const int j = et & 63, part = et >> 6;
+                    if (j < p.se_r) {
+                        const float *w1 = p.se_w1 + (size_t)(part * (BN / 4)) * p.se_r + j;
+                        const float inv_cells = 1.0f / (float)p.n_cells;
+                        float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) s += s_part[i * BN + et];
-                    s_mean[et] = s / (float)p.n_cells + p.par[et];
+                        for (int i = 0; i < BN / 4; i += 4) {
+                            float m4[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int ii = part * (BN / 4) + i + u;
+                                float sum = 0.0f;
+#pragma unroll
+                                for (int k = 0; k < 8; k++) sum += s_part[k * BN + ii];
+                                m4[u] = sum * inv_cells;
+                            }
+                            h0 = fmaf(m4[0], __ldg(w1 + (size_t)(i) * p.se_r), h0);
+                            h1 = fmaf(m4[1], __ldg(w1 + (size_t)(i + 1) * p.se_r), h1);
+                            h2 = fmaf(m4[2], __ldg(w1 + (size_t)(i + 2) * p.se_r), h2);
+                            h3 = fmaf(m4[3], __ldg(w1 + (size_t)(i + 3) * p.se_r), h3);
+                        }
+                        s_mean[part * 64 + j] = (h0 + h1) + (h2 + h3);   // hidden partials [4][64] (s_mean .. s_hid)
+                    }
                 }
                 named_bar_sync(1, 256);
-                if (et < p.se_r) { // 4 independent accumulators hide the FMA / load latency of the 128-long dot product
-                    float h0 = p.se_b1[et], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
-                    const float *w1 = p.se_w1 + et;
-#pragma unroll 8
-                    for (int i = 0; i < BN; i += 4) {
-                        h0 = fmaf(s_mean[i], w1[(i) * p.se_r], h0);
-                        h1 = fmaf(s_mean[i + 1], w1[(i + 1) * p.se_r], h1);
-                        h2 = fmaf(s_mean[i + 2], w1[(i + 2) * p.se_r], h2);
-                        h3 = fmaf(s_mean[i + 3], w1[(i + 3) * p.se_r], h3);
+                if (!(dbg & 128)) {
+                    // dense2 (R -> C): output channel cc, half `part` of the hidden units (relu(dense1) rebuilt on the fly)
+                    const int cc = et & (BN - 1), part = et / BN;
+                    const int r2 = p.se_r >> 1;
+                    if (part < 2) {
+                        const float *w2 = p.se_w2 + (size_t)(part * r2) * BN + cc;
+                        float g0 = 0.0f, g1 = 0.0f;
+#pragma unroll 16
+                        for (int i = 0; i < r2; i += 2) {
+                            const int ii = part * r2 + i;
+                            const float ha = fmaxf(((s_mean[ii] + s_mean[64 + ii]) + (s_mean[128 + ii] + s_mean[192 + ii])) + __ldg(p.se_b1 + ii), 0.0f);
+                            const float hb = fmaxf(((s_mean[ii + 1] + s_mean[65 + ii]) + (s_mean[129 + ii] + s_mean[193 + ii])) + __ldg(p.se_b1 + ii + 1), 0.0f);
+                            g0 = fmaf(ha, __ldg(w2 + (size_t)(i) * BN), g0);
+                            g1 = fmaf(hb, __ldg(w2 + (size_t)(i + 1) * BN), g1);
+                        }
+                        s_part[part * BN + cc] = g0 + g1;                  // gate partials reuse the sums' slots
                     }
-                    s_hid[et] = fmaxf((h0 + h1) + (h2 + h3), 0.0f);
                 }
                 named_bar_sync(1, 256);
-                if (et < BN) {
-                    float g0 = p.se_b2[et], g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
-                    const float *w2 = p.se_w2 + et;
-#pragma unroll 8
-                    for (int i = 0; i < p.se_r; i += 4) {
-                        g0 = fmaf(s_hid[i], w2[(i) * BN], g0);
-                        g1 = fmaf(s_hid[i + 1], w2[(i + 1) * BN], g1);
-                        g2 = fmaf(s_hid[i + 2], w2[(i + 2) * BN], g2);
-                        g3 = fmaf(s_hid[i + 3], w2[(i + 3) * BN], g3);
-                    }
-                    s_gate[et] = 1.0f / (1.0f + expf(-((g0 + g1) + (g2 + g3))));
-                }
+                if (et < BN) s_gate[et] = (dbg & 128) ? 0.5f : 1.0f / (1.0f + expf(-((s_part[et] + s_part[BN + et]) + p.se_b2[et])));
                 named_bar_sync(1, 256);
             }
             // ---- output pass over the 32-column chunks of this warp's 32 rows; the residual of chunk i+1 is

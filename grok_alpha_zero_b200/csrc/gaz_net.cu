@@ -15,6 +15,7 @@
 #include "gaz_internal.h"
 #include "gaz_tc.cuh"
 #include "gaz_conv.cuh"
+#include "gaz_convt.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -22,6 +23,11 @@
 
 using namespace gaz_tc;
 using gaz_conv::f32_blk_index;
+using gaz_convt::f32_t_index;
+// fp32 row tensors: layout 0 = 32x32 blocked (gaz_conv.cuh, default), 1 = 8-row interleaved (gaz_convt.cuh, GAZ_CONV_T=1)
+__host__ __device__ __forceinline__ size_t f32_index(long long row, int c, int C, int layout) {
+    return layout ? f32_t_index(row, c, C) : f32_blk_index(row, c, C);
+}
 
 #define CKN(x)                                                                                             \
     do {                                                                                                   \
@@ -205,7 +211,7 @@ struct StemArgs {
     const int32_t *count;
     int max_count;
     const int8_t *states; // [leaf][H*W*Cin] HWC
-    int H, W, Cin, Cout, K, P_pad, Wp, act;
+    int H, W, Cin, Cout, K, P_pad, Wp, act, layout;
     const float *w;       // [K*K][Cin][Cout]
     const float *bias, *scale, *shift; // conv bias, stem BN affine
     __nv_bfloat16 *out_q; // activation itself in bf16 (operand of a 1x1 projection), optional
@@ -283,7 +289,12 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
                 a[j] = live ? fmaxf(fmaf(sav[j], t, tav[j]), 0.0f) : 0.0f;
             }
             const size_t o = (size_t)row * p.Cout + c0;
-            if (p.out_raw) *reinterpret_cast<float4 *>(p.out_raw + f32_blk_index(row, c0, p.Cout)) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.out_raw) {
+                if (p.layout == 0) *reinterpret_cast<float4 *>(p.out_raw + f32_blk_index(row, c0, p.Cout)) = make_float4(v[0], v[1], v[2], v[3]);
+                else
+#pragma unroll
+                    for (int j = 0; j < 4; j++) p.out_raw[f32_t_index(row, c0 + j, p.Cout)] = v[j];
+            }
             if (p.out_q) {
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
                 *reinterpret_cast<uint2 *>(p.out_q + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
@@ -298,7 +309,7 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
 
 struct SeArgs {
     const int32_t *count;
-    int max_count, H, W, C, R, P_pad, Wp;
+    int max_count, H, W, C, R, P_pad, Wp, layout;
     const float *c2;  // conv2 output (+bias), fp32 padded rows
     const float *res; // residual stream
     const float *w1, *b1, *w2, *b2; // dense1 [C][R], dense2 [R][C]
@@ -318,7 +329,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
         const long long row0 = (long long)b * p.P_pad;
         float s = 0.0f;
         for (int y = 0; y < p.H; y++)
-            for (int x = 0; x < p.W; x++) s += p.c2[f32_blk_index(row0 + (y + 1) * p.Wp + x, c, p.C)];
+            for (int x = 0; x < p.W; x++) s += p.c2[f32_index(row0 + (y + 1) * p.Wp + x, c, p.C, p.layout)];
         s_mean[c] = s / (float)(p.H * p.W);
         __syncthreads();
         if (c < p.R) {
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
         for (int pos = 0; pos < p.P_pad; pos++) {
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
             const bool live = yy != 0 && xx != p.Wp - 1;
-            const size_t ob = f32_blk_index(row0 + pos, c, p.C);
+            const size_t ob = f32_index(row0 + pos, c, p.C, p.layout);
             const size_t o = (size_t)(row0 + pos) * p.C + c;
             float v = live ? fmaf(p.c2[ob], gate, p.res[ob]) : 0.0f;
             if (p.out_raw) p.out_raw[ob] = v;
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
 
 struct HeadConvArgs {
     const int32_t *count;
-    int max_count, H, W, Cin, Cout, K, P_pad, Wp, in_f32;
+    int max_count, H, W, Cin, Cout, K, P_pad, Wp, in_f32, layout;
     long long in_rows;  // allocated rows of the input buffer
     const void *in;     // padded rows, bf16 or fp32
     const float *w;     // [K*K][Cin][Cout]
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
                 const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * p.Cout;
                 if (p.in_f32) {
                     for (int ci = 0; ci < p.Cin; ci++) {
-                        const float a = ((const float *)p.in)[f32_blk_index(r, ci, p.Cin)];
+                        const float a = ((const float *)p.in)[f32_index(r, ci, p.Cin, p.layout)];
 #pragma unroll
                         for (int j = 0; j < 16; j++) if (j < p.Cout) acc[j] = fmaf(a, wp[ci * p.Cout + j], acc[j]);
                     }
@@ -437,7 +448,7 @@ __global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
 #pragma unroll
             for (int j = 0; j < CPL; j++) {
                 float x_;
-                if (IN_F32) x_ = ((const float *)p.in)[f32_blk_index(r, lane + 32 * j, p.Cin)];
+                if (IN_F32) x_ = ((const float *)p.in)[f32_index(r, lane + 32 * j, p.Cin, p.layout)];
                 else x_ = __bfloat162float(((const __nv_bfloat16 *)p.in)[r * p.Cin + lane + 32 * j]);
                 a[t][j] = ok ? x_ : 0.0f;
             }
@@ -601,10 +612,13 @@ struct NetOp {
     CUtensorMap tmA2;     // v2 (conv_board_kernel): 152-row half-slab box
     CUtensorMap tmB2;     // v2 pair mode: half of the output channels per CTA
     CUtensorMap tmOa, tmOb; // v2 epilogue: bf16 outputs as 32-row x 32-channel SWIZZLE_64B store boxes
+    CUtensorMap tmWt, tmOta, tmOtb; // v3 (conv_t_kernel): weight box of min(cout,128) rows, 16-row x 32-channel store boxes
     int fused_se;         // this conv carries the following SE op in its epilogue
     gaz_net_op se;        // ... whose parameters are here
     int skip;             // SE op folded into the previous conv
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
+    float *d_par;         // device copy (v3 kernel)
+    float *d_se_b1;       // v3 fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
 };
 
 struct gaz_net {
@@ -629,6 +643,7 @@ struct gaz_net {
     int base_offset_mode;  // GAZ_DESC_BASE_OFFSET (default 0, see gaz_conv.cuh)
     int fuse_se;           // GAZ_FUSE_SE (default 1)
     int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
+    int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
     std::vector<cudaEvent_t> ev;
     size_t ev_used;
     std::vector<int> ev_op;
@@ -689,6 +704,16 @@ template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_
     return 0;
 }
 
+static int launch_conv_t(gaz_net *n, NetOp &op, const gaz_conv::BoardConvArgs &a, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CKN(cudaFuncSetAttribute(gaz_convt::conv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_convt::TCfg::SMEM));
+        attr_set = true;
+    }
+    gaz_convt::conv_t_kernel<<<n->n_sm, 640, gaz_convt::TCfg::SMEM, s>>>(op.tmA2, op.tmWt, op.tmOta, op.tmOtb, a, op.d.cout);
+    return 0;
+}
+
 static const float *wfp(gaz_net *n, int64_t off) { return off < 0 ? nullptr : n->wf + off; }
 
 static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, float *policy, float *value, cudaStream_t s) {
@@ -701,7 +726,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         case GAZ_OP_STEM: {
             StemArgs a;
             a.count = count; a.max_count = n->max_batch; a.states = states;
-            a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize; a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act;
+            a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize; a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act; a.layout = n->conv_t;
             a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.scale = wfp(n, d.scale_b); a.shift = wfp(n, d.shift_b);
             a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
             a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
@@ -738,13 +763,17 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->base_offset_mode;
                 const gaz_net_op &o = op.fused_se ? op.se : d; // outputs / residual of the fused SE op
                 memcpy(a.par, op.par, sizeof a.par);
+                a.d_par = op.d_par;
                 a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
                 a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.out_b = (__nv_bfloat16 *)buf(o.out_b);
                 if (op.fused_se) {
                     a.se = 1; a.se_r = op.se.cin; a.n_cells = n->H * n->W;
                     a.se_w1 = wfp(n, op.se.w2); a.se_b1 = wfp(n, op.se.bias2); a.se_w2 = wfp(n, op.se.w3); a.se_b2 = wfp(n, op.se.bias3);
+                    a.se_b1 = op.d_se_b1; // conv bias folded into the dense1 bias (b1 + W1^T bias)
                 }
-                rc = d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
+                if (n->conv_t && d.cout >= 64) rc = launch_conv_t(n, op, a, s);
+                else if (n->conv_t && (a.res || a.out_raw)) rc = gaz_fail("conv_tc cout %d with fp32 tensors needs the v3 kernel", d.cout);
+                else rc = d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
                      : d.cout == 32 ? launch_conv_board<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
             }
             if (rc != 0) return rc;
@@ -755,7 +784,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             if (op.skip) break;
             SeArgs a;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.C = d.cout; a.R = d.cin;
-            a.P_pad = n->P_pad; a.Wp = n->Wp;
+            a.P_pad = n->P_pad; a.Wp = n->Wp; a.layout = n->conv_t;
             a.c2 = (const float *)buf(d.in_buf); a.res = (const float *)buf(d.res_buf);
             a.w1 = wfp(n, d.w2); a.b1 = wfp(n, d.bias2); a.w2 = wfp(n, d.w3); a.b2 = wfp(n, d.bias3);
             a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.out_b = (__nv_bfloat16 *)buf(d.out_b);
@@ -767,7 +796,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         case GAZ_OP_HEADCONV: {
             HeadConvArgs a;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize;
-            a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32;
+            a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32; a.layout = n->conv_t;
             a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
             size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
             const int cpl = d.cin / 32;
@@ -847,6 +876,9 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         n->fuse_se = e3 ? atoi(e3) : 1;
         const char *e4 = getenv("GAZ_CONV_PAIR");
         n->conv_pair = e4 ? atoi(e4) : 1;
+        const char *e5 = getenv("GAZ_CONV_T");
+        n->conv_t = e5 ? atoi(e5) : 0;
+        if (n->conv_v1) n->conv_t = 0;
     }
     n->profile = 0;
     n->ev_used = 0;
@@ -892,6 +924,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         memset(&op.tmB2, 0, sizeof op.tmB2);
         op.fused_se = 0;
         op.skip = 0;
+        op.d_par = nullptr;
+        op.d_se_b1 = nullptr;
         memset(&op.se, 0, sizeof op.se);
         const gaz_net_op &d = op.d;
         if (d.type == GAZ_OP_CONV_TC) {
@@ -917,7 +951,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         if (d.type == GAZ_OP_SE && !n->conv_v1 && n->fuse_se && n->P_pad == gaz_conv::TILE_ROWS && !n->ops.empty()) {
             NetOp &prev = n->ops.back();
             if (prev.d.type == GAZ_OP_CONV_TC && prev.d.out_raw == d.in_buf && prev.d.out_a < 0 && prev.d.out_b < 0 &&
-                prev.d.res_buf < 0 && prev.d.cout == d.cout && d.cout <= 128 && d.cin <= d.cout) {
+                prev.d.res_buf < 0 && prev.d.cout == d.cout && d.cout == 128 && d.cin <= d.cout) {
                 prev.fused_se = 1;
                 prev.se = d;
                 op.skip = 1;
@@ -930,6 +964,10 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         const gaz_net_op &o = op.fused_se ? op.se : op.d;
         memset(&op.tmOa, 0, sizeof op.tmOa);
         memset(&op.tmOb, 0, sizeof op.tmOb);
+        memset(&op.tmOta, 0, sizeof op.tmOta);
+        memset(&op.tmOtb, 0, sizeof op.tmOtb);
+        if (make_map(enc, &op.tmWt, n->wh + op.d.w, (uint64_t)op.d.ksize * op.d.ksize * op.d.cin, (uint64_t)op.d.cout,
+                     (uint32_t)(op.d.cout < 128 ? op.d.cout : 128)) != 0) { gaz_net_destroy(n); return -1; }
         for (int k = 0; k < 2; k++) {
             const int id = k == 0 ? o.out_a : o.out_b;
             if (id < 0) continue;
@@ -937,12 +975,27 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             if (ob.kind != GAZ_BUF_ROWS_BF16 || ob.width != op.d.cout) { gaz_net_destroy(n); return gaz_fail("conv_tc output buffer must be bf16 rows of width cout"); }
             if (make_map_ex(enc, k == 0 ? &op.tmOa : &op.tmOb, ob.ptr, (uint64_t)ob.width, (uint64_t)n->rows_alloc, 32, 32,
                             CU_TENSOR_MAP_SWIZZLE_64B) != 0) { gaz_net_destroy(n); return -1; }
+            if (make_map_ex(enc, k == 0 ? &op.tmOta : &op.tmOtb, ob.ptr, (uint64_t)ob.width, (uint64_t)n->rows_alloc, 32, 16,
+                            CU_TENSOR_MAP_SWIZZLE_NONE) != 0) { gaz_net_destroy(n); return -1; }
         }
         const int64_t offs[5] = {op.d.bias, o.scale_a, o.shift_a, o.scale_b, o.shift_b};
         const float dflt[5] = {0.0f, 1.0f, 0.0f, 1.0f, 0.0f};
         for (int k = 0; k < 5; k++)
             for (int c = 0; c < 128; c++)
                 op.par[k * 128 + c] = (offs[k] >= 0 && c < op.d.cout) ? desc->wf[offs[k] + c] : dflt[k];
+        if (alloc((void **)&op.d_par, sizeof op.par) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(op.d_par, op.par, sizeof op.par, cudaMemcpyHostToDevice));
+        if (op.fused_se) {
+            const int R = op.se.cin, Cc = op.d.cout;
+            std::vector<float> b1((size_t)R);
+            for (int j = 0; j < R; j++) {
+                double acc = desc->wf[op.se.bias2 + j];
+                for (int i = 0; i < Cc; i++) acc += (double)op.par[i] * (double)desc->wf[op.se.w2 + (int64_t)i * R + j];
+                b1[(size_t)j] = (float)acc;
+            }
+            if (alloc((void **)&op.d_se_b1, (size_t)R * 4) != 0) { gaz_net_destroy(n); return -1; }
+            CKN(cudaMemcpy(op.d_se_b1, b1.data(), (size_t)R * 4, cudaMemcpyHostToDevice));
+        }
     }
     CKN(cudaDeviceSynchronize());
     *out = n;
@@ -953,6 +1006,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
+    for (auto &op : n->ops) { if (op.d_par) cudaFree(op.d_par); if (op.d_se_b1) cudaFree(op.d_se_b1); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);

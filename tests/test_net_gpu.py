@@ -95,3 +95,13 @@ def test_closed_loop_search_with_cuda_net_is_bit_exact(game, over, iters):
         np.testing.assert_array_equal(st["values"].view(np.uint32), ref["values"].view(np.uint32))
     eng.close()
     net.close()
+
+
+@pytest.mark.parametrize("env", [{"GAZ_CONV_T": "1"}, {"GAZ_CONV_PAIR": "0"}], ids=["transposed-v3", "single-cta"])
+def test_alternative_conv_kernels_stay_within_tolerance(env, monkeypatch):
+    """the experimental channel-on-lanes kernel (gaz_convt.cuh) and the single-CTA form of the board kernel are
+    selected by environment switches read at network creation; both must meet the same tolerance"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_net_matches_fp32_oracle("gomoku", "softmax", dict(num_blocks=2, use_se=True), 9)
+    test_net_matches_fp32_oracle("connect4", "softmax", {}, 70)
