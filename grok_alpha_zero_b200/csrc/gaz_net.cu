@@ -487,6 +487,73 @@ __global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
     }
 }
 
+// Head convolutions on a 32-channel bf16 row tensor (Gomoku policy_conv1 3x3 32->8, value_conv1 1x1 32->4): one CTA
+// stages a whole board (+ halo rows) in shared memory with coalesced 16-byte loads, then every warp walks cells with
+// lane = input channel, weights in registers and the halving butterfly of headconv_warp_kernel.  Compared with the
+// per-cell global loads of headconv_warp_kernel the 9-fold re-read of the input moves from L2 to shared memory.
+template <int COUT, int K>
+__global__ void __launch_bounds__(128) headconv_board_kernel(HeadConvArgs p) {
+    constexpr int TAPS = K * K, kh = K >> 1;
+    extern __shared__ __align__(16) uint8_t s_board[]; // [(P_pad + 2 * halo)][32] bf16
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int halo = kh * (p.Wp + 1);
+    const int srows = p.P_pad + 2 * halo;
+    float w[TAPS][COUT];
+#pragma unroll
+    for (int t = 0; t < TAPS; t++)
+#pragma unroll
+        for (int co = 0; co < COUT; co++) w[t][co] = p.w[(size_t)(t * 32 + lane) * COUT + co];
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int ncell = p.H * p.W;
+    const uint4 *gin = reinterpret_cast<const uint4 *>(p.in); // 4 uint4 per 64-byte row
+    uint4 *sin = reinterpret_cast<uint4 *>(s_board);
+    for (int b = blockIdx.x; b < cnt; b += gridDim.x) {
+        __syncthreads();
+        const long long g0 = ((long long)b * p.P_pad - halo) * 4;
+        for (int i = threadIdx.x; i < srows * 4; i += blockDim.x) {
+            const long long gi = g0 + i;
+            sin[i] = (gi >= 0 && gi < p.in_rows * 4) ? gin[gi] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        const __nv_bfloat16 *sb = reinterpret_cast<const __nv_bfloat16 *>(s_board) + (size_t)halo * 32 + lane;
+        for (int cell = warp; cell < ncell; cell += 4) {
+            const int y = cell / p.W, x = cell - y * p.W;
+            const int r0 = (y + 1) * p.Wp + x;
+            float acc[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; co++) acc[co] = 0.0f;
+#pragma unroll
+            for (int t = 0; t < TAPS; t++) {
+                const float a = __bfloat162float(sb[(r0 + (t / K - kh) * p.Wp + (t % K - kh)) * 32]);
+#pragma unroll
+                for (int co = 0; co < COUT; co++) acc[co] = fmaf(a, w[t][co], acc[co]);
+            }
+            int n = COUT, co_base = 0;
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                if (n > 1) {
+                    const int h = n >> 1;
+                    const bool up = (lane & m) != 0;
+#pragma unroll
+                    for (int i = 0; i < COUT / 2; i++)
+                        if (i < h) {
+                            const float send = up ? acc[i] : acc[i + h];
+                            const float keep = up ? acc[i + h] : acc[i];
+                            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                        }
+                    co_base += up ? h : 0;
+                    n = h;
+                } else {
+                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], m);
+                }
+            }
+            constexpr int REP = 32 / COUT;
+            if ((lane & (REP - 1)) == 0) p.out[((size_t)b * ncell + cell) * COUT + co_base] = acc[0] + p.bias[co_base];
+        }
+    }
+}
+
 struct DenseArgs {
     const int32_t *count;
     int max_count, In, Out, act, pre_affine, pre_relu;
@@ -805,6 +872,15 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
 #define HC(CPL_, CO_, K_) \
     (a.in_f32 ? (void)(headconv_warp_kernel<CPL_, CO_, K_, true><<<g2, 256, 0, s>>>(a)) \
               : (void)(headconv_warp_kernel<CPL_, CO_, K_, false><<<g2, 256, 0, s>>>(a)))
+            if (d.cin == 32 && !a.in_f32 && ((d.cout == 8 && d.ksize == 3) || (d.cout == 4 && d.ksize == 1))) {
+                const int halo = (d.ksize / 2) * (n->Wp + 1);
+                const size_t smb = (size_t)(n->P_pad + 2 * halo) * 64;
+                if (smb <= 48 * 1024) {
+                    if (d.cout == 8) headconv_board_kernel<8, 3><<<n->n_sm * 8, 128, smb, s>>>(a);
+                    else headconv_board_kernel<4, 1><<<n->n_sm * 8, 128, smb, s>>>(a);
+                    break;
+                }
+            }
             if (d.cin % 32 != 0) done = false;
             else if (cpl == 1 && d.cout == 8 && d.ksize == 3) HC(1, 8, 3);
             else if (cpl == 1 && d.cout == 4 && d.ksize == 1) HC(1, 4, 1);
