@@ -262,7 +262,6 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
     launches = groups[key][1] * passes
     avg_ms = groups[key][0] / max(1.0, launches)
     flops = 2.0 * leaves_per_launch * hw * k * k * cin * cout
-    achieved = flops / (avg_ms * 1e-3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tp):
@@ -272,13 +271,25 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roof = dict(bound="tensor",
-                kernel="gaz_conv::conv_board_kernel<%d, pair> %dx%d C%d->C%d%s (tcgen05 cta_group::2 implicit GEMM)"
-                       % (cout, k, k, cin, cout, " + fused SE/skip epilogue" if tag else ""),
-                achieved=round(achieved, 2), peak=peaks["sustained"], unit="TFLOP/s", frac=round(achieved / peaks["sustained"], 4),
-                peak_source="%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
-                flops_per_launch=flops, avg_launch_ms=round(avg_ms, 4), launches_timed=int(launches),
-                share_of_conv_time=round(groups[key][0] / max(tot, 1e-9), 4), traffic=traffic, groups=detail)
+    name = ("gaz_conv::conv_board_kernel<%d, pair> %dx%d C%d->C%d%s (tcgen05 cta_group::2 implicit GEMM)"
+            % (cout, k, k, cin, cout, " + fused SE/skip epilogue" if tag else ""))
+    common = dict(kernel=name, avg_launch_ms=round(avg_ms, 4), launches_timed=int(launches),
+                  share_of_conv_time=round(groups[key][0] / max(tot, 1e-9), 4), traffic=traffic, groups=detail)
+    if tag:
+        # The fused-SE convolution also streams the fp32 residual in and out: per live cell it reads cin bf16 + cout fp32 and
+        # writes cout fp32 + cout bf16.  Arithmetic intensity = 2*9*cin*cout / that = 169 FLOP/B < the machine balance
+        # (1399 TFLOP/s / 6545 GB/s = 214 FLOP/B), so its roofline is HBM.
+        bytes_alg = leaves_per_launch * hw * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
+        achieved = bytes_alg / (avg_ms * 1e-3) / 1e9
+        roof = dict(bound="hbm", achieved=round(achieved, 1), peak=peaks["hbm"], unit="GB/s", frac=round(achieved / peaks["hbm"], 4),
+                    peak_source="%s HBM copy bandwidth" % peaks["source"], bytes_per_launch=bytes_alg,
+                    tensor_view=dict(tflops=round(flops / (avg_ms * 1e-3) / 1e12, 1), flops_per_launch=flops), **common)
+    else:
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", achieved=round(achieved, 2), peak=peaks["sustained"], unit="TFLOP/s",
+                    frac=round(achieved / peaks["sustained"], 4),
+                    peak_source="%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
+                    flops_per_launch=flops, **common)
     return roof, dict(conv_ms_total=tot, conv_launches=cnt)
 
 
