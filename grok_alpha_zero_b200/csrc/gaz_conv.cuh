@@ -74,6 +74,11 @@ struct BoardConvArgs {
     float *out_raw;           // blocked fp32 output (optional)
     __nv_bfloat16 *out_a;     // relu(scale_a * v + shift_a) as bf16 rows (optional)
     __nv_bfloat16 *out_b;
+    // dense-layer mode (heads): rows are leaves (all live), one launch per 128-wide slice of the outputs
+    int dense;                // 1: every row < valid_rows is live; the padding mask is not applied
+    int n_off;                // first output feature of this launch (row offset into the weight tensor / flat_out column)
+    float *flat_out;          // fp32 row-major [row][flat_ld] output (optional)
+    int flat_ld, flat_n;      // leading dimension and number of valid output features
     // fused Squeeze-Excitation (tile == board, P_pad == 256): dense1 [C][R], dense2 [R][C]
     int se, se_r, n_cells;
     const float *se_w1, *se_b1, *se_w2, *se_b2;
@@ -191,10 +196,10 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         mbar_wait(&b_empty[r.idx], r.phase ^ 1);
                         if (PAIR) {
                             if (rank == 0) mbar_expect_tx(&b_full[r.idx], 2 * Cfg::B_BYTES);
-                            tma_load_2d_pair(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, rank * Cfg::B_ROWS);
+                            tma_load_2d_pair(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, p.n_off + rank * Cfg::B_ROWS);
                         } else {
                             mbar_expect_tx(&b_full[r.idx], Cfg::B_BYTES);
-                            tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, 0);
+                            tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, p.n_off);
                         }
                         r.advance(NB);
                     }
@@ -260,7 +265,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const long long row = (long long)t * TILE_ROWS + sub * 128 + q * 32 + lane;
             const int pos = (int)(row % p.P_pad);
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-            const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
+            const bool live = row < valid_rows && (p.dense || (yy != 0 && xx != p.Wp - 1));
             float rnext[32]; // residual of the first output chunk: issued before the accumulator is even ready
             const bool use_res = p.res && !(dbg & 8);
             if (use_res) {
@@ -393,6 +398,12 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 const size_t blk = f32_blk_index(row, ch * 32, BN); // this lane's first piece of the 32x32 block
                 if (dbg & 4) continue; // timing experiment only: no output stores
+                if (p.flat_out && live) { // dense layers: plain row-major fp32 [leaf][features]
+                    float *fo = p.flat_out + (size_t)row * p.flat_ld + p.n_off + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (p.n_off + ch * 32 + j < p.flat_n) fo[j] = v[j];
+                }
                 if (p.out_raw && !(dbg & 16)) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {

@@ -366,6 +366,9 @@ struct HeadConvArgs {
     const float *w;     // [K*K][Cin][Cout]
     const float *bias;
     float *out;         // flat [leaf][H*W*Cout] (H,W,C order)
+    __nv_bfloat16 *out_act; // optional: relu(act_scale[f] * out + act_shift[f]) as bf16, same flat order (operand of a
+    const float *act_scale, *act_shift; // tensor-core dense layer)
+    int act_ld;         // row pitch of out_act in elements (features padded to a multiple of 8 for the TMA pitch rule)
 };
 
 // small convolutions of the heads (C_out <= 16): thread per (leaf, cell), weights in shared memory
@@ -549,7 +552,12 @@ __global__ void __launch_bounds__(128) headconv_board_kernel(HeadConvArgs p) {
                 }
             }
             constexpr int REP = 32 / COUT;
-            if ((lane & (REP - 1)) == 0) p.out[((size_t)b * ncell + cell) * COUT + co_base] = acc[0] + p.bias[co_base];
+            if ((lane & (REP - 1)) == 0) {
+                const size_t f = (size_t)cell * COUT + co_base;
+                const float vv = acc[0] + p.bias[co_base];
+                if (p.out_act) p.out_act[(size_t)b * p.act_ld + f] = __float2bfloat16_rn(fmaxf(fmaf(p.act_scale[f], vv, p.act_shift[f]), 0.0f));
+                else p.out[(size_t)b * ncell * COUT + f] = vv;
+            }
         }
     }
 }
@@ -686,6 +694,12 @@ struct NetOp {
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
     float *d_par;         // device copy (v3 kernel)
     float *d_se_b1;       // v3 fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
+    // dense layer on the tensor cores (DENSE op fed by a HEADCONV op): bf16 activated input + bf16 [Out][In] weights
+    int dense_tc;
+    __nv_bfloat16 *d_act; // [rows_dense][In]: written by the producing head convolution
+    __nv_bfloat16 *d_wt;  // [Out][In]
+    CUtensorMap tmDA, tmDW, tmDW2;
+    long long rows_dense;
 };
 
 struct gaz_net {
@@ -865,6 +879,12 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize;
             a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32; a.layout = n->conv_t;
             a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
+            a.out_act = nullptr; a.act_scale = a.act_shift = nullptr; a.act_ld = 0;
+            if (oi + 1 < n->ops.size() && n->ops[oi + 1].dense_tc) {
+                const NetOp &nx = n->ops[oi + 1];
+                a.out_act = nx.d_act; a.act_scale = wfp(n, nx.d.scale_a); a.act_shift = wfp(n, nx.d.shift_a);
+                a.act_ld = (nx.d.cin + 7) & ~7;
+            }
             size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
             const int cpl = d.cin / 32;
             const int g2 = n->n_sm * 8;
@@ -894,6 +914,24 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             break;
         }
         case GAZ_OP_DENSE: {
+            if (op.dense_tc) { // [leaf][In] bf16 x [Out][In] bf16 on the board kernel: rows = leaves, 128 outputs per launch
+                float *outp = (d.flags & 4) ? value : (float *)buf(d.out_raw);
+                for (int n0 = 0; n0 < d.cout; n0 += 128) {
+                    gaz_conv::BoardConvArgs a;
+                    memset(&a, 0, sizeof a);
+                    a.count = count; a.max_count = n->max_batch; a.P_pad = 1; a.Wp = 1;
+                    a.taps = 1; a.kpt = (d.cin + 63) / 64; a.base_offset_mode = 0;
+                    for (int c = 0; c < 128; c++) {
+                        a.par[c] = n0 + c < d.cout ? op.par[n0 + c] : 0.0f;
+                        a.par[128 + c] = 1.0f; a.par[384 + c] = 1.0f;
+                    }
+                    a.dense = 1; a.n_off = n0; a.flat_out = outp; a.flat_ld = d.cout; a.flat_n = d.cout;
+                    NetOp tmp = op; // maps: activations of this dense op, weights
+                    tmp.tmA2 = op.tmDA; tmp.tmB = op.tmDW; tmp.tmB2 = op.tmDW2;
+                    if (launch_conv_board<128>(n, tmp, a, s) != 0) return -1;
+                }
+                break;
+            }
             DenseArgs a;
             a.count = count; a.max_count = n->max_batch; a.In = d.cin; a.Out = d.cout; a.act = d.act;
             a.pre_affine = d.flags & 1; a.pre_relu = (d.flags >> 1) & 1;
@@ -1002,6 +1040,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.skip = 0;
         op.d_par = nullptr;
         op.d_se_b1 = nullptr;
+        op.dense_tc = 0; op.d_act = nullptr; op.d_wt = nullptr; op.rows_dense = 0;
         memset(&op.se, 0, sizeof op.se);
         const gaz_net_op &d = op.d;
         if (d.type == GAZ_OP_CONV_TC) {
@@ -1034,6 +1073,39 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             }
         }
         n->ops.push_back(op);
+    }
+    // dense layers fed by a head convolution and followed by nothing exotic go to the tensor cores:
+    // DENSE with pre-affine + pre-relu, Out % 128 == 0, In * 2 bytes % 16 == 0 (TMA pitch), producer = HEADCONV on bf16 rows
+    for (size_t oi = 1; oi < n->ops.size(); oi++) {
+        NetOp &op = n->ops[oi];
+        const gaz_net_op &d = op.d;
+        const char *etc = getenv("GAZ_DENSE_TC");
+        if (etc && atoi(etc) == 0) break;
+        if (d.type != GAZ_OP_DENSE || (d.flags & 3) != 3 || (d.flags & 4) || d.act != GAZ_ACT_NONE) continue;
+        const NetOp &pr = n->ops[oi - 1];
+        if (pr.d.type != GAZ_OP_HEADCONV || pr.d.out_raw != d.in_buf || pr.d.cin != 32) continue;
+        if (n->bufs[(size_t)pr.d.in_buf].kind != GAZ_BUF_ROWS_BF16) continue;
+        if (d.cout % 128 != 0 || d.cout > 640 || d.cin > 4096) continue;
+        const int in_pad = (d.cin + 7) & ~7; // TMA row pitch must be a multiple of 16 bytes
+        if (!((pr.d.cout == 8 && pr.d.ksize == 3) || (pr.d.cout == 4 && pr.d.ksize == 1))) continue; // headconv_board_kernel shapes
+        op.rows_dense = (((long long)n->max_batch + 255) / 256) * 256;
+        if (alloc((void **)&op.d_act, (size_t)op.rows_dense * in_pad * 2) != 0) { gaz_net_destroy(n); return -1; }
+        std::vector<uint16_t> wt((size_t)d.cout * in_pad, (uint16_t)0);
+        for (int i = 0; i < d.cin; i++)
+            for (int o = 0; o < d.cout; o++) {
+                float f = desc->wf[d.w + (int64_t)i * d.cout + o];
+                uint32_t u; memcpy(&u, &f, 4);
+                u = (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;      // round to nearest even bf16
+                wt[(size_t)o * in_pad + i] = (uint16_t)u;
+            }
+        if (alloc((void **)&op.d_wt, wt.size() * 2) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(op.d_wt, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        if (make_map(enc, &op.tmDA, op.d_act, (uint64_t)in_pad, (uint64_t)op.rows_dense, gaz_conv::SLAB_BOX_ROWS) != 0 ||
+            make_map(enc, &op.tmDW, op.d_wt, (uint64_t)in_pad, (uint64_t)d.cout, 128) != 0 ||
+            make_map(enc, &op.tmDW2, op.d_wt, (uint64_t)in_pad, (uint64_t)d.cout, 64) != 0) { gaz_net_destroy(n); return -1; }
+        for (int c = 0; c < 640; c++) op.par[c] = 0.0f;
+        for (int o = 0; o < d.cout && o < 640; o++) op.par[o] = desc->wf[d.bias + o]; // bias of up to 640 outputs
+        op.dense_tc = 1;
     }
     for (auto &op : n->ops) { // per-channel epilogue parameters of the tensor-core convolutions (host copies)
         if (op.d.type != GAZ_OP_CONV_TC) continue;
@@ -1082,7 +1154,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    for (auto &op : n->ops) { if (op.d_par) cudaFree(op.d_par); if (op.d_se_b1) cudaFree(op.d_se_b1); }
+    for (auto &op : n->ops) { if (op.d_par) cudaFree(op.d_par); if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
