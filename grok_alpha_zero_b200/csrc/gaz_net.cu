@@ -227,6 +227,12 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
     constexpr int TAPS_CIN = K * K * CIN;
     constexpr int kh = K >> 1;
     __shared__ float s_in[18 * 18 * CIN]; // board with a zero border of kh cells, as floats: no bounds checks, no I2F
+    // CIN == 2 (Gomoku, TicTacToe): plane 0 is the constant side-to-move plane (Gomoku.py:173-177), so its contribution is
+    // s0 * (sum of the plane-0 weights of the in-bounds taps), which depends only on how close the cell is to each
+    // border: (2*kh+1)^2 classes.  The table replaces K*K broadcast loads + FMAs per row by one.
+    constexpr int NCLS = (2 * kh + 1);
+    extern __shared__ float s_tab[]; // [NCLS*NCLS][Cout] when the table form is used
+    const bool use_tab = CIN == 2 && p.H >= NCLS && p.W >= NCLS; // a cell is near at most one border per axis
     const int pitch = (p.W + 2 * kh) * CIN;
     const int npad = (p.H + 2 * kh) * pitch;
     const int cpr = p.Cout >> 2;                 // threads per row
@@ -246,6 +252,21 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
     const int n_boards_pad = (int)((total_rows + p.P_pad - 1) / p.P_pad);
     const int nin = p.H * p.W * CIN;
     for (int i = threadIdx.x; i < npad; i += blockDim.x) s_in[i] = 0.0f;
+    if (use_tab) {
+        for (int i = threadIdx.x; i < NCLS * NCLS * p.Cout; i += blockDim.x) {
+            const int cls = i / p.Cout, ch = i - cls * p.Cout;
+            const int cy = cls / NCLS, cx = cls - cy * NCLS; // distance class: 0..kh-1 = that many cells from the top/left border,
+            float sum = 0.0f;                                 // kh = interior, kh+1..2kh = (2kh - class) cells from the bottom/right
+            for (int ky = 0; ky < K; ky++)
+                for (int kx = 0; kx < K; kx++) {
+                    const int dy = ky - kh, dx = kx - kh;
+                    const bool oky = cy < kh ? dy >= -cy : (cy > kh ? dy <= 2 * kh - cy : true);
+                    const bool okx = cx < kh ? dx >= -cx : (cx > kh ? dx <= 2 * kh - cx : true);
+                    if (oky && okx) sum += p.w[(size_t)((ky * K + kx) * CIN) * p.Cout + ch];
+                }
+            s_tab[i] = sum;
+        }
+    }
     for (int b = blockIdx.x; b < n_boards_pad; b += gridDim.x) {
         __syncthreads();
         if (b < cnt)
@@ -263,18 +284,37 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live) {
                 const float *wp0 = s_in + yy * pitch + xx * CIN; // top-left of the receptive field (padded coords)
+                if (use_tab) {
+                    const int cy = yy < kh ? yy : (yy >= p.H - kh ? 2 * kh - (p.H - 1 - yy) : kh);
+                    const int cx = xx < kh ? xx : (xx >= p.W - kh ? 2 * kh - (p.W - 1 - xx) : kh);
+                    const float s0 = wp0[kh * pitch + kh * CIN];   // plane 0 at the cell itself (constant over the board)
+                    const float4 t4 = *reinterpret_cast<const float4 *>(s_tab + (size_t)(cy * NCLS + cx) * p.Cout + c0);
+                    acc.x = s0 * t4.x; acc.y = s0 * t4.y; acc.z = s0 * t4.z; acc.w = s0 * t4.w;
 #pragma unroll
-                for (int ky = 0; ky < K; ky++) {
-                    const float *wp = wp0 + ky * pitch;
+                    for (int ky = 0; ky < K; ky++)
 #pragma unroll
-                    for (int kx = 0; kx < K; kx++)
-#pragma unroll
-                        for (int ci = 0; ci < CIN; ci++) {
-                            const float fs = wp[kx * CIN + ci]; // warp-uniform broadcast load
-                            const float4 ww = w[(ky * K + kx) * CIN + ci];
-                            acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
-                            acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
+                        for (int kx = 0; kx < K; kx++) {
+                            const float fs = wp0[ky * pitch + kx * CIN + 1]; // the stone plane: mostly zeros, warp-uniform
+                            if (fs != 0.0f) {
+                                const float4 ww = w[(ky * K + kx) * CIN + 1];
+                                acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
+                                acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
+                            }
                         }
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < K; ky++) {
+                        const float *wp = wp0 + ky * pitch;
+#pragma unroll
+                        for (int kx = 0; kx < K; kx++)
+#pragma unroll
+                            for (int ci = 0; ci < CIN; ci++) {
+                                const float fs = wp[kx * CIN + ci]; // warp-uniform broadcast load
+                                const float4 ww = w[(ky * K + kx) * CIN + ci];
+                                acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
+                                acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
+                            }
+                    }
                 }
             }
             float v[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
@@ -816,9 +856,10 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 return gaz_fail("stem shape unsupported (cin %d cout %d)", d.cin, d.cout);
             int grid = n->n_sm * 4;
             (void)tc;
-            if (d.ksize == 3 && d.cin == 2) stem_kernel<3, 2><<<grid, 256, 0, s>>>(a);        // Gomoku
+            const size_t tab = d.cin == 2 ? (size_t)d.ksize * d.ksize * d.cout * 4 : 0; // (2*kh+1)^2 classes x Cout floats
+            if (d.ksize == 3 && d.cin == 2) stem_kernel<3, 2><<<grid, 256, tab, s>>>(a);        // Gomoku
             else if (d.ksize == 3 && d.cin == 4) stem_kernel<3, 4><<<grid, 256, 0, s>>>(a);   // Connect4
-            else if (d.ksize == 5 && d.cin == 2) stem_kernel<5, 2><<<grid, 256, 0, s>>>(a);   // TicTacToe
+            else if (d.ksize == 5 && d.cin == 2) stem_kernel<5, 2><<<grid, 256, tab, s>>>(a);   // TicTacToe
             else return gaz_fail("stem k=%d cin=%d unsupported", d.ksize, d.cin);
             break;
         }
