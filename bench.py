@@ -249,47 +249,67 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
     n_tc_ops = sum(g[1] for g in groups.values())
     passes = cnt / max(1, n_tc_ops)
     hw = sb.spec["H"] * sb.spec["W"]
+
+    def label(cin, cout, k, tag):
+        if tag.startswith("block"):
+            return "residual block 2x(3x3 C%d->C%d)%s" % (cin, cout, "+SE+skip" if "se" in tag else "+skip")
+        return "%dx%d C%d->C%d%s" % (k, k, cin, cout, "+SE" if tag == "se" else "")
+
+    def work(cin, cout, k, tag):
+        """algorithmic (FLOPs, HBM bytes over live cells) of one launch"""
+        cells = leaves_per_launch * hw
+        conv = 2.0 * cells * k * k * cin * cout
+        if tag.startswith("block"):   # two convolutions; in: bf16 operand + fp32 residual, out: fp32 residual + bf16 operand
+            return 2.0 * conv, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
+        if tag == "se":
+            return conv, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
+        return conv, cells * (cin * 2 + cout * 2)
+
     detail = {}
     for (cin, cout, k, tag), (ms, nops) in groups.items():
         launches = nops * passes
         avg_ms = ms / max(1.0, launches)
-        flops = 2.0 * leaves_per_launch * hw * k * k * cin * cout
-        detail["%dx%d C%d->C%d%s" % (k, k, cin, cout, "+SE" if tag else "")] = dict(
-            launches=int(launches), avg_launch_ms=round(avg_ms, 4), tflops=round(flops / (avg_ms * 1e-3) / 1e12, 1),
-            share_of_conv_time=round(ms / max(tot, 1e-9), 4))
+        fl, _ = work(cin, cout, k, tag)
+        detail[label(cin, cout, k, tag)] = dict(launches=int(launches), avg_launch_ms=round(avg_ms, 4),
+                                                tflops=round(fl / (avg_ms * 1e-3) / 1e12, 1),
+                                                share_of_conv_time=round(ms / max(tot, 1e-9), 4))
     key = max(groups, key=lambda g: groups[g][0])
     cin, cout, k, tag = key
     launches = groups[key][1] * passes
     avg_ms = groups[key][0] / max(1.0, launches)
-    flops = 2.0 * leaves_per_launch * hw * k * k * cin * cout
+    flops, bytes_alg = work(cin, cout, k, tag)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tp):
         try:
-            t = json.load(open(tp)).get("%dx%d_C%d_C%d%s" % (k, k, cin, cout, "_se" if tag else ""))
+            tkey = "block_3x3_C%d_C%d" % (cin, cout) if tag.startswith("block") else "%dx%d_C%d_C%d%s" % (k, k, cin, cout, "_se" if tag else "")
+            t = json.load(open(tp)).get(tkey)
             if t and t.get("leaves") == int(round(leaves_per_launch)):
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    name = ("gaz_conv::conv_board_kernel<%d, pair> %dx%d C%d->C%d%s (tcgen05 cta_group::2 implicit GEMM)"
-            % (cout, k, k, cin, cout, " + fused SE/skip epilogue" if tag else ""))
+    if tag.startswith("block"):
+        name = "gaz_block::res_block_kernel (conv1 -> SMEM -> conv2 + SE + skip, tcgen05 cta_group::2 implicit GEMMs)"
+    else:
+        name = ("gaz_conv::conv_board_kernel<%d, pair> %dx%d C%d->C%d%s (tcgen05 cta_group::2 implicit GEMM)"
+                % (cout, k, k, cin, cout, " + fused SE/skip epilogue" if tag else ""))
     common = dict(kernel=name, avg_launch_ms=round(avg_ms, 4), launches_timed=int(launches),
                   share_of_conv_time=round(groups[key][0] / max(tot, 1e-9), 4), traffic=traffic, groups=detail)
-    if tag:
-        # The fused-SE convolution also streams the fp32 residual in and out: per live cell it reads cin bf16 + cout fp32 and
-        # writes cout fp32 + cout bf16.  Arithmetic intensity = 2*9*cin*cout / that = 169 FLOP/B < the machine balance
-        # (1399 TFLOP/s / 6545 GB/s = 214 FLOP/B), so its roofline is HBM.
-        bytes_alg = leaves_per_launch * hw * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
+    # the bound follows the arithmetic intensity: machine balance = sustained bf16 peak / HBM copy bandwidth
+    balance = peaks["sustained"] * 1e12 / (peaks["hbm"] * 1e9)
+    if flops / bytes_alg < balance:
         achieved = bytes_alg / (avg_ms * 1e-3) / 1e9
         roof = dict(bound="hbm", achieved=round(achieved, 1), peak=peaks["hbm"], unit="GB/s", frac=round(achieved / peaks["hbm"], 4),
                     peak_source="%s HBM copy bandwidth" % peaks["source"], bytes_per_launch=bytes_alg,
+                    intensity_flop_per_byte=round(flops / bytes_alg, 1), machine_balance=round(balance, 1),
                     tensor_view=dict(tflops=round(flops / (avg_ms * 1e-3) / 1e12, 1), flops_per_launch=flops), **common)
     else:
         achieved = flops / (avg_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", achieved=round(achieved, 2), peak=peaks["sustained"], unit="TFLOP/s",
                     frac=round(achieved / peaks["sustained"], 4),
                     peak_source="%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
-                    flops_per_launch=flops, **common)
+                    flops_per_launch=flops, bytes_per_launch=bytes_alg, intensity_flop_per_byte=round(flops / bytes_alg, 1),
+                    machine_balance=round(balance, 1), **common)
     return roof, dict(conv_ms_total=tot, conv_launches=cnt)
 
 

@@ -16,6 +16,7 @@
 #include "gaz_tc.cuh"
 #include "gaz_conv.cuh"
 #include "gaz_convt.cuh"
+#include "gaz_block.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -731,6 +732,8 @@ struct NetOp {
     int fused_se;         // this conv carries the following SE op in its epilogue
     gaz_net_op se;        // ... whose parameters are here
     int skip;             // SE op folded into the previous conv
+    int block_fused;      // this conv1 runs the whole residual block (gaz_block.cuh) together with the next conv (+SE)
+    int in_block;         // this conv2 is executed by the previous op's fused block kernel
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
     float *d_par;         // device copy (v3 kernel)
     float *d_se_b1;       // v3 fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
@@ -764,6 +767,7 @@ struct gaz_net {
     int base_offset_mode;  // GAZ_DESC_BASE_OFFSET (default 0, see gaz_conv.cuh)
     int fuse_se;           // GAZ_FUSE_SE (default 1)
     int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
+    int fuse_block;        // GAZ_FUSE_BLOCK (default 1): conv1 + conv2 + SE of a residual block in one kernel (gaz_block.cuh)
     int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
     std::vector<cudaEvent_t> ev;
     size_t ev_used;
@@ -825,6 +829,40 @@ template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_
     return 0;
 }
 
+static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *count, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CKN(cudaFuncSetAttribute(gaz_block::res_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_block::Cfg::SMEM));
+        attr_set = true;
+    }
+    auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
+    gaz_block::BlockArgs a;
+    memset(&a, 0, sizeof a);
+    a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.n_cells = n->H * n->W; a.dbg = n->base_offset_mode;
+    memcpy(a.par1, c1.par, sizeof a.par1);   // conv1 bias | BN2 scale | BN2 shift
+    memcpy(a.par2, c2.par, sizeof a.par2);
+    const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
+    a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
+    a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.out_b = (__nv_bfloat16 *)buf(o.out_b);
+    if (c2.fused_se) {
+        a.se = 1; a.se_r = c2.se.cin;
+        a.se_w1 = n->wf + c2.se.w2; a.se_b1 = c2.d_se_b1; a.se_w2 = n->wf + c2.se.w3; a.se_b2 = n->wf + c2.se.bias3;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(n->n_sm & ~1), 1, 1);
+    cfg.blockDim = dim3(512, 1, 1);
+    cfg.dynamicSmemBytes = gaz_block::Cfg::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CKN(cudaLaunchKernelEx(&cfg, gaz_block::res_block_kernel, c1.tmA2, c1.tmB2, c2.tmB2, c2.tmOa, c2.tmOb, a));
+    return 0;
+}
+
 static int launch_conv_t(gaz_net *n, NetOp &op, const gaz_conv::BoardConvArgs &a, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -864,12 +902,15 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             break;
         }
         case GAZ_OP_CONV_TC: {
+            if (op.in_block) break; // executed by the previous op's block kernel
             if (n->profile && n->ev_used + 2 <= n->ev.size()) {
                 n->ev_op.push_back((int)oi);
                 CKN(cudaEventRecord(n->ev[n->ev_used++], s));
             }
             int rc;
-            if (n->conv_v1) {
+            if (op.block_fused) {
+                rc = launch_res_block(n, op, n->ops[oi + 1], count, s);
+            } else if (n->conv_v1) {
                 ConvArgs a;
                 a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
                 a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64;
@@ -1034,6 +1075,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         const char *e5 = getenv("GAZ_CONV_T");
         n->conv_t = e5 ? atoi(e5) : 0;
         if (n->conv_v1) n->conv_t = 0;
+        const char *e6 = getenv("GAZ_FUSE_BLOCK");
+        n->fuse_block = e6 ? atoi(e6) : 1;
     }
     n->profile = 0;
     n->ev_used = 0;
@@ -1079,6 +1122,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         memset(&op.tmB2, 0, sizeof op.tmB2);
         op.fused_se = 0;
         op.skip = 0;
+        op.block_fused = 0;
+        op.in_block = 0;
         op.d_par = nullptr;
         op.d_se_b1 = nullptr;
         op.dense_tc = 0; op.d_act = nullptr; op.d_wt = nullptr; op.rows_dense = 0;
@@ -1184,6 +1229,18 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             }
             if (alloc((void **)&op.d_se_b1, (size_t)R * 4) != 0) { gaz_net_destroy(n); return -1; }
             CKN(cudaMemcpy(op.d_se_b1, b1.data(), (size_t)R * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    // whole-block fusion: conv1 (3x3 C128->C128, bf16 out only) directly followed by conv2 (3x3 C128->C128 reading it)
+    if (n->fuse_block && n->conv_pair && !n->conv_t && !n->conv_v1 && n->P_pad == gaz_conv::TILE_ROWS && (n->n_sm & ~1) >= 2) {
+        for (size_t oi = 0; oi + 1 < n->ops.size(); oi++) {
+            NetOp &c1 = n->ops[oi], &c2 = n->ops[oi + 1];
+            if (c1.d.type != GAZ_OP_CONV_TC || c2.d.type != GAZ_OP_CONV_TC || c1.block_fused || c1.in_block) continue;
+            if (c1.d.cin != 128 || c1.d.cout != 128 || c1.d.ksize != 3 || c2.d.cin != 128 || c2.d.cout != 128 || c2.d.ksize != 3) continue;
+            if (c1.d.out_a < 0 || c1.d.out_b >= 0 || c1.d.out_raw >= 0 || c1.d.res_buf >= 0 || c1.fused_se) continue;
+            if (c2.d.in_buf != c1.d.out_a) continue;
+            c1.block_fused = 1;
+            c2.in_block = 1;
         }
     }
     CKN(cudaDeviceSynchronize());

@@ -228,14 +228,28 @@ class Net:
         self.n_ops = len(b.ops)
         self.n_conv_tc = sum(1 for o in b.ops if o["type"] == OP_CONV_TC)
         self.conv_shapes = [(o["cin"], o["cout"], o["ksize"]) for o in b.ops if o["type"] == OP_CONV_TC]
-        # (type, cin, cout, ksize, tag): tag "se" = convolution whose epilogue carries the following SE op
+        # (type, cin, cout, ksize, tag): tag "se" = convolution whose epilogue carries the following SE op; "block" = conv1
+        # that runs the whole residual block (conv1 + conv2 + SE + skip, gaz_block.cuh) and "inblock" = the conv2 it absorbed.
+        # Mirrors the fusion rules of gaz_net_create (csrc/gaz_net.cu).
+        import os
+        tile_is_board = (spec["H"] + 1) * (spec["W"] + 1) == 256
+        fuse_block = os.environ.get("GAZ_FUSE_BLOCK", "1") != "0" and os.environ.get("GAZ_CONV_PAIR", "1") != "0" and \
+            os.environ.get("GAZ_CONV_T", "0") == "0" and os.environ.get("GAZ_CONV_V1", "0") == "0"
         self._op_shapes = []
         for i, o in enumerate(b.ops):
             tag = ""
-            if o["type"] == OP_CONV_TC and i + 1 < len(b.ops) and b.ops[i + 1]["type"] == OP_SE and \
-                    (spec["H"] + 1) * (spec["W"] + 1) == 256:
+            if o["type"] == OP_CONV_TC and i + 1 < len(b.ops) and b.ops[i + 1]["type"] == OP_SE and tile_is_board:
                 tag = "se"
-            self._op_shapes.append((o["type"], o["cin"], o["cout"], o["ksize"], tag))
+            self._op_shapes.append([o["type"], o["cin"], o["cout"], o["ksize"], tag])
+        if tile_is_board and fuse_block:
+            for i in range(len(b.ops) - 1):
+                o, o2 = b.ops[i], b.ops[i + 1]
+                if o["type"] == OP_CONV_TC and o2["type"] == OP_CONV_TC and (o["cin"], o["cout"], o["ksize"]) == (128, 128, 3) and \
+                        (o2["cin"], o2["cout"], o2["ksize"]) == (128, 128, 3) and o["out_a"] >= 0 and o["out_b"] < 0 and \
+                        o["out_raw"] < 0 and o["res_buf"] < 0 and o2["in_buf"] == o["out_a"] and self._op_shapes[i][4] == "":
+                    self._op_shapes[i][4] = "block+" + self._op_shapes[i + 1][4]
+                    self._op_shapes[i + 1][4] = "inblock"
+        self._op_shapes = [tuple(x) for x in self._op_shapes]
         bufs = (GazNetBuf * len(b.bufs))(*[GazNetBuf(k, w) for k, w in b.bufs])
         ops = (GazNetOp * len(b.ops))(*[GazNetOp(**o) for o in b.ops])
         wf = np.concatenate(b.wf) if b.wf else np.zeros(4, np.float32)
