@@ -341,6 +341,7 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     e->bytes = 0;
     e->net = nullptr;
     e->leaf_bound = 0;
+    e->round_graph = nullptr; e->round_graph_net = nullptr; e->round_graph_chunks = 0; e->round_graph_warm = 0;
     View &v = e->v;
     memset(&v, 0, sizeof v);
     v.game = cfg->game;
@@ -414,6 +415,7 @@ void gaz_destroy(gaz_engine *e) {
     if (!e) return;
 #ifndef GAZ_EMUL
     cudaStreamSynchronize(e->stream);
+    if (e->round_graph) cudaGraphExecDestroy((cudaGraphExec_t)e->round_graph);
 #endif
     for (void *p : e->allocs) dev_free(p);
 #ifndef GAZ_EMUL

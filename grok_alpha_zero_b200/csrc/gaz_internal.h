@@ -55,6 +55,10 @@ struct gaz_engine {
     std::vector<void *> allocs;
     struct gaz_net *net; // attached evaluator (gaz_net.cu) or null
     int leaf_bound;      // host-side upper bound of outstanding leaf requests (0 = n_trees)
+    // CUDA graph of one search round (select -> network -> expand), built by gaz_net.cu on first use
+    void *round_graph;   // cudaGraphExec_t
+    void *round_graph_net;
+    int round_graph_chunks, round_graph_warm;
     int32_t *d_limits;   // [n_trees]
     int16_t *d_actions;  // [n_trees]
     uint8_t *d_mask;     // [n_trees]

@@ -767,6 +767,7 @@ struct gaz_net {
     int base_offset_mode;  // GAZ_DESC_BASE_OFFSET (default 0, see gaz_conv.cuh)
     int fuse_se;           // GAZ_FUSE_SE (default 1)
     int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
+    int use_graph;         // GAZ_GRAPH (default 1): replay a captured CUDA graph per search round
     int fuse_block;        // GAZ_FUSE_BLOCK (default 1): conv1 + conv2 + SE of a residual block in one kernel (gaz_block.cuh)
     int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
     std::vector<cudaEvent_t> ev;
@@ -1072,6 +1073,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         n->fuse_se = e3 ? atoi(e3) : 1;
         const char *e4 = getenv("GAZ_CONV_PAIR");
         n->conv_pair = e4 ? atoi(e4) : 1;
+        const char *e7 = getenv("GAZ_GRAPH");
+        n->use_graph = e7 ? atoi(e7) : 1;
         const char *e5 = getenv("GAZ_CONV_T");
         n->conv_t = e5 ? atoi(e5) : 0;
         if (n->conv_v1) n->conv_t = 0;
@@ -1281,6 +1284,8 @@ int gaz_attach_net(gaz_engine *e, gaz_net *n) {
         if (n->game != e->cfg.game) return gaz_fail("network game %d != engine game %d", n->game, e->cfg.game);
     }
     e->net = n;
+    if (e->round_graph) { cudaGraphExecDestroy((cudaGraphExec_t)e->round_graph); e->round_graph = nullptr; }
+    e->round_graph_warm = 0;
     return 0;
 }
 
@@ -1307,13 +1312,51 @@ int gaz_eval_net(gaz_engine *e) {
     return engine_forward(e);
 }
 
+static int one_round_eager(gaz_engine *e) {
+    if (gaz_internal_launch_select(e) != 0) return -1;
+    if (engine_forward(e) != 0) return -1;
+    return gaz_internal_launch_expand(e);
+}
+
+// n_rounds x (select -> network -> expand).  One round is ~30-45 kernel launches; for small networks (TicTacToe: 0.2 ms of
+// GPU work per round) the launch path is the bottleneck, so the round is captured once into a CUDA graph and replayed.
+// Every kernel reads its leaf count from device memory, so the graph does not depend on the data; it is rebuilt when
+// the number of forward chunks or the attached network changes.  Disabled while conv launches are being event-timed.
+static int run_rounds(gaz_engine *e, int n_rounds) {
+    gaz_net *n = e->net;
+    const bool use_graph = n->use_graph && !n->profile;
+    for (int r = 0; r < n_rounds; r++) {
+        if (!use_graph) { if (one_round_eager(e) != 0) return -1; continue; }
+        const int bound = e->leaf_bound > 0 ? e->leaf_bound : e->v.n_trees;
+        const int chunks = (bound + n->max_batch - 1) / n->max_batch;
+        if (!e->round_graph || e->round_graph_chunks != chunks || e->round_graph_net != (void *)n) {
+            if (e->round_graph_warm < 1) { // first round eagerly: one-time function attributes are set outside a capture
+                if (one_round_eager(e) != 0) return -1;
+                e->round_graph_warm = 1;
+                continue;
+            }
+            if (e->round_graph) { cudaGraphExecDestroy((cudaGraphExec_t)e->round_graph); e->round_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            CKN(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = one_round_eager(e);
+            cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+            if (rc != 0 || ce != cudaSuccess || !g) return gaz_fail("CUDA graph capture of a search round failed (%s)", cudaGetErrorString(ce));
+            cudaGraphExec_t ex = nullptr;
+            ce = cudaGraphInstantiate(&ex, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return gaz_fail("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+            e->round_graph = (void *)ex;
+            e->round_graph_chunks = chunks;
+            e->round_graph_net = (void *)n;
+        }
+        CKN(cudaGraphLaunch((cudaGraphExec_t)e->round_graph, e->stream));
+    }
+    return 0;
+}
+
 int gaz_rounds_net(gaz_engine *e, int n_rounds) {
     if (!e || !e->net) return gaz_fail("no network attached");
-    for (int r = 0; r < n_rounds; r++) {
-        if (gaz_internal_launch_select(e) != 0) return -1;
-        if (engine_forward(e) != 0) return -1;
-        if (gaz_internal_launch_expand(e) != 0) return -1;
-    }
+    if (run_rounds(e, n_rounds) != 0) return -1;
     CKN(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -1321,12 +1364,7 @@ int gaz_rounds_net(gaz_engine *e, int n_rounds) {
 // same without the trailing synchronise (bench: events bracket many calls)
 int gaz_rounds_net_async(gaz_engine *e, int n_rounds) {
     if (!e || !e->net) return gaz_fail("no network attached");
-    for (int r = 0; r < n_rounds; r++) {
-        if (gaz_internal_launch_select(e) != 0) return -1;
-        if (engine_forward(e) != 0) return -1;
-        if (gaz_internal_launch_expand(e) != 0) return -1;
-    }
-    return 0;
+    return run_rounds(e, n_rounds);
 }
 
 int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
