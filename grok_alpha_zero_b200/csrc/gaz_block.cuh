@@ -18,6 +18,20 @@
 #pragma once
 #include "gaz_conv.cuh"
 
+#ifdef GAZ_BLOCK_CLK   // per-role stall accounting (clock64 + printf from CTA 0), build with -DGAZ_BLOCK_CLK, run with dbg bit 1024
+#define TK_BEGIN() do { if (dbg & 1024) tq = clock64(); } while (0)
+#define TK_END(acc) do { if (dbg & 1024) acc += clock64() - tq; } while (0)
+#define TK_PRINT(...) printf(__VA_ARGS__)
+#define TK_START(v) v = clock64()
+#define TK_STOP(v) v = clock64() - v
+#else
+#define TK_START(v) do { } while (0)
+#define TK_STOP(v) do { } while (0)
+#define TK_BEGIN() do { } while (0)
+#define TK_END(acc) do { } while (0)
+#define TK_PRINT(...) do { } while (0)
+#endif
+
 namespace gaz_block {
 using namespace gaz_tc;
 using gaz_conv::f32_blk_index;
@@ -47,9 +61,116 @@ struct Cfg {
     static constexpr int NW = 4;                    // weight-tile ring (half tiles: 64 output channels x 64 k)
     static constexpr int W_BYTES = 64 * 128;
     static constexpr int STAGE_BYTES = 8 * 2 * 2048; // epilogue-2 warps: one 32 x 32-channel bf16 tile per output
-    static constexpr int SE_FLOATS = 8 * 128 + 3 * 128;
-    static constexpr int SMEM = 4 * SLAB_BYTES + NW * W_BYTES + STAGE_BYTES + 1024 + 256 + SE_FLOATS * 4;
+    static constexpr int SE_FLOATS = 8 * 128 + 128 + 256 + 64 + 128 + 128;
+    static constexpr int SMEM = 4 * SLAB_BYTES + NW * W_BYTES + STAGE_BYTES + 1024 + 256 + SE_FLOATS * 4 + 2 * 128 * 4;
 };
+
+// per-channel sums of 32 accumulator columns over the 32 rows of a warp: halving butterfly (31 shuffles), lane l ends
+// with the sum of column `col(l)` and stores it to dst[col]
+__device__ __forceinline__ void colsum32(const uint32_t (&r)[32], uint32_t mask, int lane, float *dst) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j] & mask);
+    int col = 0;
+#pragma unroll
+    for (int m = 16, h = 16; m >= 1; m >>= 1, h >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (i < h) {
+                const float send = up ? v[i] : v[i + h];
+                const float keep = up ? v[i + h] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        col += up ? h : 0;
+    }
+    dst[col] = v[0];
+}
+
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) { // {hi, lo} -> max(., 0) -> bf16x2
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// epilogue 2, one 16-column chunk of one row: gate * (conv2 + bias) + residual -> fp32 stream, relu(BN(.)) -> bf16
+// operand(s) of the next layer through the warp's 32 x 32-channel SWIZZLE_64B staging tile (one TMA store per 2 chunks)
+template <int ODD>
+__device__ __forceinline__ void e2_chunk(const uint32_t (&acc)[16], const float (&res)[16], bool use_res, int ck, const BlockArgs &p,
+                                         float *outp, uint32_t gate_addr, uint32_t bg_addr, uint32_t stage_addr, uint32_t mask,
+                                         int lane, int row0, const CUtensorMap &tmOa, const CUtensorMap &tmOb, int dbg) {
+    const int c0 = ck * 16;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float4 g = lds128f(gate_addr + (uint32_t)(c0 * 4 + j * 16)), b = lds128f(bg_addr + (uint32_t)(c0 * 4 + j * 16));
+        v[4 * j] = fmaf(__uint_as_float(acc[4 * j]), g.x, b.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), g.y, b.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), g.z, b.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(acc[4 * j + 3]), g.w, b.w);
+    }
+    if (use_res) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] += res[j];
+    }
+    if (dbg & 4) return;
+    if (p.out_raw && !(dbg & 16)) { // padding rows / columns carry don't-care values in the fp32 stream (never read by a live cell)
+        stg256(outp + (2 * ck) * 256, *reinterpret_cast<const float(*)[8]>(&v[0]));
+        stg256(outp + (2 * ck + 1) * 256, *reinterpret_cast<const float(*)[8]>(&v[8]));
+    }
+#pragma unroll
+    for (int o = 0; o < 2; o++) {
+        if (!(o == 0 ? p.out_a : p.out_b) || (dbg & 32)) continue;
+        const float *sc = p.par2 + (1 + 2 * o) * 128 + c0, *sh = p.par2 + (2 + 2 * o) * 128 + c0;
+        const uint32_t st = stage_addr + (uint32_t)(o * 2048);
+        if (!ODD) { // the store that used this tile one chunk pair ago must have drained it
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int c = 8 * j + 2 * i;
+                w[i] = pack_relu_bf16x2(fmaf(sc[c], v[c], sh[c]), fmaf(sc[c + 1], v[c + 1], sh[c + 1])) & mask;
+            }
+            const int piece = ODD * 2 + j; // 32-row x 32-channel SWIZZLE_64B tile: row = lane (64 B)
+            sts128(st + (uint32_t)(lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)), w[0], w[1], w[2], w[3]);
+        }
+        if (ODD) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d_addr(o == 0 ? &tmOa : &tmOb, st, c0 - 16, row0);
+                tma_store_commit();
+            }
+        }
+    }
+}
+
+// epilogue 1, one piece: 32 accumulator columns (channels c32*32 .. +31) of one row -> relu(BN2(. + b1)) -> bf16 -> the
+// row's four 16-byte chunks in K-block c32/2 of slab H, XOR-swizzled with the row phase like a SWIZZLE_128B TMA write.
+// The per-channel scale and (bias-folded) shift come from shared memory through volatile broadcast loads: as kernel
+// arguments the compiler hoists them across pieces into registers and spills them.
+__device__ __forceinline__ void e1_piece(const uint32_t (&r)[32], uint32_t par_addr, uint32_t sH_addr, int c32, int srow, bool live) {
+    const uint32_t rowp = sH_addr + (uint32_t)((c32 >> 1) * SLAB_BYTES + srow * 128);
+    const int sw = srow & 7, j0 = (c32 & 1) * 4;
+    const uint32_t mask = live ? 0xffffffffu : 0u;   // padding rows / columns of the board stay zero
+    const uint32_t sc_addr = par_addr + (uint32_t)(c32 * 128), sh_addr = sc_addr + 512;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        const float4 s0 = lds128f(sc_addr + ch * 32), s1 = lds128f(sc_addr + ch * 32 + 16);
+        const float4 h0 = lds128f(sh_addr + ch * 32), h1 = lds128f(sh_addr + ch * 32 + 16);
+        const int j = ch * 8;
+        uint32_t w[4];
+        w[0] = pack_relu_bf16x2(fmaf(s0.x, __uint_as_float(r[j]), h0.x), fmaf(s0.y, __uint_as_float(r[j + 1]), h0.y)) & mask;
+        w[1] = pack_relu_bf16x2(fmaf(s0.z, __uint_as_float(r[j + 2]), h0.z), fmaf(s0.w, __uint_as_float(r[j + 3]), h0.w)) & mask;
+        w[2] = pack_relu_bf16x2(fmaf(s1.x, __uint_as_float(r[j + 4]), h1.x), fmaf(s1.y, __uint_as_float(r[j + 5]), h1.y)) & mask;
+        w[3] = pack_relu_bf16x2(fmaf(s1.z, __uint_as_float(r[j + 6]), h1.z), fmaf(s1.w, __uint_as_float(r[j + 7]), h1.w)) & mask;
+        sts128(rowp + (uint32_t)(((j0 + ch) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+    }
+}
 
 __global__ void __launch_bounds__(512, 1)
 res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
@@ -68,6 +189,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
              *acc2_full = acc1_full + 3 /*[2]*/, *acc2_empty = acc1_full + 5 /*[2]*/;
     uint32_t *tmem_slot = (uint32_t *)(acc1_full + 7);
     float *s_se = (float *)(bars + 32);
+    float *s_e1par = s_se + Cfg::SE_FLOATS;   // epilogue 1: BN2 scale[128] | BN2 shift + scale * conv1 bias [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -76,7 +198,6 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (cnt > p.max_count) cnt = p.max_count;
     const int n_tiles = cnt;                      // tile == board
     const int n_loop = (n_tiles + 1) / 2;
-    const long long valid_rows = (long long)cnt * TILE_ROWS;
     const int dbg = p.dbg;
 
     // slab H halo rows are never written by epilogue 1: zero them once (rows [0, HALO) and [HALO + 256, 304) of both slabs)
@@ -84,6 +205,11 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int slab = i / (2 * HALO * 8), r = (i / 8) % (2 * HALO), ch = i & 7;
         const int row = r < HALO ? r : TILE_ROWS + r;
         *reinterpret_cast<uint4 *>(sH + slab * SLAB_BYTES + row * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (threadIdx.x < 128) {
+        const float sc = p.par1[128 + threadIdx.x];
+        s_e1par[threadIdx.x] = sc;
+        s_e1par[128 + threadIdx.x] = fmaf(sc, p.par1[threadIdx.x], p.par1[256 + threadIdx.x]);
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
@@ -141,6 +267,8 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             Ring rw;
             uint32_t ph = 0;
             int it = 0;
+            [[maybe_unused]] long long tk_e2 = 0, tk_e1 = 0, tk_w = 0, tk0 = 0, tq = 0;
+            TK_START(tk0);
             for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1, it++) {
                 // Accumulator set `as` (256 TMEM columns) serves BOTH convolutions of this board: conv1 fills it, epilogue 1
                 // drains it into slab H, conv2 refills it, epilogue 2 reads it - while the next board already runs both of
@@ -149,15 +277,21 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t sph = (uint32_t)((it >> 1) & 1);
                 const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * BN);
                 for (int cv = 0; cv < 2; cv++) {
+                    TK_BEGIN();
                     if (cv == 0) mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
                     else mbar_wait(e1_done, ph);                       // epilogue 1: set drained, slab H written (both CTAs)
+                    if (cv == 0) TK_END(tk_e2); else TK_END(tk_e1);
                     tc_fence_after();
                     for (int kc = 0; kc < 2; kc++) {
+                        TK_BEGIN();
                         if (cv == 0) mbar_wait(&x_full[kc], ph);
+                        TK_END(tk_w);
                         const uint32_t slab_lo = umma_desc_lo(smem_u32((cv == 0 ? sX : sH) + kc * SLAB_BYTES) + (uint32_t)(HALO * 128));
                         int dy = -1, dx = -1;
                         for (int tap = 0; tap < 9; tap++) {
+                            TK_BEGIN();
                             mbar_wait(&w_full[rw.idx], rw.phase);
+                            TK_END(tk_w);
                             tc_fence_after();
                             const uint32_t b_lo = umma_desc_lo(smem_u32(sW + rw.idx * Cfg::W_BYTES));
                             const uint32_t a_lo = slab_lo + (uint32_t)((dy * p.Wp + dx) * 8);
@@ -178,60 +312,76 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     else { umma_commit_elect<true>(h_empty); umma_commit_elect<true>(&acc2_full[as]); }
                 }
             }
+            if ((dbg & 1024) && blockIdx.x == 0 && lane == 0)
+            {
+                TK_STOP(tk0);
+                TK_PRINT("issuer: boards %d total %lld wait_e2 %lld wait_e1 %lld wait_loads %lld\n", it, tk0, tk_e2, tk_e1, tk_w);
+            }
         }
     } else if (warp >= 4 && warp < 8) { // ---------------- epilogue 1: acc1 -> relu(BN2(conv1 + b1)) -> slab H (bf16, swizzled)
         const int q = warp & 3;
         uint32_t ph = 0;
         int it = 0;
+        [[maybe_unused]] long long tk_work = 0, tq = 0;
+        const int e1_pos0 = q * 32 + lane, e1_pos1 = 128 + e1_pos0;
+        const int e1_srow0 = HALO + e1_pos0, e1_srow1 = HALO + e1_pos1;
+        const bool e1_live0 = (e1_pos0 / p.Wp) != 0 && (e1_pos0 % p.Wp) != p.Wp - 1;
+        const bool e1_live1 = (e1_pos1 / p.Wp) != 0 && (e1_pos1 % p.Wp) != p.Wp - 1;
+        const uint32_t sH_addr = smem_u32(sH), par_addr = smem_u32(s_e1par);
         for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1, it++) {
             const int t = 2 * lt + rank;
             const int as = it & 1;
             mbar_wait(acc1_full, ph);
             mbar_wait(h_empty, ph ^ 1);  // conv2 of the previous board has finished reading slab H
             tc_fence_after();
-            if (t < n_tiles) {
+            TK_BEGIN();
+            const bool work = t < n_tiles && !(dbg & 512);
+            // 8 pieces of 32 columns; the TMEM load of piece n+1 is in flight while piece n is converted.  (conv2 cannot
+            // start on K-block 0 of slab H before the whole set is drained: its first MMA overwrites all 128 columns)
+            uint32_t ra[32], rb[32];
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN);
+            if (work) {
+                // piece n = (c32 = n >> 1, sub = n & 1); TMEM column of piece n = sub * BN + c32 * 32
+                tmem_ld_32x32(t0, ra);
 #pragma unroll 1
-                for (int sub = 0; sub < 2; sub++) {
-                    const int pos = sub * 128 + q * 32 + lane;
-                    const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-                    const bool live = yy != 0 && xx != p.Wp - 1;
-                    const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + sub * BN);
-                    const int srow = HALO + pos;
-#pragma unroll 1
-                    for (int ck = 0; ck < 8; ck++) {
-                        uint32_t r[16];
-                        tmem_ld_32x16(t_acc + (uint32_t)(ck * 16), r);
-                        tmem_ld_wait();
-                        const float *pb = p.par1 + ck * 16, *sc = p.par1 + 128 + ck * 16, *sh = p.par1 + 256 + ck * 16;
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int c = 2 * i;
-                            const float a0 = fmaxf(fmaf(sc[c], __uint_as_float(r[c]) + pb[c], sh[c]), 0.0f);
-                            const float a1 = fmaxf(fmaf(sc[c + 1], __uint_as_float(r[c + 1]) + pb[c + 1], sh[c + 1]), 0.0f);
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
-                            w[i] = *reinterpret_cast<uint32_t *>(&hh);
-                        }
-                        // channels ck*16 .. +15 = K-block ck/4, 16-byte chunks 2*(ck%4) and +1, XOR-swizzled with the row phase
-                        uint8_t *rowp = sH + (ck >> 2) * SLAB_BYTES + srow * 128;
-                        const int j0 = (ck & 3) * 2;
-                        *reinterpret_cast<uint4 *>(rowp + (((j0) ^ (srow & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4 *>(rowp + (((j0 + 1) ^ (srow & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-                    }
+                for (int c32 = 0; c32 < 4; c32++) {
+                    tmem_ld_wait_dep(ra);
+                    tmem_ld_32x32(t0 + (uint32_t)(BN + c32 * 32), rb);
+                    e1_piece(ra, par_addr, sH_addr, c32, e1_srow0, e1_live0);
+                    tmem_ld_wait_dep(rb);
+                    if (c32 < 3) tmem_ld_32x32(t0 + (uint32_t)(c32 * 32 + 32), ra);
+                    e1_piece(rb, par_addr, sH_addr, c32, e1_srow1, e1_live1);
                 }
             }
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(e1_done);
+            TK_END(tk_work);
         }
+        if ((dbg & 1024) && blockIdx.x == 0 && warp == 4 && lane == 0) TK_PRINT("epilogue1: work %lld\n", tk_work);
     } else if (warp >= 8) { // ---------------- epilogue 2: SE + skip add + outputs (acc2)
         const int ew = warp - 8;
         const int q = warp & 3, sub = ew >> 2;
         const int et = threadIdx.x - 256; // 0..255
-        float *s_part = s_se, *s_hp = s_se + 8 * BN, *s_gate = s_hp + 2 * BN;
+        // s_se: column-sum partials [8 warps][128] (later the two dense2 partials) | mean[128] | dense1 partials [4][64] |
+        // hidden[64] | gate[128] | gate * conv2 bias [128]
+        float *s_part = s_se, *s_mean = s_se + 8 * BN, *s_hp = s_mean + BN, *s_h = s_hp + 256, *s_gate = s_h + 64, *s_bg = s_gate + BN;
+        float *s_gp = s_part;
         const float inv_cells = 1.0f / (float)p.n_cells;
+        const int pos = sub * 128 + q * 32 + lane;          // row of the board: the same for every board of this thread
+        const bool live = (pos / p.Wp) != 0 && (pos % p.Wp) != p.Wp - 1;
+        const uint32_t mask = live ? 0xffffffffu : 0u;
+        const bool use_res = p.res && !(dbg & 8);
+        const bool do_se = p.se && !(dbg & 64);
+        if (!do_se) { // no gate: out = conv2 + bias (+ residual)
+            if (et < BN) { s_gate[et] = 1.0f; s_bg[et] = p.par2[et]; }
+            named_bar_sync(1, 256);
+        }
+        const uint32_t gate_addr = smem_u32(s_gate), bg_addr = smem_u32(s_bg);
+        const uint32_t stage_addr = smem_u32(sStage + ew * 2 * 2048);
         int it = 0;
+        [[maybe_unused]] long long tk_wait = 0, tk_se = 0, tk_out = 0, tq = 0;
         for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
             const int t = 2 * lt + rank;
             const int as = it & 1;
@@ -243,181 +393,127 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) mbar_arrive_leader(&acc2_empty[as]);
                 continue;
             }
-            const long long row = (long long)t * TILE_ROWS + sub * 128 + q * 32 + lane;
-            const int pos = sub * 128 + q * 32 + lane;
-            const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-            const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
-            const bool use_res = p.res && !(dbg & 8);
-            float rnext[16];
+            // blocked fp32 layout (f32_blk_index): the 32 rows x 128 channels of this warp are 16 KB contiguous; 8-channel
+            // piece k of this thread's row sits at + k * 256 floats
+            const size_t rbase = ((size_t)(t * 8 + sub * 4 + q) << 12) + (size_t)(lane * 8);
+            const float *resp = p.res + rbase;
+            float *outp = p.out_raw + rbase;
+            const int row0 = t * TILE_ROWS + sub * 128 + q * 32;   // first row of this warp (TMA store coordinate)
+            float resA[16], resB[16];
             if (use_res) {
 #pragma unroll 1
-                for (int ck = 2; ck < 8; ck += 2) { // pull the rest of this row's residual into L2 meanwhile
-                    const float *pp = p.res + f32_blk_index(row, ck * 16, BN);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + j * 256));
-                }
-                const size_t blk0 = f32_blk_index(row, 0, BN);
-                ldg256(p.res + blk0, *reinterpret_cast<float(*)[8]>(&rnext[0]));
-                ldg256(p.res + blk0 + 256, *reinterpret_cast<float(*)[8]>(&rnext[8]));
+                for (int k = 4; k < 16; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(resp + k * 256));
+                ldg256(resp, *reinterpret_cast<float(*)[8]>(&resA[0]));
+                ldg256(resp + 256, *reinterpret_cast<float(*)[8]>(&resA[8]));
             }
+            TK_BEGIN();
             mbar_wait(&acc2_full[as], sph);
+            TK_END(tk_wait);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + sub * BN);
-            if (p.se && !(dbg & 64)) {
-                // ---- pass 1: per-channel sums over the board's live cells
+            TK_BEGIN();
+            if (do_se) {
+                // ---- pass 1: per-channel sums over the live cells of this warp's 32 rows (32-column pieces, the TMEM load
+                // of the next piece in flight while this one is folded)
+                {
+                    uint32_t ra[32], rb[32];
+                    float *dst = s_part + ew * BN;
+                    tmem_ld_32x32(t_acc, ra);
 #pragma unroll 1
-                for (int ck = 0; ck < 8; ck++) {
-                    uint32_t r[16];
-                    tmem_ld_32x16(t_acc + (uint32_t)(ck * 16), r);
-                    tmem_ld_wait();
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = live ? __uint_as_float(r[j]) : 0.0f;
-                    int col = 0;
-#pragma unroll
-                    for (int m = 16, h = 8; m >= 2; m >>= 1, h >>= 1) {
-                        const bool up = (lane & m) != 0;
-#pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            if (i < h) {
-                                const float send = up ? v[i] : v[i + h];
-                                const float keep = up ? v[i + h] : v[i];
-                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-                            }
-                        col += up ? h : 0;
+                    for (int h = 0; h < 2; h++) {
+                        tmem_ld_wait_dep(ra);
+                        tmem_ld_32x32(t_acc + (uint32_t)(h * 64 + 32), rb);
+                        colsum32(ra, mask, lane, dst + h * 64);
+                        tmem_ld_wait_dep(rb);
+                        if (h == 0) tmem_ld_32x32(t_acc + 64u, ra);
+                        colsum32(rb, mask, lane, dst + h * 64 + 32);
                     }
-                    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-                    if ((lane & 1) == 0) s_part[(sub * 4 + q) * BN + ck * 16 + col] = v[0];
                 }
                 named_bar_sync(1, 256);
-                {   // dense1 (C -> R) over 256 threads: output j, quarter `part` of the inputs
+                if (et < BN) { // board mean per channel
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sum += s_part[k * BN + et];
+                    s_mean[et] = sum * inv_cells;
+                }
+                named_bar_sync(1, 256);
+                {   // dense1 (C -> R): output j, quarter `part` of the inputs
                     const int j = et & 63, part = et >> 6;
                     if (j < p.se_r) {
                         const float *w1 = p.se_w1 + (size_t)(part * 32) * p.se_r + j;
+                        const float4 *m4 = reinterpret_cast<const float4 *>(s_mean + part * 32);
                         float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float m4[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int ii = part * 32 + i + u;
-                                float sum = 0.0f;
-#pragma unroll
-                                for (int k = 0; k < 8; k++) sum += s_part[k * BN + ii];
-                                m4[u] = sum * inv_cells;
-                            }
-                            h0 = fmaf(m4[0], __ldg(w1 + (size_t)(i) * p.se_r), h0);
-                            h1 = fmaf(m4[1], __ldg(w1 + (size_t)(i + 1) * p.se_r), h1);
-                            h2 = fmaf(m4[2], __ldg(w1 + (size_t)(i + 2) * p.se_r), h2);
-                            h3 = fmaf(m4[3], __ldg(w1 + (size_t)(i + 3) * p.se_r), h3);
+                        for (int i = 0; i < 8; i++) {
+                            const float4 m = m4[i];
+                            h0 = fmaf(m.x, __ldg(w1 + (size_t)(4 * i) * p.se_r), h0);
+                            h1 = fmaf(m.y, __ldg(w1 + (size_t)(4 * i + 1) * p.se_r), h1);
+                            h2 = fmaf(m.z, __ldg(w1 + (size_t)(4 * i + 2) * p.se_r), h2);
+                            h3 = fmaf(m.w, __ldg(w1 + (size_t)(4 * i + 3) * p.se_r), h3);
                         }
                         s_hp[part * 64 + j] = (h0 + h1) + (h2 + h3);
                     }
                 }
                 named_bar_sync(1, 256);
+                if (et < p.se_r) s_h[et] = fmaxf(((s_hp[et] + s_hp[64 + et]) + (s_hp[128 + et] + s_hp[192 + et])) + __ldg(p.se_b1 + et), 0.0f);
+                named_bar_sync(1, 256);
                 {   // dense2 (R -> C): output channel cc, half `part` of the hidden units
                     const int cc = et & 127, part = et >> 7;
                     const int r2 = p.se_r >> 1;
                     const float *w2 = p.se_w2 + (size_t)(part * r2) * BN + cc;
+                    const float *hh = s_h + part * r2;
                     float g0 = 0.0f, g1 = 0.0f;
-#pragma unroll 16
+#pragma unroll 8
                     for (int i = 0; i < r2; i += 2) {
-                        const int ii = part * r2 + i;
-                        const float ha = fmaxf(((s_hp[ii] + s_hp[64 + ii]) + (s_hp[128 + ii] + s_hp[192 + ii])) + __ldg(p.se_b1 + ii), 0.0f);
-                        const float hb = fmaxf(((s_hp[ii + 1] + s_hp[65 + ii]) + (s_hp[129 + ii] + s_hp[193 + ii])) + __ldg(p.se_b1 + ii + 1), 0.0f);
-                        g0 = fmaf(ha, __ldg(w2 + (size_t)(i) * BN), g0);
-                        g1 = fmaf(hb, __ldg(w2 + (size_t)(i + 1) * BN), g1);
+                        g0 = fmaf(hh[i], __ldg(w2 + (size_t)(i) * BN), g0);
+                        g1 = fmaf(hh[i + 1], __ldg(w2 + (size_t)(i + 1) * BN), g1);
                     }
-                    s_part[part * BN + cc] = g0 + g1;
+                    s_gp[part * BN + cc] = g0 + g1;
                 }
                 named_bar_sync(1, 256);
-                if (et < BN) s_gate[et] = 1.0f / (1.0f + expf(-((s_part[et] + s_part[BN + et]) + p.se_b2[et])));
-                named_bar_sync(1, 256);
-            } else if (p.se) {
-                if (et < BN) s_gate[et] = 1.0f;
+                if (et < BN) {
+                    const float g = 1.0f / (1.0f + expf(-((s_gp[et] + s_gp[BN + et]) + p.se_b2[et])));
+                    s_gate[et] = g;
+                    s_bg[et] = g * p.par2[et];   // gate * (conv2 + bias) = fma(conv2, gate, gate * bias)
+                }
                 named_bar_sync(1, 256);
             }
-            // ---- output pass over 16-column chunks
+            TK_END(tk_se);
+            TK_BEGIN();
+            // ---- output pass: 16-column chunks in pairs (A, B); TMEM load and residual load of the next chunk are in
+            // flight while the current one is written
+            {
+                uint32_t accA[16], accB[16];
+                tmem_ld_32x16(t_acc, accA);
 #pragma unroll 1
-            for (int ck = 0; ck < 8; ck++) {
-                const int c0 = ck * 16;
-                uint32_t r[16];
-                tmem_ld_32x16(t_acc + (uint32_t)c0, r);
-                float rcur[16];
-                if (use_res) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) rcur[j] = rnext[j];
-                    if (ck + 1 < 8) {
-                        const size_t blk2 = f32_blk_index(row, c0 + 16, BN);
-                        ldg256(p.res + blk2, *reinterpret_cast<float(*)[8]>(&rnext[0]));
-                        ldg256(p.res + blk2 + 256, *reinterpret_cast<float(*)[8]>(&rnext[8]));
+                for (int cp = 0; cp < 4; cp++) {
+                    const int ck = 2 * cp;
+                    tmem_ld_wait_dep(accA);
+                    tmem_ld_32x16(t_acc + (uint32_t)(ck * 16 + 16), accB);
+                    if (use_res) {
+                        ldg256(resp + (2 * ck + 2) * 256, *reinterpret_cast<float(*)[8]>(&resB[0]));
+                        ldg256(resp + (2 * ck + 3) * 256, *reinterpret_cast<float(*)[8]>(&resB[8]));
                     }
-                }
-                tmem_ld_wait();
-                float v[16];
-                const float *pb = p.par2 + c0;
-#pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + pb[j];
-                if (p.se) {
-                    const float4 *g4 = reinterpret_cast<const float4 *>(s_gate + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float4 g = g4[j];
-                        v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
-                    }
-                }
-                if (use_res) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] += rcur[j];
-                }
-                if (dbg & 4) continue;
-                if (p.out_raw && !(dbg & 16)) {
-                    const size_t blk = f32_blk_index(row, c0, BN);
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        float tt[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) tt[i] = live ? v[8 * j + i] : 0.0f;
-                        stg256(p.out_raw + blk + j * 256, tt);
-                    }
-                }
-#pragma unroll
-                for (int o = 0; o < 2; o++) {
-                    if (!(o == 0 ? p.out_a : p.out_b) || (dbg & 32)) continue;
-                    const float *sc = p.par2 + (1 + 2 * o) * 128 + c0, *sh = p.par2 + (2 + 2 * o) * 128 + c0;
-                    uint8_t *st = sStage + (ew * 2 + o) * 2048;
-                    if ((ck & 1) == 0) { // the store that used this tile one chunk pair ago must have drained it
-                        if (lane == 0) tma_store_wait_read();
-                        __syncwarp();
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int c = 8 * j + 2 * i;
-                            const float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
-                            const float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
-                            w[i] = *reinterpret_cast<uint32_t *>(&hh);
+                    e2_chunk<0>(accA, resA, use_res, ck, p, outp, gate_addr, bg_addr, stage_addr, mask, lane, row0, tmOa, tmOb, dbg);
+                    tmem_ld_wait_dep(accB);
+                    if (cp < 3) {
+                        tmem_ld_32x16(t_acc + (uint32_t)(ck * 16 + 32), accA);
+                        if (use_res) {
+                            ldg256(resp + (2 * ck + 4) * 256, *reinterpret_cast<float(*)[8]>(&resA[0]));
+                            ldg256(resp + (2 * ck + 5) * 256, *reinterpret_cast<float(*)[8]>(&resA[8]));
                         }
-                        const int piece = (ck & 1) * 2 + j; // 32-row x 32-channel SWIZZLE_64B tile: row = lane (64 B)
-                        *reinterpret_cast<uint4 *>(st + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                    if (ck & 1) {
-                        fence_proxy_async();
+                    } else { // the accumulator set is in registers: hand it back to the MMA issuer before the last stores
+                        tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(o == 0 ? &tmOa : &tmOb, st, c0 - 16, (int)(row - lane));
-                            tma_store_commit();
-                        }
+                        if (lane == 0) mbar_arrive_leader(&acc2_empty[as]);
                     }
+                    e2_chunk<1>(accB, resB, use_res, ck + 1, p, outp, gate_addr, bg_addr, stage_addr, mask, lane, row0, tmOa, tmOb, dbg);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&acc2_empty[as]);
+            TK_END(tk_out);
         }
+        if ((dbg & 1024) && blockIdx.x == 0 && (warp == 8 || warp == 15) && lane == 0)
+            TK_PRINT("epilogue2 warp %d: wait_acc %lld se %lld out %lld\n", warp, tk_wait, tk_se, tk_out);
         if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
