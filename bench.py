@@ -252,6 +252,8 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
 
     def label(cin, cout, k, tag):
         if tag.startswith("block"):
+            if cin != cout:
+                return "residual block 3x3 C%d->C%d, 3x3 C%d->C%d%s" % (cin, cout, cout, cout, "+SE+skip" if "se" in tag else "+skip")
             return "residual block 2x(3x3 C%d->C%d)%s" % (cin, cout, "+SE+skip" if "se" in tag else "+skip")
         return "%dx%d C%d->C%d%s" % (k, k, cin, cout, "+SE" if tag == "se" else "")
 
@@ -260,7 +262,7 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
         cells = leaves_per_launch * hw
         conv = 2.0 * cells * k * k * cin * cout
         if tag.startswith("block"):   # two convolutions; in: bf16 operand + fp32 residual, out: fp32 residual + bf16 operand
-            return 2.0 * conv, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
+            return conv + 2.0 * cells * k * k * cout * cout, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
         if tag == "se":
             return conv, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
         return conv, cells * (cin * 2 + cout * 2)

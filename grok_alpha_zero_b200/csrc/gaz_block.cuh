@@ -1,20 +1,26 @@
 // gaz_block.cuh -- one pre-activation residual block (Net/ResNet/ResNet_Block.py:27-41 + Net/SE/SE_Block.py:15-23) as ONE
-// kernel for tile == board geometries (Gomoku: 256 padded rows per board), C_in = C_out = 128:
+// kernel for tile == board geometries (Gomoku: 256 padded rows per board), C_in = 128 or 256, C_out = 128:
 //
-//   a_x (bf16, HBM) --TMA--> slab X --conv1 MMAs--> TMEM acc1 --epilogue 1: relu(BN2(. + b1))--> slab H (bf16, SMEM only)
-//        --conv2 MMAs--> TMEM acc2 --epilogue 2: SE gate * (. + b2) + residual--> x_out (fp32) and relu(BN(x_out)) (bf16)
+//   a_x (bf16, HBM) --TMA--> slab --conv1 MMAs--> TMEM --epilogue 1: relu(BN2(. + b1))--> the SAME slab (bf16, in place)
+//        --conv2 MMAs--> TMEM --epilogue 2: SE gate * (. + b2) + residual--> x_out (fp32) and relu(BN(x_out)) (bf16)
 //
 // The bf16 intermediate between the two convolutions never leaves the SM (2.1 GB per block and launch at 16384 leaves),
 // and conv1 - a tensor-bound kernel on its own - runs in the shadow of the memory-bound fused-SE epilogue of the
 // previous board.  Every board depends only on itself: the rows a live output reads outside its own board are padding
-// rows/columns (zeros), so slab H needs no data from neighbouring boards (its halo rows stay zero).
-// CTA pairs (cta_group::2) as in gaz_conv.cuh: each CTA owns its board, slabs, TMEM and epilogues; the leader issues
+// rows/columns, which are zero in the input slab's halo as well, so conv1's output can overwrite the input slab in place
+// (rows 0..255 only; the halo keeps the neighbours' padding zeros) - the shared memory this saves is the 12-deep weight
+// ring that keeps the tensor pipe fed across L2 latency.  C_in = 256 (first block of the trunk): the four input K-blocks
+// stream through the two slab halves (K-block kc -> half kc & 1).
+// CTA pairs (cta_group::2) as in gaz_conv.cuh: each CTA owns its board, slab, TMEM and epilogues; the leader issues
 // every MMA for both (M = 256) and each CTA stages half of every weight tile.
-// Warp roles (512 threads): 0 slab-X TMA producer, 1 weight TMA producer (W1 tiles then W2 tiles per board), 2 MMA
+// Warp roles (512 threads): 0 slab TMA producer, 1 weight TMA producer (W1 tiles then W2 tiles per board), 2 MMA
 // issuer, 3 idle, 4..7 epilogue 1 (one per TMEM lane quarter), 8..15 epilogue 2 (quarter x 128-row half).
 // TMEM: two accumulator sets of 256 columns (2 x 128-row halves x 128 channels); boards alternate between the sets and
-// BOTH convolutions of a board use the board's set (conv1 -> epilogue 1 drains it into slab H -> conv2 -> epilogue 2),
+// BOTH convolutions of a board use the board's set (conv1 -> epilogue 1 drains it into the slab -> conv2 -> epilogue 2),
 // so conv1, epilogue 1 and conv2 of board i+1 all run while epilogue 2 of board i is still reading the other set.
+// Both epilogues are software-pipelined (the TMEM load / residual load of the next piece is in flight while the current
+// one is converted) and keep their per-channel parameters out of registers (shared-memory broadcast loads, indexed
+// constant bank).  Cycle accounting per role: build with -DGAZ_BLOCK_CLK, run with debug bit 1024.
 #pragma once
 #include "gaz_conv.cuh"
 
@@ -48,6 +54,7 @@ struct BlockArgs {
     const int32_t *count;
     int max_count;
     int Wp, n_cells, dbg;
+    int nkc1;                 // 64-channel K-blocks of conv1's input (2: C_in = 128, 4: C_in = 256)
     float par1[3 * 128];      // conv1 bias | BN2 scale | BN2 shift          (constant bank, uniform loads)
     float par2[5 * 128];      // conv2 bias | scale_a | shift_a | scale_b | shift_b
     const float *res;         // blocked fp32 residual stream in
@@ -58,11 +65,11 @@ struct BlockArgs {
 };
 
 struct Cfg {
-    static constexpr int NW = 4;                    // weight-tile ring (half tiles: 64 output channels x 64 k)
+    static constexpr int NW = 12;                   // weight-tile ring (half tiles: 64 output channels x 64 k)
     static constexpr int W_BYTES = 64 * 128;
     static constexpr int STAGE_BYTES = 8 * 2 * 2048; // epilogue-2 warps: one 32 x 32-channel bf16 tile per output
     static constexpr int SE_FLOATS = 8 * 128 + 128 + 256 + 64 + 128 + 128;
-    static constexpr int SMEM = 4 * SLAB_BYTES + NW * W_BYTES + STAGE_BYTES + 1024 + 256 + SE_FLOATS * 4 + 2 * 128 * 4;
+    static constexpr int SMEM = 2 * SLAB_BYTES + NW * W_BYTES + STAGE_BYTES + 1024 + 512 + SE_FLOATS * 4 + 2 * 128 * 4;
 };
 
 // per-channel sums of 32 accumulator columns over the 32 rows of a warp: halving butterfly (31 shuffles), lane l ends
@@ -179,16 +186,16 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int BN = 128, NW = Cfg::NW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sX = base;                       // 2 slabs: K-blocks 0/1 of the block input
-    uint8_t *sH = base + 2 * SLAB_BYTES;      // 2 slabs: K-blocks 0/1 of the conv1 output
-    uint8_t *sW = base + 4 * SLAB_BYTES;
+    uint8_t *sX = base;                       // 2 slabs: K-blocks 0/1 of the block input, then (in place) of the conv1 output
+    uint8_t *sH = sX;
+    uint8_t *sW = base + 2 * SLAB_BYTES;
     uint8_t *sStage = sW + NW * Cfg::W_BYTES;
     uint64_t *bars = (uint64_t *)(sStage + Cfg::STAGE_BYTES);
     uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 4 + NW;
     uint64_t *acc1_full = bars + 4 + 2 * NW, *e1_done = acc1_full + 1, *h_empty = acc1_full + 2,
              *acc2_full = acc1_full + 3 /*[2]*/, *acc2_empty = acc1_full + 5 /*[2]*/;
     uint32_t *tmem_slot = (uint32_t *)(acc1_full + 7);
-    float *s_se = (float *)(bars + 32);
+    float *s_se = (float *)(bars + 64);
     float *s_e1par = s_se + Cfg::SE_FLOATS;   // epilogue 1: BN2 scale[128] | BN2 shift + scale * conv1 bias [128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,12 +207,6 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_loop = (n_tiles + 1) / 2;
     const int dbg = p.dbg;
 
-    // slab H halo rows are never written by epilogue 1: zero them once (rows [0, HALO) and [HALO + 256, 304) of both slabs)
-    for (int i = threadIdx.x; i < 2 * 2 * HALO * 8; i += blockDim.x) {
-        const int slab = i / (2 * HALO * 8), r = (i / 8) % (2 * HALO), ch = i & 7;
-        const int row = r < HALO ? r : TILE_ROWS + r;
-        *reinterpret_cast<uint4 *>(sH + slab * SLAB_BYTES + row * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
     if (threadIdx.x < 128) {
         const float sc = p.par1[128 + threadIdx.x];
         s_e1par[threadIdx.x] = sc;
@@ -225,7 +226,6 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.out_a) tma_prefetch_desc(&tmOa);
         if (p.out_b) tma_prefetch_desc(&tmOb);
     }
-    fence_proxy_async(); // the zeroed halo rows must be visible to the MMA (async proxy) reads
     if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
     cluster_sync_all();
@@ -233,17 +233,20 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) { // ---------------- slab-X TMA producer
-            uint32_t ph = 0;
-            for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1) {
+        if (lane == 0) { // ---------------- slab-X TMA producer: K-block kc of the input goes to slab kc & 1
+            const int half = p.nkc1 >> 1;
+            int it = 0;
+            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
                 const int t = 2 * lt + rank;
                 const int row0 = t * TILE_ROWS - HALO;
-                for (int kc = 0; kc < 2; kc++) {
-                    mbar_wait(&x_empty[kc], ph ^ 1);
-                    if (rank == 0) mbar_expect_tx(&x_full[kc], 2 * SLAB_BYTES);
-                    uint8_t *dst = sX + kc * SLAB_BYTES;
-                    tma_load_2d_pair(dst, &tmA, &x_full[kc], kc * 64, row0);
-                    tma_load_2d_pair(dst + SLAB_BYTES / 2, &tmA, &x_full[kc], kc * 64, row0 + SLAB_BOX_ROWS);
+                for (int kc = 0; kc < p.nkc1; kc++) {
+                    const int sl = kc & 1;
+                    const uint32_t use = (uint32_t)(it * half + (kc >> 1));   // how often slab sl has been filled before
+                    mbar_wait(&x_empty[sl], (use & 1) ^ 1);
+                    if (rank == 0) mbar_expect_tx(&x_full[sl], 2 * SLAB_BYTES);
+                    uint8_t *dst = sX + sl * SLAB_BYTES;
+                    tma_load_2d_pair(dst, &tmA, &x_full[sl], kc * 64, row0);
+                    tma_load_2d_pair(dst + SLAB_BYTES / 2, &tmA, &x_full[sl], kc * 64, row0 + SLAB_BOX_ROWS);
                 }
             }
         }
@@ -251,15 +254,17 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) { // ---------------- weight-tile TMA producer: per board W1 (kc, tap) then W2 (kc, tap)
             Ring r;
             for (int lt = pair0; lt < n_loop; lt += pair_step)
-                for (int cv = 0; cv < 2; cv++)
-                    for (int kc = 0; kc < 2; kc++)
+                for (int cv = 0; cv < 2; cv++) {
+                    const int nkc = cv == 0 ? p.nkc1 : 2, cin = nkc * 64;
+                    for (int kc = 0; kc < nkc; kc++)
                         for (int tap = 0; tap < 9; tap++) {
                             mbar_wait(&w_empty[r.idx], r.phase ^ 1);
                             if (rank == 0) mbar_expect_tx(&w_full[r.idx], 2 * Cfg::W_BYTES);
                             tma_load_2d_pair(sW + r.idx * Cfg::W_BYTES, cv == 0 ? &tmW1 : &tmW2, &w_full[r.idx],
-                                             tap * 128 + kc * 64, rank * 64);
+                                             tap * cin + kc * 64, rank * 64);
                             r.advance(NW);
                         }
+                }
         }
     } else if (warp == 2) {
         if (rank == 0) { // ---------------- MMA issuer (leader CTA): whole warp, one elected lane per instruction
@@ -282,11 +287,13 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     else mbar_wait(e1_done, ph);                       // epilogue 1: set drained, slab H written (both CTAs)
                     if (cv == 0) TK_END(tk_e2); else TK_END(tk_e1);
                     tc_fence_after();
-                    for (int kc = 0; kc < 2; kc++) {
+                    const int nkc = cv == 0 ? p.nkc1 : 2;
+                    for (int kc = 0; kc < nkc; kc++) {
+                        const int sl = kc & 1;
                         TK_BEGIN();
-                        if (cv == 0) mbar_wait(&x_full[kc], ph);
+                        if (cv == 0) mbar_wait(&x_full[sl], (uint32_t)(it * (p.nkc1 >> 1) + (kc >> 1)) & 1u);
                         TK_END(tk_w);
-                        const uint32_t slab_lo = umma_desc_lo(smem_u32((cv == 0 ? sX : sH) + kc * SLAB_BYTES) + (uint32_t)(HALO * 128));
+                        const uint32_t slab_lo = umma_desc_lo(smem_u32(sX + sl * SLAB_BYTES) + (uint32_t)(HALO * 128));
                         int dy = -1, dx = -1;
                         for (int tap = 0; tap < 9; tap++) {
                             TK_BEGIN();
@@ -306,10 +313,12 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             rw.advance(NW);
                             if (++dx == 2) { dx = -1; dy++; }
                         }
-                        if (cv == 0) umma_commit_elect<true>(&x_empty[kc]);
+                        // slab sl is free again: for the next K-block pair of this board's input (C_in = 256), or, after conv2 has
+                        // read H from it, for the next board
+                        if (cv == 1 || kc + 2 < nkc) umma_commit_elect<true>(&x_empty[sl]);
                     }
                     if (cv == 0) umma_commit_elect<true>(acc1_full);
-                    else { umma_commit_elect<true>(h_empty); umma_commit_elect<true>(&acc2_full[as]); }
+                    else umma_commit_elect<true>(&acc2_full[as]);
                 }
             }
             if ((dbg & 1024) && blockIdx.x == 0 && lane == 0)
@@ -332,7 +341,6 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int t = 2 * lt + rank;
             const int as = it & 1;
             mbar_wait(acc1_full, ph);
-            mbar_wait(h_empty, ph ^ 1);  // conv2 of the previous board has finished reading slab H
             tc_fence_after();
             TK_BEGIN();
             const bool work = t < n_tiles && !(dbg & 512);

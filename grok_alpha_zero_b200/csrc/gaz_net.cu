@@ -840,6 +840,7 @@ static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *cou
     gaz_block::BlockArgs a;
     memset(&a, 0, sizeof a);
     a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.n_cells = n->H * n->W; a.dbg = n->base_offset_mode;
+    a.nkc1 = c1.d.cin / 64;
     memcpy(a.par1, c1.par, sizeof a.par1);   // conv1 bias | BN2 scale | BN2 shift
     memcpy(a.par2, c2.par, sizeof a.par2);
     const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
@@ -1234,12 +1235,12 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             CKN(cudaMemcpy(op.d_se_b1, b1.data(), (size_t)R * 4, cudaMemcpyHostToDevice));
         }
     }
-    // whole-block fusion: conv1 (3x3 C128->C128, bf16 out only) directly followed by conv2 (3x3 C128->C128 reading it)
+    // whole-block fusion: conv1 (3x3 C128|C256 -> C128, bf16 out only) directly followed by conv2 (3x3 C128->C128 reading it)
     if (n->fuse_block && n->conv_pair && !n->conv_t && !n->conv_v1 && n->P_pad == gaz_conv::TILE_ROWS && (n->n_sm & ~1) >= 2) {
         for (size_t oi = 0; oi + 1 < n->ops.size(); oi++) {
             NetOp &c1 = n->ops[oi], &c2 = n->ops[oi + 1];
             if (c1.d.type != GAZ_OP_CONV_TC || c2.d.type != GAZ_OP_CONV_TC || c1.block_fused || c1.in_block) continue;
-            if (c1.d.cin != 128 || c1.d.cout != 128 || c1.d.ksize != 3 || c2.d.cin != 128 || c2.d.cout != 128 || c2.d.ksize != 3) continue;
+            if ((c1.d.cin != 128 && c1.d.cin != 256) || c1.d.cout != 128 || c1.d.ksize != 3 || c2.d.cin != 128 || c2.d.cout != 128 || c2.d.ksize != 3) continue;
             if (c1.d.out_a < 0 || c1.d.out_b >= 0 || c1.d.out_raw >= 0 || c1.d.res_buf >= 0 || c1.fused_se) continue;
             if (c2.d.in_buf != c1.d.out_a) continue;
             c1.block_fused = 1;

@@ -244,7 +244,7 @@ class Net:
         if tile_is_board and fuse_block:
             for i in range(len(b.ops) - 1):
                 o, o2 = b.ops[i], b.ops[i + 1]
-                if o["type"] == OP_CONV_TC and o2["type"] == OP_CONV_TC and (o["cin"], o["cout"], o["ksize"]) == (128, 128, 3) and \
+                if o["type"] == OP_CONV_TC and o2["type"] == OP_CONV_TC and (o["cin"], o["cout"], o["ksize"]) in ((128, 128, 3), (256, 128, 3)) and \
                         (o2["cin"], o2["cout"], o2["ksize"]) == (128, 128, 3) and o["out_a"] >= 0 and o["out_b"] < 0 and \
                         o["out_raw"] < 0 and o["res_buf"] < 0 and o2["in_buf"] == o["out_a"] and self._op_shapes[i][4] == "":
                     self._op_shapes[i][4] = "block+" + self._op_shapes[i + 1][4]
