@@ -179,6 +179,33 @@ __device__ __forceinline__ void e1_piece(const uint32_t (&r)[32], uint32_t par_a
     }
 }
 
+// epilogue 1 for one 128-row half of a board: this warp's 32 rows x 128 channels, four 32-column pieces, the TMEM load of
+// the next piece in flight while the current one is converted
+__device__ __forceinline__ void e1_drain(uint32_t t_sub, uint32_t par_addr, uint32_t sH_addr, int srow, bool live) {
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(t_sub, ra);
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        tmem_ld_wait_dep(ra);
+        tmem_ld_32x32(t_sub + (uint32_t)(c * 64 + 32), rb);
+        e1_piece(ra, par_addr, sH_addr, 2 * c, srow, live);
+        tmem_ld_wait_dep(rb);
+        if (c == 0) tmem_ld_32x32(t_sub + 64u, ra);
+        e1_piece(rb, par_addr, sH_addr, 2 * c + 1, srow, live);
+    }
+}
+// one board of epilogue 1 for a whole warp: wait for conv1, drain, publish the slab rows to the async proxy, arrive
+__device__ __forceinline__ void e1_board(uint64_t *acc1_full, uint64_t *e1_done, uint32_t ph, bool work, uint32_t t_sub,
+                                         uint32_t par_addr, uint32_t sH_addr, int srow, bool live, int lane) {
+    mbar_wait(acc1_full, ph);
+    tc_fence_after();
+    if (work) e1_drain(t_sub, par_addr, sH_addr, srow, live);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(e1_done);
+}
+
 __global__ void __launch_bounds__(512, 1)
 res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOa,
@@ -216,7 +243,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < 2; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
         for (int s = 0; s < NW; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(acc1_full, 1);
-        mbar_init(e1_done, 8);      // 4 epilogue-1 warps of each CTA arrive on the leader's copy
+        mbar_init(e1_done, 16);     // 8 epilogue-1 warps (two groups) of each CTA arrive on the leader's copy
         mbar_init(h_empty, 1);
         for (int a = 0; a < 2; a++) { mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], 16); } // 8 epilogue-2 warps of each CTA
         fence_barrier_init();
@@ -232,11 +259,22 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) { // ---------------- slab-X TMA producer: K-block kc of the input goes to slab kc & 1
-            const int half = p.nkc1 >> 1;
-            int it = 0;
-            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
+    // epilogue 1 is shared by two warp groups: warps 4..7 drain the first 128-row half of a board, warps 0..3 - whose own
+    // roles (TMA producers, MMA issuer) are idle exactly while conv1's accumulator is drained - the second half
+    const int e1_q = warp & 3, e1_sub = warp < 4 ? 1 : 0;
+    const int e1_pos = e1_sub * 128 + e1_q * 32 + lane, e1_srow = HALO + e1_pos;
+    const bool e1_live = (e1_pos / p.Wp) != 0 && (e1_pos % p.Wp) != p.Wp - 1;
+    const uint32_t e1_t = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)(e1_sub * BN);
+    const uint32_t sH_addr = smem_u32(sH), par_addr = smem_u32(s_e1par);
+    const bool e1_off = (dbg & 512) != 0;
+#define E1_BOARD(it_) e1_board(acc1_full, e1_done, (uint32_t)((it_) & 1), (2 * lt + rank) < n_tiles && !e1_off, \
+                               e1_t + (uint32_t)(((it_) & 1) * 2 * BN), par_addr, sH_addr, e1_srow, e1_live, lane)
+
+    if (warp == 0) { // ---------------- slab TMA producer (one lane) + epilogue 1, second half
+        const int half = p.nkc1 >> 1;
+        int it = 0;
+        for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
+            if (lane == 0) { // K-block kc of the input goes to slab kc & 1
                 const int t = 2 * lt + rank;
                 const int row0 = t * TILE_ROWS - HALO;
                 for (int kc = 0; kc < p.nkc1; kc++) {
@@ -249,23 +287,31 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tma_load_2d_pair(dst + SLAB_BYTES / 2, &tmA, &x_full[sl], kc * 64, row0 + SLAB_BOX_ROWS);
                 }
             }
+            __syncwarp();
+            E1_BOARD(it);
         }
-    } else if (warp == 1) {
-        if (lane == 0) { // ---------------- weight-tile TMA producer: per board W1 (kc, tap) then W2 (kc, tap)
-            Ring r;
-            for (int lt = pair0; lt < n_loop; lt += pair_step)
-                for (int cv = 0; cv < 2; cv++) {
-                    const int nkc = cv == 0 ? p.nkc1 : 2, cin = nkc * 64;
-                    for (int kc = 0; kc < nkc; kc++)
-                        for (int tap = 0; tap < 9; tap++) {
+    } else if (warp == 1) { // ---------------- weight-tile TMA producer (one lane): per board W1 (kc, tap) then W2 (kc, tap);
+        // once the ring holds the first NW tiles of conv2 there is nothing to load until conv2 starts: epilogue 1, second half
+        Ring r;
+        int it = 0;
+        for (int lt = pair0; lt < n_loop; lt += pair_step, it++)
+            for (int cv = 0; cv < 2; cv++) {
+                const int nkc = cv == 0 ? p.nkc1 : 2, cin = nkc * 64;
+                for (int kc = 0; kc < nkc; kc++)
+                    for (int tap = 0; tap < 9; tap++) {
+                        if (cv == 1 && kc * 9 + tap == NW) {
+                            __syncwarp();
+                            E1_BOARD(it);
+                        }
+                        if (lane == 0) {
                             mbar_wait(&w_empty[r.idx], r.phase ^ 1);
                             if (rank == 0) mbar_expect_tx(&w_full[r.idx], 2 * Cfg::W_BYTES);
                             tma_load_2d_pair(sW + r.idx * Cfg::W_BYTES, cv == 0 ? &tmW1 : &tmW2, &w_full[r.idx],
                                              tap * cin + kc * 64, rank * 64);
-                            r.advance(NW);
                         }
-                }
-        }
+                        r.advance(NW);
+                    }
+            }
     } else if (warp == 2) {
         if (rank == 0) { // ---------------- MMA issuer (leader CTA): whole warp, one elected lane per instruction
             constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
@@ -283,6 +329,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * BN);
                 for (int cv = 0; cv < 2; cv++) {
                     TK_BEGIN();
+                    if (cv == 1) E1_BOARD(it);                         // the issuer has nothing to issue meanwhile: it drains too
                     if (cv == 0) mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
                     else mbar_wait(e1_done, ph);                       // epilogue 1: set drained, slab H written (both CTAs)
                     if (cv == 0) TK_END(tk_e2); else TK_END(tk_e1);
@@ -326,48 +373,19 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 TK_STOP(tk0);
                 TK_PRINT("issuer: boards %d total %lld wait_e2 %lld wait_e1 %lld wait_loads %lld\n", it, tk0, tk_e2, tk_e1, tk_w);
             }
+        } else { // follower CTA: its warp 2 only drains
+            int it = 0;
+            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) E1_BOARD(it);
         }
-    } else if (warp >= 4 && warp < 8) { // ---------------- epilogue 1: acc1 -> relu(BN2(conv1 + b1)) -> slab H (bf16, swizzled)
-        const int q = warp & 3;
-        uint32_t ph = 0;
+    } else if (warp < 8) { // ---------------- warp 3 and warps 4..7: epilogue 1 only (acc1 -> relu(BN2(conv1 + b1)) -> slab, bf16, swizzled)
         int it = 0;
         [[maybe_unused]] long long tk_work = 0, tq = 0;
-        const int e1_pos0 = q * 32 + lane, e1_pos1 = 128 + e1_pos0;
-        const int e1_srow0 = HALO + e1_pos0, e1_srow1 = HALO + e1_pos1;
-        const bool e1_live0 = (e1_pos0 / p.Wp) != 0 && (e1_pos0 % p.Wp) != p.Wp - 1;
-        const bool e1_live1 = (e1_pos1 / p.Wp) != 0 && (e1_pos1 % p.Wp) != p.Wp - 1;
-        const uint32_t sH_addr = smem_u32(sH), par_addr = smem_u32(s_e1par);
-        for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1, it++) {
-            const int t = 2 * lt + rank;
-            const int as = it & 1;
-            mbar_wait(acc1_full, ph);
-            tc_fence_after();
+        for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
             TK_BEGIN();
-            const bool work = t < n_tiles && !(dbg & 512);
-            // 8 pieces of 32 columns; the TMEM load of piece n+1 is in flight while piece n is converted.  (conv2 cannot
-            // start on K-block 0 of slab H before the whole set is drained: its first MMA overwrites all 128 columns)
-            uint32_t ra[32], rb[32];
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN);
-            if (work) {
-                // piece n = (c32 = n >> 1, sub = n & 1); TMEM column of piece n = sub * BN + c32 * 32
-                tmem_ld_32x32(t0, ra);
-#pragma unroll 1
-                for (int c32 = 0; c32 < 4; c32++) {
-                    tmem_ld_wait_dep(ra);
-                    tmem_ld_32x32(t0 + (uint32_t)(BN + c32 * 32), rb);
-                    e1_piece(ra, par_addr, sH_addr, c32, e1_srow0, e1_live0);
-                    tmem_ld_wait_dep(rb);
-                    if (c32 < 3) tmem_ld_32x32(t0 + (uint32_t)(c32 * 32 + 32), ra);
-                    e1_piece(rb, par_addr, sH_addr, c32, e1_srow1, e1_live1);
-                }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(e1_done);
+            E1_BOARD(it);
             TK_END(tk_work);
         }
-        if ((dbg & 1024) && blockIdx.x == 0 && warp == 4 && lane == 0) TK_PRINT("epilogue1: work %lld\n", tk_work);
+        if ((dbg & 1024) && blockIdx.x == 0 && warp == 4 && lane == 0) TK_PRINT("epilogue1: wait + work %lld\n", tk_work);
     } else if (warp >= 8) { // ---------------- epilogue 2: SE + skip add + outputs (acc2)
         const int ew = warp - 8;
         const int q = warp & 3, sub = ew >> 2;
