@@ -603,6 +603,107 @@ __global__ void __launch_bounds__(128) headconv_board_kernel(HeadConvArgs p) {
     }
 }
 
+// Head convolutions on a 32-channel bf16 row tensor (Gomoku policy_conv1 3x3 32->8, value_conv1 1x1 32->4) on the
+// warp-level tensor-core path (mma.sync m16n8k16 - far too small for a tcgen05 pipeline: 0.5 MFLOP per board).  One CTA
+// stages a whole board (+ halo rows) in shared memory (64-byte rows, 16-byte chunks XOR-swizzled so ldmatrix is
+// conflict-free); an M tile is 16 consecutive padded rows, a filter tap is a row shift of the ldmatrix addresses, N = 8
+// output channels (zero padded), K = 32 input channels = 2 k-steps.  Weights stay fp32-accurate: every B fragment is
+// split into bf16 hi + lo parts and issued as two MMAs (inputs are bf16 already, accumulation is fp32).
+template <int K>
+__global__ void __launch_bounds__(128) headconv_mma_kernel(HeadConvArgs p) {
+    constexpr int TAPS = K * K, kh = K >> 1;
+    extern __shared__ __align__(16) uint8_t s_board[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int halo = kh * (p.Wp + 1);
+    const int n_mt = (p.P_pad + 15) >> 4;
+    const int srows = n_mt * 16 + 2 * halo;
+    // B fragments (k x n, "col" layout): this lane holds k = (lane & 3) * 2 + {0, 1} (+ 8 for the second register), n = lane >> 2.
+    // They live in shared memory as [tap][k-step][lane] uint4 = {hi0, hi1, lo0, lo1} (one conflict-free LDS.128 per use):
+    // in registers (72) they cap the kernel at 3 CTAs per SM.
+    uint4 *s_frag = reinterpret_cast<uint4 *>(s_board + (size_t)srows * 64);
+    if (warp == 0) {
+        const int nn = lane >> 2, k0 = (lane & 3) * 2;
+        for (int t = 0; t < TAPS; t++)
+            for (int ks = 0; ks < 2; ks++) {
+                uint32_t hi[2], lo[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    float w2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int ci = ks * 16 + h * 8 + k0 + e;
+                        w2[e] = nn < p.Cout ? p.w[(size_t)(t * 32 + ci) * p.Cout + nn] : 0.0f;
+                    }
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(w2[0]), h1 = __float2bfloat16_rn(w2[1]);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(w2[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(w2[1] - __bfloat162float(h1));
+                    hi[h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[h] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                s_frag[(t * 2 + ks) * 32 + lane] = make_uint4(hi[0], hi[1], lo[0], lo[1]);
+            }
+    }
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int ncell = p.H * p.W;
+    const uint4 *gin = reinterpret_cast<const uint4 *>(p.in); // 4 uint4 per 64-byte row
+    uint4 *sin = reinterpret_cast<uint4 *>(s_board);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_board);
+    // ldmatrix.x4: lane -> (matrix mi = lane >> 3, row lane & 7); matrices = (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+    const int a_row = ((lane >> 3) & 1) * 8 + (lane & 7), a_chunk = lane >> 4;
+    const float bias0 = (lane & 3) * 2 < p.Cout ? p.bias[(lane & 3) * 2] : 0.0f;
+    const float bias1 = (lane & 3) * 2 + 1 < p.Cout ? p.bias[(lane & 3) * 2 + 1] : 0.0f;
+    for (int b = blockIdx.x; b < cnt; b += gridDim.x) {
+        __syncthreads();
+        const long long g0 = ((long long)b * p.P_pad - halo) * 4;
+        for (int i = threadIdx.x; i < srows * 4; i += blockDim.x) {
+            const long long gi = g0 + i;
+            const int row = i >> 2, ch = i & 3;
+            sin[row * 4 + (ch ^ ((row >> 1) & 3))] = (gi >= 0 && gi < p.in_rows * 4) ? gin[gi] : make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        for (int mt = warp; mt < n_mt; mt += 4) {
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int t = 0; t < TAPS; t++) {
+                const int sr = halo + mt * 16 + a_row + (t / K - kh) * p.Wp + (t % K - kh);
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++) {
+                    const uint32_t addr = sbase + (uint32_t)(sr * 64 + (((ks * 2 + a_chunk) ^ ((sr >> 1) & 3)) << 4));
+                    uint32_t a0, a1, a2, a3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+                    const uint4 bf = s_frag[(t * 2 + ks) * 32 + lane];
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.z), "r"(bf.w));
+                }
+            }
+            // C fragment: acc[0..1] = row lane >> 2, columns (lane & 3) * 2 + {0, 1}; acc[2..3] = row + 8
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int pos = mt * 16 + (lane >> 2) + h * 8;
+                const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
+                if (pos >= p.P_pad || yy < 0 || xx >= p.W) continue;
+                const int cell = yy * p.W + xx;
+                const int co = (lane & 3) * 2;           // Cout is even: the channel pair is in or out together
+                if (co >= p.Cout) continue;
+                const size_t f = (size_t)cell * p.Cout + co;
+                const float v0 = acc[2 * h] + bias0, v1 = acc[2 * h + 1] + bias1;
+                if (p.out_act) {
+                    *reinterpret_cast<__nv_bfloat162 *>(p.out_act + (size_t)b * p.act_ld + f) =
+                        __floats2bfloat162_rn(fmaxf(fmaf(p.act_scale[f], v0, p.act_shift[f]), 0.0f),
+                                              fmaxf(fmaf(p.act_scale[f + 1], v1, p.act_shift[f + 1]), 0.0f));
+                } else {
+                    *reinterpret_cast<float2 *>(p.out + (size_t)b * ncell * p.Cout + f) = make_float2(v0, v1);
+                }
+            }
+        }
+    }
+}
+
 struct DenseArgs {
     const int32_t *count;
     int max_count, In, Out, act, pre_affine, pre_relu;
@@ -768,6 +869,7 @@ struct gaz_net {
     int fuse_se;           // GAZ_FUSE_SE (default 1)
     int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
     int use_graph;         // GAZ_GRAPH (default 1): replay a captured CUDA graph per search round
+    int head_mma;          // GAZ_HEAD_MMA (default 1): 32-channel head convolutions on mma.sync instead of CUDA cores
     int fuse_block;        // GAZ_FUSE_BLOCK (default 1): conv1 + conv2 + SE of a residual block in one kernel (gaz_block.cuh)
     int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
     std::vector<cudaEvent_t> ev;
@@ -979,6 +1081,12 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             if (d.cin == 32 && !a.in_f32 && ((d.cout == 8 && d.ksize == 3) || (d.cout == 4 && d.ksize == 1))) {
                 const int halo = (d.ksize / 2) * (n->Wp + 1);
                 const size_t smb = (size_t)(n->P_pad + 2 * halo) * 64;
+                const size_t smm = (size_t)(((n->P_pad + 15) / 16) * 16 + 2 * halo) * 64 + (size_t)d.ksize * d.ksize * 2 * 32 * 16;
+                if (n->head_mma && smm <= 48 * 1024 && (d.cout & 1) == 0 && (((d.cout * n->H * n->W + 7) & ~7) & 1) == 0) {
+                    if (d.ksize == 3) headconv_mma_kernel<3><<<n->n_sm * 8, 128, smm, s>>>(a);
+                    else headconv_mma_kernel<1><<<n->n_sm * 8, 128, smm, s>>>(a);
+                    break;
+                }
                 if (smb <= 48 * 1024) {
                     if (d.cout == 8) headconv_board_kernel<8, 3><<<n->n_sm * 8, 128, smb, s>>>(a);
                     else headconv_board_kernel<4, 1><<<n->n_sm * 8, 128, smb, s>>>(a);
@@ -1081,6 +1189,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         if (n->conv_v1) n->conv_t = 0;
         const char *e6 = getenv("GAZ_FUSE_BLOCK");
         n->fuse_block = e6 ? atoi(e6) : 1;
+        const char *e8 = getenv("GAZ_HEAD_MMA");
+        n->head_mma = e8 ? atoi(e8) : 1;
     }
     n->profile = 0;
     n->ev_used = 0;
