@@ -17,6 +17,7 @@
 #include "gaz_conv.cuh"
 #include "gaz_convt.cuh"
 #include "gaz_block.cuh"
+#include "gaz_stem.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -842,6 +843,9 @@ struct NetOp {
     int dense_tc;
     __nv_bfloat16 *d_act; // [rows_dense][In]: written by the producing head convolution
     __nv_bfloat16 *d_wt;  // [Out][In]
+    int stem_tc;          // stem on the tensor cores (gaz_stem.cuh): d_stem_w / d_stem_par / tmOa (out_a) / tmOb (out_q) are set
+    uint16_t *d_stem_w;   // [256][64] bf16 hi | lo split filters
+    float *d_stem_par;    // [4][256] BN scale | shift + scale * bias | scale_a | shift_a
     CUtensorMap tmDA, tmDW, tmDW2;
     long long rows_dense;
 };
@@ -869,6 +873,7 @@ struct gaz_net {
     int fuse_se;           // GAZ_FUSE_SE (default 1)
     int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
     int use_graph;         // GAZ_GRAPH (default 1): replay a captured CUDA graph per search round
+    int stem_tc;           // GAZ_STEM_TC (default 1): Gomoku-shaped stem as an implicit GEMM on tcgen05 (gaz_stem.cuh)
     int head_mma;          // GAZ_HEAD_MMA (default 1): 32-channel head convolutions on mma.sync instead of CUDA cores
     int fuse_block;        // GAZ_FUSE_BLOCK (default 1): conv1 + conv2 + SE of a residual block in one kernel (gaz_block.cuh)
     int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
@@ -996,6 +1001,19 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             const int tc = d.ksize * d.ksize * d.cin;
             if (d.cout % 4 != 0 || 256 % (d.cout / 4) != 0 || d.cin > 4 || (n->H + 2 * (d.ksize / 2)) > 18 || (n->W + 2 * (d.ksize / 2)) > 18)
                 return gaz_fail("stem shape unsupported (cin %d cout %d)", d.cin, d.cout);
+            if (op.stem_tc) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    CKN(cudaFuncSetAttribute(gaz_stem::stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_stem::Cfg::SMEM));
+                    attr_set = true;
+                }
+                gaz_stem::StemTcArgs t;
+                t.count = count; t.max_count = n->max_batch; t.states = states; t.H = n->H; t.W = n->W; t.Wp = n->Wp;
+                t.relu = d.act == GAZ_ACT_RELU; t.wpack = op.d_stem_w; t.par = op.d_stem_par;
+                t.has_q = d.out_b >= 0; t.has_a = d.out_a >= 0;
+                gaz_stem::stem_tc_kernel<<<2 * n->n_sm, 256, gaz_stem::Cfg::SMEM, s>>>(op.tmOb, op.tmOa, t);
+                break;
+            }
             int grid = n->n_sm * 4;
             (void)tc;
             const size_t tab = d.cin == 2 ? (size_t)d.ksize * d.ksize * d.cout * 4 : 0; // (2*kh+1)^2 classes x Cout floats
@@ -1191,6 +1209,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         n->fuse_block = e6 ? atoi(e6) : 1;
         const char *e8 = getenv("GAZ_HEAD_MMA");
         n->head_mma = e8 ? atoi(e8) : 1;
+        const char *e9 = getenv("GAZ_STEM_TC");
+        n->stem_tc = e9 ? atoi(e9) : 1;
     }
     n->profile = 0;
     n->ev_used = 0;
@@ -1238,6 +1258,9 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.skip = 0;
         op.block_fused = 0;
         op.in_block = 0;
+        op.stem_tc = 0;
+        op.d_stem_w = nullptr;
+        op.d_stem_par = nullptr;
         op.d_par = nullptr;
         op.d_se_b1 = nullptr;
         op.dense_tc = 0; op.d_act = nullptr; op.d_wt = nullptr; op.rows_dense = 0;
@@ -1357,6 +1380,49 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             c2.in_block = 1;
         }
     }
+    // stem on the tensor cores: 3x3 on 2 planes -> 256 filters, tile == board, bf16 outputs only
+    for (auto &op : n->ops) {
+        const gaz_net_op &d = op.d;
+        if (d.type != GAZ_OP_STEM || !n->stem_tc || n->conv_t || n->conv_v1) continue;
+        if (d.ksize != 3 || d.cin != 2 || d.cout != 256 || n->P_pad != 256 || n->H > 16 || n->W > 16 || d.out_raw >= 0) continue;
+        if (d.act != GAZ_ACT_NONE && d.act != GAZ_ACT_RELU) continue;
+        if (d.out_a < 0 && d.out_b < 0) continue;
+        std::vector<uint16_t> wp((size_t)256 * 64, 0);
+        auto bf16_bits = [](float f) -> uint16_t { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16); };
+        auto bf16_val = [](uint16_t b) -> float { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; };
+        for (int o = 0; o < 256; o++)
+            for (int k = 0; k < 18; k++) {
+                const float w = desc->wf[d.w + (int64_t)k * 256 + o];   // [tap][plane][filter]
+                const uint16_t hi = bf16_bits(w);
+                wp[(size_t)o * 64 + k] = hi;
+                wp[(size_t)o * 64 + 18 + k] = bf16_bits(w - bf16_val(hi));
+            }
+        std::vector<float> par((size_t)4 * 256);
+        for (int c = 0; c < 256; c++) {
+            const float sc = d.scale_b >= 0 ? desc->wf[d.scale_b + c] : 1.0f, sh = d.shift_b >= 0 ? desc->wf[d.shift_b + c] : 0.0f;
+            par[c] = sc;
+            par[256 + c] = fmaf(sc, desc->wf[d.bias + c], sh);
+            par[512 + c] = d.scale_a >= 0 ? desc->wf[d.scale_a + c] : 1.0f;
+            par[768 + c] = d.shift_a >= 0 ? desc->wf[d.shift_a + c] : 0.0f;
+        }
+        if (alloc((void **)&op.d_stem_w, wp.size() * 2) != 0 || alloc((void **)&op.d_stem_par, par.size() * 4) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(op.d_stem_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+        CKN(cudaMemcpy(op.d_stem_par, par.data(), par.size() * 4, cudaMemcpyHostToDevice));
+        memset(&op.tmOa, 0, sizeof op.tmOa);
+        memset(&op.tmOb, 0, sizeof op.tmOb);
+        bool ok = true;
+        for (int k = 0; k < 2 && ok; k++) {
+            const int id = k == 0 ? d.out_a : d.out_b;
+            if (id < 0) continue;
+            const NetBuf &ob = n->bufs[(size_t)id];
+            if (ob.kind != GAZ_BUF_ROWS_BF16 || ob.width != 256) { ok = false; break; }
+            if (make_map_ex(enc, k == 0 ? &op.tmOa : &op.tmOb, ob.ptr, 256, (uint64_t)n->rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) != 0) {
+                gaz_net_destroy(n);
+                return -1;
+            }
+        }
+        op.stem_tc = ok ? 1 : 0;
+    }
     CKN(cudaDeviceSynchronize());
     *out = n;
     return 0;
@@ -1366,7 +1432,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    for (auto &op : n->ops) { if (op.d_par) cudaFree(op.d_par); if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); }
+    for (auto &op : n->ops) { if (op.d_par) cudaFree(op.d_par); if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);

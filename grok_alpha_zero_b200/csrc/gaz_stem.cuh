@@ -1,0 +1,217 @@
+// gaz_stem.cuh -- the network stem (Net/ResNet/*: first 3x3 convolution on the 2 input planes + BN [+ ReLU]) on the
+// tensor cores for tile == board geometries (Gomoku: 256 padded rows per board, 256 stem filters).
+//
+// The CUDA-core stem (stem_kernel in gaz_net.cu) is instruction-bound: 2 x 256 channels x 256 rows of bf16 outputs per
+// board cost ~50k warp instructions.  Here a board is one small implicit GEMM: A = im2col of the board built in shared
+// memory (256 rows x K, K = 9 taps x 2 planes; the entries are -1/0/+1, exact in bf16), B = the filters, D in TMEM, and
+// the only real work left is the store-bound epilogue (BN affine, optional ReLU, the two bf16 operands of the first
+// residual block through swizzled staging tiles + TMA stores).
+// fp32 filter accuracy is kept by splitting every weight into bf16 hi + lo parts along K: k = 0..17 multiplies the hi
+// parts, k = 18..35 the lo parts (A repeats its 18 entries), K is padded to 48 = three k-steps of 16.
+// One CTA computes HALF of the output channels (N = 128) of one board at a time: 256 TMEM columns (2 x 128-row halves),
+// so two CTAs share an SM and one CTA's epilogue overlaps the other's im2col + MMA without any pipeline inside a CTA.
+#pragma once
+#include "gaz_conv.cuh"
+
+namespace gaz_stem {
+using namespace gaz_tc;
+
+struct StemTcArgs {
+    const int32_t *count;
+    int max_count;
+    const int8_t *states;   // [leaf][H*W*2] HWC (plane 0 = side to move, plane 1 = stones), values -1/0/+1
+    int H, W, Wp, relu;
+    const uint16_t *wpack;  // [256 filters][64 k] bf16: k = tap*2 + plane (hi parts) | 18 + tap*2 + plane (lo parts) | zeros
+    const float *par;       // [4][256]: BN scale | BN shift + scale * conv bias | scale_a | shift_a
+    int has_q, has_a;       // out_q = activation itself (bf16), out_a = relu(scale_a * activation + shift_a) (bf16)
+};
+
+struct Cfg {
+    static constexpr int A_BYTES = 256 * 128, B_BYTES = 128 * 128, STAGE_BYTES = 8 * 2 * 2048, PAR_BYTES = 4 * 128 * 4;
+    static constexpr int IN_BYTES = 18 * 18 * 2 + 28;  // zero-bordered int8 board (H, W <= 16)
+    static constexpr int SMEM = 1024 + A_BYTES + B_BYTES + STAGE_BYTES + PAR_BYTES + IN_BYTES + 64;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// one 32-column piece of one row: BN affine (+ReLU) -> out_q / out_a staging tiles (32 rows x 32 channels, SWIZZLE_64B)
+__device__ __forceinline__ void stem_piece(const uint32_t (&r)[32], uint32_t par_addr, int c32, bool relu, bool has_q, bool has_a,
+                                           uint32_t stage_addr, uint32_t mask, int lane) {
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) { // 8 channels = one 16-byte chunk of each output tile
+        const uint32_t o = (uint32_t)(c32 * 128 + ch * 32);
+        const float4 s0 = lds128f(par_addr + o), s1 = lds128f(par_addr + o + 16);
+        const float4 h0 = lds128f(par_addr + 512 + o), h1 = lds128f(par_addr + 512 + o + 16);
+        float v[8];
+        const int j = ch * 8;
+        v[0] = fmaf(s0.x, __uint_as_float(r[j]), h0.x);     v[1] = fmaf(s0.y, __uint_as_float(r[j + 1]), h0.y);
+        v[2] = fmaf(s0.z, __uint_as_float(r[j + 2]), h0.z); v[3] = fmaf(s0.w, __uint_as_float(r[j + 3]), h0.w);
+        v[4] = fmaf(s1.x, __uint_as_float(r[j + 4]), h1.x); v[5] = fmaf(s1.y, __uint_as_float(r[j + 5]), h1.y);
+        v[6] = fmaf(s1.z, __uint_as_float(r[j + 6]), h1.z); v[7] = fmaf(s1.w, __uint_as_float(r[j + 7]), h1.w);
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i], 0.0f);
+        }
+        const uint32_t off = (uint32_t)(lane * 64) + (((uint32_t)ch ^ sw) << 4);
+        if (has_q)
+            sts128(stage_addr + off, pack_bf16x2(v[0], v[1]) & mask, pack_bf16x2(v[2], v[3]) & mask, pack_bf16x2(v[4], v[5]) & mask,
+                   pack_bf16x2(v[6], v[7]) & mask);
+        if (has_a) {
+            const float4 a0 = lds128f(par_addr + 1024 + o), a1 = lds128f(par_addr + 1024 + o + 16);
+            const float4 t0 = lds128f(par_addr + 1536 + o), t1 = lds128f(par_addr + 1536 + o + 16);
+            sts128(stage_addr + 2048 + off, pack_relu_bf16x2(fmaf(a0.x, v[0], t0.x), fmaf(a0.y, v[1], t0.y)) & mask,
+                   pack_relu_bf16x2(fmaf(a0.z, v[2], t0.z), fmaf(a0.w, v[3], t0.w)) & mask,
+                   pack_relu_bf16x2(fmaf(a1.x, v[4], t1.x), fmaf(a1.y, v[5], t1.y)) & mask,
+                   pack_relu_bf16x2(fmaf(a1.z, v[6], t1.z), fmaf(a1.w, v[7], t1.w)) & mask);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmOq, const __grid_constant__ CUtensorMap tmOa, const StemTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base, *sB = base + Cfg::A_BYTES, *sStage = sB + Cfg::B_BYTES;
+    float *s_par = (float *)(sStage + Cfg::STAGE_BYTES);
+    int8_t *s_in = (int8_t *)(s_par + 4 * 128);
+    uint64_t *bar = (uint64_t *)(((uintptr_t)(s_in + Cfg::IN_BYTES) + 7) & ~(uintptr_t)7);
+    uint32_t *tmem_slot = (uint32_t *)(bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nhalf = (int)(blockIdx.x & 1);              // which 128 of the 256 filters
+    const int b0 = (int)(blockIdx.x >> 1), bstep = (int)(gridDim.x >> 1);
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+
+    // one-time setup: filters (swizzled like a SWIZZLE_128B TMA write), parameters, zeroed A tile and input border
+    for (int i = threadIdx.x; i < 128 * 8; i += 256) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4 *>(sB + r * 128 + ((c ^ (r & 7)) << 4)) =
+            *reinterpret_cast<const uint4 *>(p.wpack + (size_t)(nhalf * 128 + r) * 64 + c * 8);
+    }
+    for (int i = threadIdx.x; i < 256 * 8; i += 256) *reinterpret_cast<uint4 *>(sA + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 4 * 128; i += 256) s_par[i] = p.par[(i >> 7) * 256 + nhalf * 128 + (i & 127)];
+    for (int i = threadIdx.x; i < Cfg::IN_BYTES; i += 256) s_in[i] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        if (p.has_q) tma_prefetch_desc(&tmOq);
+        if (p.has_a) tma_prefetch_desc(&tmOa);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pos = threadIdx.x;                           // padded row of the board owned by this thread (im2col + epilogue)
+    const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
+    const bool live = yy >= 0 && yy < p.H && xx < p.W;
+    const uint32_t mask = live ? 0xffffffffu : 0u;
+    const int pitch = (p.W + 2) * 2;                       // zero-bordered board, 2 bytes (planes) per cell
+    const int q = warp & 3, sub = warp >> 2;               // TMEM lane quarter / 128-row half: rows sub*128 + q*32 + lane = pos
+    const uint32_t a_row = smem_u32(sA) + (uint32_t)(pos * 128);
+    const uint32_t par_addr = smem_u32(s_par), stage_addr = smem_u32(sStage + warp * 2 * 2048);
+    const uint32_t a_lo = umma_desc_lo(smem_u32(sA)), b_lo = umma_desc_lo(smem_u32(sB));
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    const int ncell = p.H * p.W;
+    uint32_t ph = 0;
+
+    for (int b = b0; b < cnt; b += bstep, ph ^= 1) {
+        // ---- board -> zero-bordered int8 tile
+        if (threadIdx.x < ncell) {
+            const int y = threadIdx.x / p.W, x = threadIdx.x - y * p.W;
+            *reinterpret_cast<uint16_t *>(s_in + (y + 1) * pitch + (x + 1) * 2) =
+                *reinterpret_cast<const uint16_t *>(p.states + ((size_t)b * ncell + threadIdx.x) * 2);
+        }
+        __syncthreads();
+        // ---- im2col row: 9 taps x 2 planes (k = tap*2 + plane), repeated for the lo parts of the weights
+        if (live) {
+            uint32_t w[10];
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const uint16_t two = *reinterpret_cast<const uint16_t *>(s_in + (yy + t / 3) * pitch + (xx + t % 3) * 2);
+                const int v0 = (int)(int8_t)(two & 0xff), v1 = (int)(int8_t)(two >> 8);
+                // -1 / 0 / +1 -> bf16 bits 0xBF80 / 0 / 0x3F80
+                const uint32_t h0 = v0 == 0 ? 0u : (v0 > 0 ? 0x3F80u : 0xBF80u), h1 = v1 == 0 ? 0u : (v1 > 0 ? 0x3F80u : 0xBF80u);
+                w[t] = h0 | (h1 << 16);
+            }
+            w[9] = 0u;
+            const uint32_t sw = (uint32_t)(pos & 7);
+            // words 0..8 = k 0..17, words 9..17 = k 18..35 (same entries), words 18, 19 = 0
+            sts128(a_row + ((0u ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            sts128(a_row + ((1u ^ sw) << 4), w[4], w[5], w[6], w[7]);
+            sts128(a_row + ((2u ^ sw) << 4), w[8], w[0], w[1], w[2]);
+            sts128(a_row + ((3u ^ sw) << 4), w[3], w[4], w[5], w[6]);
+            sts128(a_row + ((4u ^ sw) << 4), w[7], w[8], w[9], w[9]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // ---- D[256 rows][128 filters] = A[256][48] x B[128][48]^T : 2 halves x 3 k-steps
+        if (warp == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    umma_bf16_elect<false>(tmem_base + (uint32_t)(s * 128), a_lo + (uint32_t)(s * 1024 + k * 2), b_lo + (uint32_t)(k * 2),
+                                           idesc, k > 0 ? 1u : 0u);
+            umma_commit_elect<false>(bar);
+        }
+        mbar_wait(bar, ph);
+        tc_fence_after();
+        // ---- epilogue: this thread's row, 4 pieces of 32 filters
+        {
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 128);
+            const int row0 = b * 256 + sub * 128 + q * 32;
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(t_acc, ra);
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                tmem_ld_wait_dep(ra);
+                tmem_ld_32x32(t_acc + (uint32_t)(c * 64 + 32), rb);
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+                stem_piece(ra, par_addr, 2 * c, p.relu != 0, p.has_q != 0, p.has_a != 0, stage_addr, mask, lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.has_q) tma_store_2d_addr(&tmOq, stage_addr, nhalf * 128 + c * 64, row0);
+                    if (p.has_a) tma_store_2d_addr(&tmOa, stage_addr + 2048, nhalf * 128 + c * 64, row0);
+                    tma_store_commit();
+                }
+                tmem_ld_wait_dep(rb);
+                if (c == 0) tmem_ld_32x32(t_acc + 64u, ra);
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+                stem_piece(rb, par_addr, 2 * c + 1, p.relu != 0, p.has_q != 0, p.has_a != 0, stage_addr, mask, lane);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.has_q) tma_store_2d_addr(&tmOq, stage_addr, nhalf * 128 + c * 64 + 32, row0);
+                    if (p.has_a) tma_store_2d_addr(&tmOa, stage_addr + 2048, nhalf * 128 + c * 64 + 32, row0);
+                    tma_store_commit();
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // TMEM, the A tile and the input tile are free for the next board
+    }
+    if (lane == 0) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+} // namespace gaz_stem
