@@ -151,7 +151,7 @@ class SelfPlayBench:
         self.next_player = np.full(n_games, -1, np.int32)
         self.alive = np.ones(n_games, bool)
         self.launches = 0
-        self.per_round_launches = 3 + 1 + self.net.n_ops  # counter reset, select, expand + chunk count + net ops
+        self.per_round_launches = 3 + 1 + self.net.n_launches  # counter reset, select, expand + chunk count + network kernels
 
     # ---- Self_Play.play pieces -------------------------------------------------------------
     def start(self):
@@ -172,7 +172,7 @@ class SelfPlayBench:
             m[:, k] = 1 if mask is None else mask
             if e.new_roots(m.reshape(-1)) > 0:
                 e.eval_net()
-                self.launches += 1 + self.net.n_ops
+                self.launches += 1 + self.net.n_launches
             e.expand()
             self.launches += 3
 
@@ -211,7 +211,7 @@ class SelfPlayBench:
         pa = np.repeat(np.where(self.alive, act, -1).astype(np.int16), self.tpg)
         if e.prune(pa, create_new_root=self.gumbel) > 0:  # Gumbel: tree rebuilt every move (Self_Play.py:151-153)
             e.eval_net()
-            self.launches += 1 + self.net.n_ops
+            self.launches += 1 + self.net.n_launches
         e.expand()
         self.launches += 6
         self._begin_run()

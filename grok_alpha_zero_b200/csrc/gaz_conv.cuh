@@ -92,14 +92,15 @@ constexpr int SLAB_BOX_ROWS = SLAB_ROWS / 2;
 
 template <int BN, bool PAIR> struct BoardCfg {
     static constexpr int NSLAB = PAIR ? 4 : 3;
-    static constexpr int NB = 4;
+    static constexpr int NB = BN <= 32 ? 16 : (BN <= 64 ? 8 : 4);  // weight-tile ring: small tiles are consumed in ~100 cycles each,
+                                                                   // the ring has to span the L2 latency
     static constexpr int NSTAGE = PAIR ? 2 : 1; // 32-row x 32-channel bf16 staging tiles per epilogue warp (TMA store source)
     static constexpr int STAGE_BYTES = 8 * NSTAGE * 2048;
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN; // weight rows (output channels) this CTA stages per tile
     static constexpr int B_BYTES = B_ROWS * 128;
     static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;
     static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [8 warps][BN], mean, hidden, gate
-    static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+    static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ +
                                 SE_FLOATS * 4;
 };
 
@@ -134,7 +135,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t *a_full = bars, *a_empty = bars + NSLAB, *b_full = bars + 2 * NSLAB, *b_empty = bars + 2 * NSLAB + NB;
     uint64_t *tfull = bars + 2 * NSLAB + 2 * NB, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
-    float *s_se = (float *)(bars + 32);
+    float *s_se = (float *)(bars + 64);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0; // 0 = leader (issues the MMAs, owns the full/tempty barriers)

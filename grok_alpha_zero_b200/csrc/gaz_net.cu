@@ -1546,7 +1546,12 @@ int gaz_rounds_net_async(gaz_engine *e, int n_rounds) {
 
 int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
 
-int gaz_net_launches_per_forward(gaz_net *n) { return n ? (int)n->ops.size() : 0; }
+int gaz_net_launches_per_forward(gaz_net *n) { // kernels actually launched: ops folded into another op's kernel do not count
+    if (!n) return 0;
+    int k = 0;
+    for (auto &op : n->ops) k += (op.skip || op.in_block) ? 0 : 1;
+    return k;
+}
 
 /* profile = number of conv launches to keep events for (0 disables).  While enabled every tcgen05 conv
  * launch is bracketed by CUDA events on the launching stream. */

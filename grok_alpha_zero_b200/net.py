@@ -263,6 +263,7 @@ class Net:
         if rc < 0:
             raise EngineError(self.lib.gaz_last_error().decode())
         self._h = h
+        self.n_launches = int(self.lib.gaz_net_launches_per_forward(h))   # kernels per forward (fused ops launch nothing)
 
     def _ck(self, rc):
         if rc < 0:
