@@ -1,2 +1,2 @@
-timeout 300 python bench.py --steps 3 --warmup 3 --presearch 8 --no-cpu-baseline > gpurun_out/b_small.json 2> gpurun_out/b_small.err; echo rc=$?
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:res_block_kernel -s 21 -c 2 -o gpurun_out/prof_block_r2 -f python bench.py --steps 3 --warmup 3 --presearch 8 --no-cpu-baseline > gpurun_out/ncu_blk.log 2>&1; echo rc=$?; ls -la gpurun_out/*.ncu-rep
+timeout 600 python -m pytest tests/test_net_gpu.py -x -q 2>&1 | tail -3
+for d in 0 0; do timeout 120 python tests/quick_net_bench.py gomoku 16384 2>&1 | grep -E "batch 16384|per conv" | tail -7; done
