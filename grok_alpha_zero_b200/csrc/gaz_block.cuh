@@ -179,40 +179,29 @@ __device__ __forceinline__ void e1_piece(const uint32_t (&r)[32], uint32_t par_a
     }
 }
 
-// epilogue 1 for one 128-row half of a board, this warp's 32 rows x 128 channels, in two parts.
-// Part 1: wait for conv1, convert channels 0..63 into K-block 0 of the slab (the TMEM load of the next 32-column piece in
-// flight while the current one is converted), pull channels 64..127 into registers, publish: from here on the accumulator
-// set is drained and conv2 may start on K-block 0 (its first MMA overwrites all 128 columns).
-__device__ __forceinline__ void e1_part1(uint64_t *acc1_full, uint64_t *e1_half, uint32_t ph, bool work, uint32_t t_sub,
-                                         uint32_t par_addr, uint32_t sH_addr, int srow, bool live, int lane,
-                                         uint32_t (&ra)[32], uint32_t (&rb)[32]) {
+// epilogue 1 for one 128-row half of a board: this warp's 32 rows x 128 channels, four 32-column pieces, the TMEM load of
+// the next piece in flight while the current one is converted
+__device__ __forceinline__ void e1_drain(uint32_t t_sub, uint32_t par_addr, uint32_t sH_addr, int srow, bool live) {
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(t_sub, ra);
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        tmem_ld_wait_dep(ra);
+        tmem_ld_32x32(t_sub + (uint32_t)(c * 64 + 32), rb);
+        e1_piece(ra, par_addr, sH_addr, 2 * c, srow, live);
+        tmem_ld_wait_dep(rb);
+        if (c == 0) tmem_ld_32x32(t_sub + 64u, ra);
+        e1_piece(rb, par_addr, sH_addr, 2 * c + 1, srow, live);
+    }
+}
+// one board of epilogue 1 for a whole warp: wait for conv1, drain, publish the slab rows to the async proxy, arrive
+__device__ __forceinline__ void e1_board(uint64_t *acc1_full, uint64_t *e1_done, uint32_t ph, bool work, uint32_t t_sub,
+                                         uint32_t par_addr, uint32_t sH_addr, int srow, bool live, int lane) {
     mbar_wait(acc1_full, ph);
     tc_fence_after();
-    if (work) {
-        tmem_ld_32x32(t_sub, ra);
-        tmem_ld_wait_dep(ra);
-        tmem_ld_32x32(t_sub + 32u, rb);
-        e1_piece(ra, par_addr, sH_addr, 0, srow, live);
-        tmem_ld_wait_dep(rb);
-        tmem_ld_32x32(t_sub + 64u, ra);
-        e1_piece(rb, par_addr, sH_addr, 1, srow, live);
-        tmem_ld_32x32(t_sub + 96u, rb);
-        tmem_ld_wait_dep(ra);
-        tmem_ld_wait_dep(rb);
-    }
+    if (work) e1_drain(t_sub, par_addr, sH_addr, srow, live);
     fence_proxy_async();
     tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_leader(e1_half);
-}
-// Part 2: convert the channels held in registers into K-block 1 of the slab while conv2 already runs on K-block 0
-__device__ __forceinline__ void e1_part2(uint64_t *e1_done, bool work, uint32_t par_addr, uint32_t sH_addr, int srow, bool live,
-                                         int lane, uint32_t (&ra)[32], uint32_t (&rb)[32]) {
-    if (work) {
-        e1_piece(ra, par_addr, sH_addr, 2, srow, live);
-        e1_piece(rb, par_addr, sH_addr, 3, srow, live);
-    }
-    fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive_leader(e1_done);
 }
@@ -230,7 +219,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t *sStage = sW + NW * Cfg::W_BYTES;
     uint64_t *bars = (uint64_t *)(sStage + Cfg::STAGE_BYTES);
     uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 4 + NW;
-    uint64_t *acc1_full = bars + 4 + 2 * NW, *e1_done = acc1_full + 1, *e1_half = acc1_full + 2,
+    uint64_t *acc1_full = bars + 4 + 2 * NW, *e1_done = acc1_full + 1, *h_empty = acc1_full + 2,
              *acc2_full = acc1_full + 3 /*[2]*/, *acc2_empty = acc1_full + 5 /*[2]*/;
     uint32_t *tmem_slot = (uint32_t *)(acc1_full + 7);
     float *s_se = (float *)(bars + 64);
@@ -255,7 +244,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < NW; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         mbar_init(acc1_full, 1);
         mbar_init(e1_done, 16);     // 8 epilogue-1 warps (two groups) of each CTA arrive on the leader's copy
-        mbar_init(e1_half, 16);
+        mbar_init(h_empty, 1);
         for (int a = 0; a < 2; a++) { mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], 16); } // 8 epilogue-2 warps of each CTA
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -278,11 +267,8 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t e1_t = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)(e1_sub * BN);
     const uint32_t sH_addr = smem_u32(sH), par_addr = smem_u32(s_e1par);
     const bool e1_off = (dbg & 512) != 0;
-    uint32_t e1_ra[32], e1_rb[32];
-#define E1_PART1(it_) e1_part1(acc1_full, e1_half, (uint32_t)((it_) & 1), (2 * lt + rank) < n_tiles && !e1_off, \
-                               e1_t + (uint32_t)(((it_) & 1) * 2 * BN), par_addr, sH_addr, e1_srow, e1_live, lane, e1_ra, e1_rb)
-#define E1_PART2() e1_part2(e1_done, (2 * lt + rank) < n_tiles && !e1_off, par_addr, sH_addr, e1_srow, e1_live, lane, e1_ra, e1_rb)
-#define E1_BOARD(it_) do { E1_PART1(it_); E1_PART2(); } while (0)
+#define E1_BOARD(it_) e1_board(acc1_full, e1_done, (uint32_t)((it_) & 1), (2 * lt + rank) < n_tiles && !e1_off, \
+                               e1_t + (uint32_t)(((it_) & 1) * 2 * BN), par_addr, sH_addr, e1_srow, e1_live, lane)
 
     if (warp == 0) { // ---------------- slab TMA producer (one lane) + epilogue 1, second half
         const int half = p.nkc1 >> 1;
@@ -343,28 +329,17 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * BN);
                 for (int cv = 0; cv < 2; cv++) {
                     TK_BEGIN();
-                    if (cv == 1) {
-                        E1_PART1(it);                  // the issuer has nothing to issue meanwhile: it drains too
-                        mbar_wait(e1_half, ph);        // set drained, K-block 0 of the slab rewritten (both CTAs)
-                        TK_END(tk_e1);
-                    } else {
-                        mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
-                        TK_END(tk_e2);
-                    }
+                    if (cv == 1) E1_BOARD(it);                         // the issuer has nothing to issue meanwhile: it drains too
+                    if (cv == 0) mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
+                    else mbar_wait(e1_done, ph);                       // epilogue 1: set drained, slab H written (both CTAs)
+                    if (cv == 0) TK_END(tk_e2); else TK_END(tk_e1);
                     tc_fence_after();
                     const int nkc = cv == 0 ? p.nkc1 : 2;
                     for (int kc = 0; kc < nkc; kc++) {
                         const int sl = kc & 1;
                         TK_BEGIN();
-                        if (cv == 0) {
-                            mbar_wait(&x_full[sl], (uint32_t)(it * (p.nkc1 >> 1) + (kc >> 1)) & 1u);
-                            TK_END(tk_w);
-                        } else if (kc == 1) {
-                            E1_PART2();                // its own share of K-block 1, while the tensor pipe works on K-block 0
-                            mbar_wait(e1_done, ph);    // K-block 1 of the slab rewritten (both CTAs)
-                            TK_END(tk_e1);
-                            tc_fence_after();
-                        }
+                        if (cv == 0) mbar_wait(&x_full[sl], (uint32_t)(it * (p.nkc1 >> 1) + (kc >> 1)) & 1u);
+                        TK_END(tk_w);
                         const uint32_t slab_lo = umma_desc_lo(smem_u32(sX + sl * SLAB_BYTES) + (uint32_t)(HALO * 128));
                         int dy = -1, dx = -1;
                         for (int tap = 0; tap < 9; tap++) {
