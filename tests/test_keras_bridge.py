@@ -1,0 +1,61 @@
+"""CPU suite: Keras checkpoint bridge -- automatic layer names replayed from the reference builders'
+creation order, import/export round trip, loud failures on missing or mis-shaped variables."""
+import numpy as np
+import pytest
+
+from grok_alpha_zero_b200 import keras_bridge as kb
+from grok_alpha_zero_b200 import netspec
+
+
+def test_gomoku_names_follow_creation_order():
+    spec = netspec.build_spec("gomoku", "softmax", use_se=False)       # Gomoku/Build_Model.py:21-86, 10 blocks
+    n = kb.keras_layer_names(spec)
+    assert n["eyes"] == "conv2d" and n["eyes_bn"] == "batch_normalization"
+    # ResNet_Block.__init__ creates bn1, conv1, bn2, conv2, residual_conv (Net/ResNet/ResNet_Block.py:11-20)
+    assert (n["block0.bn1"], n["block0.conv1"], n["block0.bn2"], n["block0.conv2"], n["block0.proj"]) == \
+        ("batch_normalization_1", "conv2d_1", "batch_normalization_2", "conv2d_2", "conv2d_3")
+    assert "block1.proj" not in n                                       # created (conv2d_6) but never built
+    assert n["block1.conv1"] == "conv2d_4" and n["block9.conv2"] == "conv2d_29"
+    assert n["policy_bn0"] == "batch_normalization_21" and n["policy_conv0"] == "conv2d_31"
+    assert n["policy_conv1"] == "conv2d_32" and n["value_conv0"] == "conv2d_33" and n["value_conv1"] == "conv2d_34"
+    assert n["policy_1"] == "policy_1" and n["value_3"] == "value_3"    # explicit names in the Gomoku builder
+    assert n["value_bn4"] == "batch_normalization_29"
+
+
+def test_connect4_and_tictactoe_dense_layers_are_auto_named():
+    n = kb.keras_layer_names(netspec.build_spec("connect4", "softmax"))
+    assert [n["policy_1"], n["policy_2"], n["policy_3"], n["value_1"], n["value_2"], n["value_3"]] == \
+        ["dense", "dense_1", "dense_2", "dense_3", "dense_4", "dense_5"]
+    assert n["policy_conv0"] == "conv2d_16" and n["value_conv0"] == "conv2d_17"     # 1 + 5 * 3 convolutions before
+    n = kb.keras_layer_names(netspec.build_spec("tictactoe", "softmax"))
+    assert n["block0.proj"] == "conv2d_3" and n["policy_conv0"] == "conv2d_7" and n["value_bn0"] == "batch_normalization_6"
+
+
+@pytest.mark.parametrize("game,over,prefix", [("gomoku", dict(use_se=False, num_blocks=3), "res_net__block/"),
+                                              ("connect4", {}, ""), ("tictactoe", {}, "functional/")])
+def test_round_trip(game, over, prefix):
+    spec = netspec.build_spec(game, "softmax", **over)
+    W = netspec.init_weights(spec, seed=5)
+    exported = kb.export_keras_weights(spec, W, prefix=prefix)
+    exported = {k + ":0": v for k, v in exported.items()}              # Keras-2 spelling of a variable name
+    back = kb.import_keras_weights(spec, exported)
+    assert set(back) == set(W)
+    for k in W:
+        np.testing.assert_array_equal(back[k], W[k])
+    assert set(kb.expected_shapes(spec)) == set(W)
+
+
+def test_failures_are_loud():
+    spec = netspec.build_spec("connect4", "softmax")
+    W = netspec.init_weights(spec, seed=5)
+    ex = kb.export_keras_weights(spec, W)
+    missing = dict(ex)
+    del missing["dense_3/bias"]
+    with pytest.raises(KeyError):
+        kb.import_keras_weights(spec, missing)
+    wrong = dict(ex)
+    wrong["conv2d_1/kernel"] = np.zeros((3, 3, 128, 64), np.float32)
+    with pytest.raises(ValueError):
+        kb.import_keras_weights(spec, wrong)
+    with pytest.raises(ValueError):
+        kb.keras_layer_names(netspec.build_spec("gomoku", "softmax"))   # use_se=True: no Keras counterpart
