@@ -194,9 +194,10 @@ __device__ __forceinline__ void e1_drain(uint32_t t_sub, uint32_t par_addr, uint
         e1_piece(rb, par_addr, sH_addr, 2 * c + 1, srow, live);
     }
 }
-// one board of epilogue 1 for a whole warp: wait for conv1, drain, publish the slab rows to the async proxy, arrive
-__device__ __forceinline__ void e1_board(uint64_t *acc1_full, uint64_t *e1_done, uint32_t ph, bool work, uint32_t t_sub,
-                                         uint32_t par_addr, uint32_t sH_addr, int srow, bool live, int lane) {
+// epilogue 1 of one 128-row half for a whole warp: wait for that half of conv1, drain, publish the slab rows to the async
+// proxy, arrive
+__device__ __forceinline__ void e1_half(uint64_t *acc1_full, uint64_t *e1_done, uint32_t ph, bool work, uint32_t t_sub,
+                                        uint32_t par_addr, uint32_t sH_addr, int srow, bool live, int lane) {
     mbar_wait(acc1_full, ph);
     tc_fence_after();
     if (work) e1_drain(t_sub, par_addr, sH_addr, srow, live);
@@ -204,6 +205,22 @@ __device__ __forceinline__ void e1_board(uint64_t *acc1_full, uint64_t *e1_done,
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_leader(e1_done);
+}
+
+// MMAs of one (K-block, tap) weight tile for the 128-row halves SUBS (bit 0: rows 0..127, bit 1: rows 128..255 of each
+// CTA's board), then the tile goes back to the weight producer
+template <int SUBS>
+__device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t slab_lo, uint32_t b_lo, int tap, int Wp, uint32_t accf, uint32_t idesc) {
+    const int dy = tap / 3 - 1, dx = tap - (dy + 1) * 3 - 1;
+    const uint32_t a_lo = slab_lo + (uint32_t)((dy * Wp + dx) * 8);
+#pragma unroll
+    for (int sub = 0; sub < 2; sub++) {
+        if (!((SUBS >> sub) & 1)) continue;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            umma_bf16_elect<true>(d0 + (uint32_t)(sub * 128), a_lo + (uint32_t)(sub * 128 * 8 + k * 2), b_lo + (uint32_t)(k * 2), idesc,
+                                  k == 0 ? accf : 1u);
+    }
 }
 
 __global__ void __launch_bounds__(512, 1)
@@ -219,9 +236,9 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t *sStage = sW + NW * Cfg::W_BYTES;
     uint64_t *bars = (uint64_t *)(sStage + Cfg::STAGE_BYTES);
     uint64_t *x_full = bars, *x_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 4 + NW;
-    uint64_t *acc1_full = bars + 4 + 2 * NW, *e1_done = acc1_full + 1, *h_empty = acc1_full + 2,
-             *acc2_full = acc1_full + 3 /*[2]*/, *acc2_empty = acc1_full + 5 /*[2]*/;
-    uint32_t *tmem_slot = (uint32_t *)(acc1_full + 7);
+    uint64_t *acc1_full = bars + 4 + 2 * NW /*[2]: per 128-row half*/, *e1_done = acc1_full + 2 /*[2]*/,
+             *acc2_full = acc1_full + 4 /*[2]*/, *acc2_empty = acc1_full + 6 /*[2]*/;
+    uint32_t *tmem_slot = (uint32_t *)(acc1_full + 8);
     float *s_se = (float *)(bars + 64);
     float *s_e1par = s_se + Cfg::SE_FLOATS;   // epilogue 1: BN2 scale[128] | BN2 shift + scale * conv1 bias [128]
 
@@ -242,9 +259,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
         for (int s = 0; s < NW; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        mbar_init(acc1_full, 1);
-        mbar_init(e1_done, 16);     // 8 epilogue-1 warps (two groups) of each CTA arrive on the leader's copy
-        mbar_init(h_empty, 1);
+        for (int h = 0; h < 2; h++) { mbar_init(&acc1_full[h], 1); mbar_init(&e1_done[h], 8); } // 4 epilogue-1 warps of each CTA
         for (int a = 0; a < 2; a++) { mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], 16); } // 8 epilogue-2 warps of each CTA
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -259,22 +274,27 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // epilogue 1 is shared by two warp groups: warps 4..7 drain the first 128-row half of a board, warps 0..3 - whose own
-    // roles (TMA producers, MMA issuer) are idle exactly while conv1's accumulator is drained - the second half
-    const int e1_q = warp & 3, e1_sub = warp < 4 ? 1 : 0;
-    const int e1_pos = e1_sub * 128 + e1_q * 32 + lane, e1_srow = HALO + e1_pos;
-    const bool e1_live = (e1_pos / p.Wp) != 0 && (e1_pos % p.Wp) != p.Wp - 1;
-    const uint32_t e1_t = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)(e1_sub * BN);
+    // The two 128-row halves of a board ("sub" 0 / 1) are scheduled separately at the two hand-overs between the tensor
+    // pipe and epilogue 1, so that the pipe keeps working while conv1's accumulator is drained (C_in = 128; `defer`):
+    //   conv1     K-block 0: all taps, both halves;  K-block 1: taps 0..3 both halves, taps 4..8 half 0   -> acc1_full[0]
+    //          C: K-block 1, taps 4..8 of half 1 (they read slab rows >= 128 only)                        -> acc1_full[1]
+    //             ... while epilogue 1 rewrites rows 0..127 of the slab in place (half 0)
+    //   conv2  D: K-block 0, taps 0..5 of half 0 (rows <= 128; row 128 only for the dead output row 127)   after e1_done[0]
+    //             ... while epilogue 1 rewrites rows 128..255 (half 1)
+    //          E: K-block 0, taps 0..5 of half 1, taps 6..8 of both; K-block 1 whole                       after e1_done[1]
+    // The weight tiles of C and of D's second visit are still in the ring: the issuer keeps them (no commit to w_empty) on
+    // the first visit and rewinds its ring position for the second, so the producer's order and the 36 tiles per board
+    // are unchanged, and so is the order in which every accumulator row sees its (K-block, tap) terms.
+    // C_in = 256 (K-blocks 2, 3 overwrite 0, 1): conv1 is issued whole, conv2 as above.
+    const bool defer = p.nkc1 == 2;
     const uint32_t sH_addr = smem_u32(sH), par_addr = smem_u32(s_e1par);
     const bool e1_off = (dbg & 512) != 0;
-#define E1_BOARD(it_) e1_board(acc1_full, e1_done, (uint32_t)((it_) & 1), (2 * lt + rank) < n_tiles && !e1_off, \
-                               e1_t + (uint32_t)(((it_) & 1) * 2 * BN), par_addr, sH_addr, e1_srow, e1_live, lane)
 
-    if (warp == 0) { // ---------------- slab TMA producer (one lane) + epilogue 1, second half
+    if (warp == 0) { // ---------------- slab TMA producer (one lane)
         const int half = p.nkc1 >> 1;
         int it = 0;
-        for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
-            if (lane == 0) { // K-block kc of the input goes to slab kc & 1
+        if (lane == 0)
+            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) { // K-block kc of the input goes to slab kc & 1
                 const int t = 2 * lt + rank;
                 const int row0 = t * TILE_ROWS - HALO;
                 for (int kc = 0; kc < p.nkc1; kc++) {
@@ -287,39 +307,43 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tma_load_2d_pair(dst + SLAB_BYTES / 2, &tmA, &x_full[sl], kc * 64, row0 + SLAB_BOX_ROWS);
                 }
             }
-            __syncwarp();
-            E1_BOARD(it);
-        }
-    } else if (warp == 1) { // ---------------- weight-tile TMA producer (one lane): per board W1 (kc, tap) then W2 (kc, tap);
-        // once the ring holds the first NW tiles of conv2 there is nothing to load until conv2 starts: epilogue 1, second half
-        Ring r;
-        int it = 0;
-        for (int lt = pair0; lt < n_loop; lt += pair_step, it++)
-            for (int cv = 0; cv < 2; cv++) {
-                const int nkc = cv == 0 ? p.nkc1 : 2, cin = nkc * 64;
-                for (int kc = 0; kc < nkc; kc++)
-                    for (int tap = 0; tap < 9; tap++) {
-                        if (cv == 1 && kc * 9 + tap == NW) {
-                            __syncwarp();
-                            E1_BOARD(it);
-                        }
-                        if (lane == 0) {
-                            mbar_wait(&w_empty[r.idx], r.phase ^ 1);
-                            if (rank == 0) mbar_expect_tx(&w_full[r.idx], 2 * Cfg::W_BYTES);
-                            tma_load_2d_pair(sW + r.idx * Cfg::W_BYTES, cv == 0 ? &tmW1 : &tmW2, &w_full[r.idx],
-                                             tap * cin + kc * 64, rank * 64);
-                        }
-                        r.advance(NW);
-                    }
+    } else if (warp == 1) { // ---------------- weight-tile TMA producer (one lane), tiles in the issuer's order
+        if (lane == 0) {
+            Ring r;
+            auto load = [&](int cv, int kc, int tap, int cin) {
+                mbar_wait(&w_empty[r.idx], r.phase ^ 1);
+                if (rank == 0) mbar_expect_tx(&w_full[r.idx], 2 * Cfg::W_BYTES);
+                tma_load_2d_pair(sW + r.idx * Cfg::W_BYTES, cv == 0 ? &tmW1 : &tmW2, &w_full[r.idx], tap * cin + kc * 64, rank * 64);
+                r.advance(NW);
+            };
+            for (int lt = pair0; lt < n_loop; lt += pair_step) {
+                const int cin1 = p.nkc1 * 64;
+                for (int kc = 0; kc < p.nkc1; kc++)
+                    for (int tap = 0; tap < 9; tap++) load(0, kc, tap, cin1);
+                for (int kc = 0; kc < 2; kc++)
+                    for (int tap = 0; tap < 9; tap++) load(1, kc, tap, 128);
             }
+        }
     } else if (warp == 2) {
         if (rank == 0) { // ---------------- MMA issuer (leader CTA): whole warp, one elected lane per instruction
             constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
             Ring rw;
             uint32_t ph = 0;
             int it = 0;
-            [[maybe_unused]] long long tk_e2 = 0, tk_e1 = 0, tk_w = 0, tk0 = 0, tq = 0;
+            [[maybe_unused]] long long tk_e2 = 0, tk_e1 = 0, tk_w = 0, tk_x = 0, tk0 = 0, tq = 0;
             TK_START(tk0);
+            const uint32_t slab_lo0 = umma_desc_lo(smem_u32(sX) + (uint32_t)(HALO * 128)),
+                           slab_lo1 = umma_desc_lo(smem_u32(sX + SLAB_BYTES) + (uint32_t)(HALO * 128));
+#define TILE(SUBS_, sl_, kc_, tap_, RELEASE_) do {                                                                            \
+        TK_BEGIN();                                                                                                    \
+        mbar_wait(&w_full[rw.idx], rw.phase);                                                                          \
+        TK_END(tk_w);                                                                                                  \
+        tc_fence_after();                                                                                              \
+        issue_tile<SUBS_>(d0, (sl_) ? slab_lo1 : slab_lo0, umma_desc_lo(smem_u32(sW + rw.idx * Cfg::W_BYTES)), tap_, p.Wp,            \
+                          (uint32_t)(((kc_) | (tap_)) != 0), idesc);                                                   \
+        if (RELEASE_) umma_commit_elect<true>(&w_empty[rw.idx]);                                                       \
+        rw.advance(NW);                                                                                                \
+    } while (0)
             for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1, it++) {
                 // Accumulator set `as` (256 TMEM columns) serves BOTH convolutions of this board: conv1 fills it, epilogue 1
                 // drains it into slab H, conv2 refills it, epilogue 2 reads it - while the next board already runs both of
@@ -327,62 +351,74 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int as = it & 1;
                 const uint32_t sph = (uint32_t)((it >> 1) & 1);
                 const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * BN);
-                for (int cv = 0; cv < 2; cv++) {
+                // ---- conv1
+                TK_BEGIN();
+                mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
+                TK_END(tk_e2);
+                tc_fence_after();
+                Ring hold;
+                for (int kc = 0; kc < p.nkc1; kc++) {
+                    const int sl = kc & 1;
                     TK_BEGIN();
-                    if (cv == 1) E1_BOARD(it);                         // the issuer has nothing to issue meanwhile: it drains too
-                    if (cv == 0) mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
-                    else mbar_wait(e1_done, ph);                       // epilogue 1: set drained, slab H written (both CTAs)
-                    if (cv == 0) TK_END(tk_e2); else TK_END(tk_e1);
+                    mbar_wait(&x_full[sl], (uint32_t)(it * (p.nkc1 >> 1) + (kc >> 1)) & 1u);
+                    TK_END(tk_x);
                     tc_fence_after();
-                    const int nkc = cv == 0 ? p.nkc1 : 2;
-                    for (int kc = 0; kc < nkc; kc++) {
-                        const int sl = kc & 1;
-                        TK_BEGIN();
-                        if (cv == 0) mbar_wait(&x_full[sl], (uint32_t)(it * (p.nkc1 >> 1) + (kc >> 1)) & 1u);
-                        TK_END(tk_w);
-                        const uint32_t slab_lo = umma_desc_lo(smem_u32(sX + sl * SLAB_BYTES) + (uint32_t)(HALO * 128));
-                        int dy = -1, dx = -1;
-                        for (int tap = 0; tap < 9; tap++) {
-                            TK_BEGIN();
-                            mbar_wait(&w_full[rw.idx], rw.phase);
-                            TK_END(tk_w);
-                            tc_fence_after();
-                            const uint32_t b_lo = umma_desc_lo(smem_u32(sW + rw.idx * Cfg::W_BYTES));
-                            const uint32_t a_lo = slab_lo + (uint32_t)((dy * p.Wp + dx) * 8);
-                            const uint32_t accf = (uint32_t)((kc | tap) != 0);
-#pragma unroll
-                            for (int sub = 0; sub < 2; sub++)
-#pragma unroll
-                                for (int k = 0; k < 4; k++)
-                                    umma_bf16_elect<true>(d0 + (uint32_t)(sub * BN), a_lo + (uint32_t)(sub * 128 * 8 + k * 2),
-                                                          b_lo + (uint32_t)(k * 2), idesc, k == 0 ? accf : 1u);
-                            umma_commit_elect<true>(&w_empty[rw.idx]);
-                            rw.advance(NW);
-                            if (++dx == 2) { dx = -1; dy++; }
-                        }
-                        // slab sl is free again: for the next K-block pair of this board's input (C_in = 256), or, after conv2 has
-                        // read H from it, for the next board
-                        if (cv == 1 || kc + 2 < nkc) umma_commit_elect<true>(&x_empty[sl]);
+                    for (int tap = 0; tap < 4; tap++) TILE(3, sl, kc, tap, true);
+                    if (defer && kc == 1) {
+                        hold = rw;
+                        for (int tap = 4; tap < 9; tap++) TILE(1, sl, kc, tap, false);   // tiles stay for phase C
+                    } else {
+                        for (int tap = 4; tap < 9; tap++) TILE(3, sl, kc, tap, true);
                     }
-                    if (cv == 0) umma_commit_elect<true>(acc1_full);
-                    else umma_commit_elect<true>(&acc2_full[as]);
+                    if (kc + 2 < p.nkc1) umma_commit_elect<true>(&x_empty[sl]);   // C_in = 256: the slab takes K-block kc + 2 next
                 }
+                umma_commit_elect<true>(&acc1_full[0]);
+                if (defer) {
+                    rw = hold;
+                    for (int tap = 4; tap < 9; tap++) TILE(2, 1, 1, tap, true);          // phase C
+                }
+                umma_commit_elect<true>(&acc1_full[1]);
+                // ---- conv2 (input: slab H = the two slabs, rewritten in place by epilogue 1)
+                TK_BEGIN();
+                mbar_wait(&e1_done[0], ph);            // half 0 of the set drained, rows 0..127 of H written (both CTAs)
+                TK_END(tk_e1);
+                tc_fence_after();
+                hold = rw;
+                for (int tap = 0; tap < 6; tap++) TILE(1, 0, 0, tap, false);             // phase D, tiles stay for E
+                TK_BEGIN();
+                mbar_wait(&e1_done[1], ph);            // half 1 drained, rows 128..255 written
+                TK_END(tk_e1);
+                tc_fence_after();
+                rw = hold;
+                for (int tap = 0; tap < 6; tap++) TILE(2, 0, 0, tap, true);              // phase E
+                for (int tap = 6; tap < 9; tap++) TILE(3, 0, 0, tap, true);
+                umma_commit_elect<true>(&x_empty[0]);  // conv2 has read K-block 0 of H: the slab is free for the next board
+                for (int tap = 0; tap < 9; tap++) TILE(3, 1, 1, tap, true);
+                umma_commit_elect<true>(&x_empty[1]);
+                umma_commit_elect<true>(&acc2_full[as]);
             }
+#undef TILE
             if ((dbg & 1024) && blockIdx.x == 0 && lane == 0)
             {
                 TK_STOP(tk0);
-                TK_PRINT("issuer: boards %d total %lld wait_e2 %lld wait_e1 %lld wait_loads %lld\n", it, tk0, tk_e2, tk_e1, tk_w);
+                TK_PRINT("issuer: boards %d total %lld wait_e2 %lld wait_e1 %lld wait_weights %lld wait_slab %lld\n", it, tk0, tk_e2, tk_e1,
+                         tk_w, tk_x);
             }
-        } else { // follower CTA: its warp 2 only drains
-            int it = 0;
-            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) E1_BOARD(it);
         }
-    } else if (warp < 8) { // ---------------- warp 3 and warps 4..7: epilogue 1 only (acc1 -> relu(BN2(conv1 + b1)) -> slab, bf16, swizzled)
+    } else if (warp >= 4 && warp < 8) { // ---------------- epilogue 1 (acc1 -> relu(BN2(conv1 + b1)) -> slab, bf16, swizzled), half 0 then half 1
+        const int e1_q = warp & 3;
         int it = 0;
         [[maybe_unused]] long long tk_work = 0, tq = 0;
         for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
+            const bool work = (2 * lt + rank) < n_tiles && !e1_off;
             TK_BEGIN();
-            E1_BOARD(it);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const int pos = h * 128 + e1_q * 32 + lane;
+                const bool live = (pos / p.Wp) != 0 && (pos % p.Wp) != p.Wp - 1;
+                const uint32_t t_sub = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)((it & 1) * 2 * BN + h * BN);
+                e1_half(&acc1_full[h], &e1_done[h], (uint32_t)(it & 1), work, t_sub, par_addr, sH_addr, HALO + pos, live, lane);
+            }
             TK_END(tk_work);
         }
         if ((dbg & 1024) && blockIdx.x == 0 && warp == 4 && lane == 0) TK_PRINT("epilogue1: wait + work %lld\n", tk_work);
