@@ -503,7 +503,7 @@ def main():
                 import cpu_selfplay
                 cores = os.cpu_count() or 1
                 spc = 4
-                csteps = 24 if cfg["game"] == "gomoku" else 200
+                csteps = 96 if cfg["game"] == "gomoku" else 400   # ~10 s of CPU work on the bounded sample
                 r = cpu_selfplay.run_sample(cfg["game"], sb.spec, sb.weights, n_workers=cores, sims_per_step=spc,
                                             steps=csteps, warmup=2, c_puct_init=cfg["c_puct_init"], opening=cfg["opening"],
                                             torch_threads=cores)

@@ -457,6 +457,61 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
     }
 }
 
+// Small head convolutions that read the blocked fp32 residual stream directly (Connect4: 3x3 C128 -> C8 on the trunk
+// output, Connect4/Build_Model.py:27,48): thread per (leaf, cell) like headconv_kernel and the same fmaf order (bit-identical
+// results), but every load is one 8-channel piece of the blocked layout (ld.global.v8: the 32 lanes of a warp read 1 KB
+// contiguous) and the weights of a piece come from shared memory as broadcast float4s.
+template <int COUT>
+__global__ void __launch_bounds__(128) headconv_f32_kernel(HeadConvArgs p) {
+    extern __shared__ __align__(16) float s_w[];   // [tap][Cin][COUT]
+    const int nW = p.K * p.K * p.Cin * COUT;
+    for (int i = threadIdx.x; i < nW; i += blockDim.x) s_w[i] = p.w[i];
+    __syncthreads();
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int ncell = p.H * p.W;
+    const long long total = (long long)cnt * ncell;
+    const int kh = p.K >> 1, npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
+    const float *in = (const float *)p.in;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / ncell), cell = (int)(idx - (long long)b * ncell);
+        const int y = cell / p.W, x = cell - y * p.W;
+        const long long r0 = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
+        float acc[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; j++) acc[j] = p.bias[j];
+        for (int ky = 0; ky < p.K; ky++)
+            for (int kx = 0; kx < p.K; kx++) {
+                const long long r = r0 + (ky - kh) * p.Wp + (kx - kh);
+                if (r < 0 || r >= p.in_rows) continue;
+                // gaz_conv::f32_blk_index(r, 8 * pc, Cin) = (((r >> 5) * (Cin >> 5) + (pc >> 2)) << 10) + ((pc & 3) << 8) + ((r & 31) << 3)
+                const float *base = in + ((size_t)((r >> 5) * cb_per_row) << 10) + (size_t)((r & 31) << 3);
+                const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * COUT;
+#pragma unroll 2
+                for (int pc = 0; pc < npiece; pc++) {
+                    float a[8];
+                    gaz_conv::ldg256(base + ((size_t)(pc >> 2) << 10) + (size_t)((pc & 3) << 8), a);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float4 *w4 = reinterpret_cast<const float4 *>(wp + (size_t)(pc * 8 + c) * COUT);
+#pragma unroll
+                        for (int q = 0; q < COUT / 4; q++) {
+                            const float4 w = w4[q];
+                            acc[4 * q] = fmaf(a[c], w.x, acc[4 * q]);
+                            acc[4 * q + 1] = fmaf(a[c], w.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(a[c], w.z, acc[4 * q + 2]);
+                            acc[4 * q + 3] = fmaf(a[c], w.w, acc[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+        float *op = p.out + (size_t)b * ncell * COUT + (size_t)cell * COUT;
+#pragma unroll
+        for (int q = 0; q < COUT / 4; q++)
+            *reinterpret_cast<float4 *>(op + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+}
+
 // Head convolutions with few taps*channels: one warp per output cell, lane = input channel (CPL channels per
 // lane, coalesced row loads), weights in registers, COUT partial sums folded across the warp with a halving
 // butterfly (COUT-1 + log2(32/COUT) shuffles instead of 5*COUT).
@@ -875,6 +930,7 @@ struct gaz_net {
     int use_graph;         // GAZ_GRAPH (default 1): replay a captured CUDA graph per search round
     int stem_tc;           // GAZ_STEM_TC (default 1): Gomoku-shaped stem as an implicit GEMM on tcgen05 (gaz_stem.cuh)
     int head_mma;          // GAZ_HEAD_MMA (default 1): 32-channel head convolutions on mma.sync instead of CUDA cores
+    int head_f32v;         // GAZ_HEAD_F32V (default 1): head convolutions on the fp32 stream with 8-channel vector loads
     int fuse_block;        // GAZ_FUSE_BLOCK (default 1): conv1 + conv2 + SE of a residual block in one kernel (gaz_block.cuh)
     int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
     std::vector<cudaEvent_t> ev;
@@ -1120,6 +1176,13 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
 #undef HC
             if (done) break;
             if (d.cout > 16 || sm > 48 * 1024) return gaz_fail("headconv shape unsupported (cout %d, %zu B weights)", d.cout, sm);
+            if (a.in_f32 && a.layout == 0 && d.cin % 32 == 0 && n->head_f32v && (d.cout == 4 || d.cout == 8 || d.cout == 16)) {
+                const int g3 = n->n_sm * 8;
+                if (d.cout == 4) headconv_f32_kernel<4><<<g3, 128, sm, s>>>(a);
+                else if (d.cout == 8) headconv_f32_kernel<8><<<g3, 128, sm, s>>>(a);
+                else headconv_f32_kernel<16><<<g3, 128, sm, s>>>(a);
+                break;
+            }
             headconv_kernel<<<n->n_sm * 16, 128, sm, s>>>(a);
             break;
         }
@@ -1209,6 +1272,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         n->fuse_block = e6 ? atoi(e6) : 1;
         const char *e8 = getenv("GAZ_HEAD_MMA");
         n->head_mma = e8 ? atoi(e8) : 1;
+        const char *e10 = getenv("GAZ_HEAD_F32V");
+        n->head_f32v = e10 ? atoi(e10) : 1;
         const char *e9 = getenv("GAZ_STEM_TC");
         n->stem_tc = e9 ? atoi(e9) : 1;
     }

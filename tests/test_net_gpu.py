@@ -98,8 +98,9 @@ def test_closed_loop_search_with_cuda_net_is_bit_exact(game, over, iters):
 
 
 @pytest.mark.parametrize("env", [{"GAZ_CONV_T": "1"}, {"GAZ_CONV_PAIR": "0"}, {"GAZ_FUSE_BLOCK": "0"}, {"GAZ_HEAD_MMA": "0"},
-                                 {"GAZ_STEM_TC": "0"}],
-                         ids=["transposed-v3", "single-cta", "unfused-blocks", "cuda-core-head-conv", "cuda-core-stem"])
+                                 {"GAZ_STEM_TC": "0"}, {"GAZ_HEAD_F32V": "0"}],
+                         ids=["transposed-v3", "single-cta", "unfused-blocks", "cuda-core-head-conv", "cuda-core-stem",
+                              "scalar-fp32-head-conv"])
 def test_alternative_conv_kernels_stay_within_tolerance(env, monkeypatch):
     """the experimental channel-on-lanes kernel (gaz_convt.cuh) and the single-CTA form of the board kernel are
     selected by environment switches read at network creation; both must meet the same tolerance"""
