@@ -473,42 +473,75 @@ __global__ void __launch_bounds__(128) headconv_f32_kernel(HeadConvArgs p) {
     const long long total = (long long)cnt * ncell;
     const int kh = p.K >> 1, npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
     const float *in = (const float *)p.in;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(idx / ncell), cell = (int)(idx - (long long)b * ncell);
-        const int y = cell / p.W, x = cell - y * p.W;
-        const long long r0 = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
-        float acc[COUT];
+    // two consecutive cells per thread: every weight read from shared memory feeds two FMAs (the kernel is bound by the
+    // broadcast LDS.128s otherwise); a tap that falls outside the tensor contributes fmaf(0, w, acc) = acc
+    for (long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x; 2 * pr < total; pr += (long long)gridDim.x * blockDim.x) {
+        long long r0[2];
+        bool have[2];
 #pragma unroll
-        for (int j = 0; j < COUT; j++) acc[j] = p.bias[j];
+        for (int e = 0; e < 2; e++) {
+            const long long idx = 2 * pr + e;
+            have[e] = idx < total;
+            const long long id2 = have[e] ? idx : 2 * pr;
+            const int b = (int)(id2 / ncell), cell = (int)(id2 - (long long)b * ncell);
+            const int y = cell / p.W, x = cell - y * p.W;
+            r0[e] = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
+        }
+        float acc[2][COUT];
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int j = 0; j < COUT; j++) acc[e][j] = p.bias[j];
         for (int ky = 0; ky < p.K; ky++)
             for (int kx = 0; kx < p.K; kx++) {
-                const long long r = r0 + (ky - kh) * p.Wp + (kx - kh);
-                if (r < 0 || r >= p.in_rows) continue;
+                const int sh = (ky - kh) * p.Wp + (kx - kh);
+                const long long ra = r0[0] + sh, rb = r0[1] + sh;
+                const bool oka = ra >= 0 && ra < p.in_rows, okb = rb >= 0 && rb < p.in_rows;
+                if (!oka && !okb) continue;
+                const long long ca = oka ? ra : (okb ? rb : 0), cb = okb ? rb : ca;
                 // gaz_conv::f32_blk_index(r, 8 * pc, Cin) = (((r >> 5) * (Cin >> 5) + (pc >> 2)) << 10) + ((pc & 3) << 8) + ((r & 31) << 3)
-                const float *base = in + ((size_t)((r >> 5) * cb_per_row) << 10) + (size_t)((r & 31) << 3);
+                const float *basea = in + ((size_t)((ca >> 5) * cb_per_row) << 10) + (size_t)((ca & 31) << 3);
+                const float *baseb = in + ((size_t)((cb >> 5) * cb_per_row) << 10) + (size_t)((cb & 31) << 3);
                 const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * COUT;
 #pragma unroll 2
                 for (int pc = 0; pc < npiece; pc++) {
-                    float a[8];
-                    gaz_conv::ldg256(base + ((size_t)(pc >> 2) << 10) + (size_t)((pc & 3) << 8), a);
+                    float a[2][8];
+                    const size_t po = ((size_t)(pc >> 2) << 10) + (size_t)((pc & 3) << 8);
+                    gaz_conv::ldg256(basea + po, a[0]);
+                    gaz_conv::ldg256(baseb + po, a[1]);
+                    if (!oka) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) a[0][c] = 0.0f;
+                    }
+                    if (!okb) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) a[1][c] = 0.0f;
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const float4 *w4 = reinterpret_cast<const float4 *>(wp + (size_t)(pc * 8 + c) * COUT);
 #pragma unroll
                         for (int q = 0; q < COUT / 4; q++) {
                             const float4 w = w4[q];
-                            acc[4 * q] = fmaf(a[c], w.x, acc[4 * q]);
-                            acc[4 * q + 1] = fmaf(a[c], w.y, acc[4 * q + 1]);
-                            acc[4 * q + 2] = fmaf(a[c], w.z, acc[4 * q + 2]);
-                            acc[4 * q + 3] = fmaf(a[c], w.w, acc[4 * q + 3]);
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                acc[e][4 * q] = fmaf(a[e][c], w.x, acc[e][4 * q]);
+                                acc[e][4 * q + 1] = fmaf(a[e][c], w.y, acc[e][4 * q + 1]);
+                                acc[e][4 * q + 2] = fmaf(a[e][c], w.z, acc[e][4 * q + 2]);
+                                acc[e][4 * q + 3] = fmaf(a[e][c], w.w, acc[e][4 * q + 3]);
+                            }
                         }
                     }
                 }
             }
-        float *op = p.out + (size_t)b * ncell * COUT + (size_t)cell * COUT;
 #pragma unroll
-        for (int q = 0; q < COUT / 4; q++)
-            *reinterpret_cast<float4 *>(op + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        for (int e = 0; e < 2; e++) {
+            if (!have[e]) continue;
+            float *op = p.out + (size_t)(2 * pr + e) * COUT;   // [leaf][cell][COUT] = flat index * COUT
+#pragma unroll
+            for (int q = 0; q < COUT / 4; q++)
+                *reinterpret_cast<float4 *>(op + 4 * q) = make_float4(acc[e][4 * q], acc[e][4 * q + 1], acc[e][4 * q + 2], acc[e][4 * q + 3]);
+        }
     }
 }
 
@@ -770,7 +803,8 @@ struct DenseArgs {
     float *out;       // [leaf][Out]
 };
 
-// fp32 GEMM, 64x64 tile, 16-deep K slices, 4x4 outputs per thread
+// fp32 GEMM, 64x64 tile, 16-deep K slices, 4x4 outputs per thread.  The global loads of slice i+1 are issued before
+// the FMAs of slice i (register prefetch): the small head GEMMs run one CTA per SM and were bound by load latency.
 __global__ void __launch_bounds__(256) dense_kernel(DenseArgs p) {
     __shared__ float sA[16][64 + 1], sB[16][64 + 1];
     int cnt = *p.count;
@@ -783,8 +817,11 @@ __global__ void __launch_bounds__(256) dense_kernel(DenseArgs p) {
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
-    for (int k0 = 0; k0 < p.In; k0 += 16) {
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = threadIdx.x + u * 256;
             const int kk = i & 15, mm = i >> 4;
             const int k = k0 + kk, m = m0 + mm;
             float a = 0.0f;
@@ -793,14 +830,22 @@ __global__ void __launch_bounds__(256) dense_kernel(DenseArgs p) {
                 if (p.pre_affine) a = fmaf(p.pre_scale[k], a, p.pre_shift[k]);
                 if (p.pre_relu) a = fmaxf(a, 0.0f);
             }
-            sA[kk][mm] = a;
+            ra[u] = a;
+            const int nn = i & 63, kb = i >> 6;
+            const int k2 = k0 + kb, n = n0 + nn;
+            rb[u] = (k2 < p.In && n < p.Out) ? p.w[(size_t)k2 * p.Out + n] : 0.0f;
         }
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            const int nn = i & 63, kk = i >> 6;
-            const int k = k0 + kk, n = n0 + nn;
-            sB[kk][nn] = (k < p.In && n < p.Out) ? p.w[(size_t)k * p.Out + n] : 0.0f;
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.In; k0 += 16) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = threadIdx.x + u * 256;
+            sA[i & 15][i >> 4] = ra[u];
+            sB[i >> 6][i & 63] = rb[u];
         }
         __syncthreads();
+        if (k0 + 16 < p.In) fetch(k0 + 16);
 #pragma unroll
         for (int kk = 0; kk < 16; kk++) {
             float a[4], b[4];
