@@ -458,23 +458,24 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
 }
 
 // Small head convolutions that read the blocked fp32 residual stream directly (Connect4: 3x3 C128 -> C8 on the trunk
-// output, Connect4/Build_Model.py:27,48): thread per (leaf, cell) like headconv_kernel and the same fmaf order (bit-identical
-// results), but every load is one 8-channel piece of the blocked layout (ld.global.v8: the 32 lanes of a warp read 1 KB
-// contiguous) and the weights of a piece come from shared memory as broadcast float4s.
-template <int COUT>
+// output, Connect4/Build_Model.py:27,48).  Thread per pair of consecutive cells; every load is one 8-channel piece of the
+// blocked layout (ld.global.v8: the lanes of a warp read contiguous 32-byte pieces), the weights of a piece come from
+// shared memory as broadcast float4s and feed both cells.  Loop order: 8-channel piece outside, taps inside - at any time
+// a CTA works on (cells + halo) x 32 bytes, so the 9-fold re-read of the input by the taps hits L1 instead of L2
+// (tap-outside order: 1 GB of L2 reads per launch at 4096 leaves, 213 us).
+template <int COUT, int KS>
 __global__ void __launch_bounds__(128) headconv_f32_kernel(HeadConvArgs p) {
     extern __shared__ __align__(16) float s_w[];   // [tap][Cin][COUT]
-    const int nW = p.K * p.K * p.Cin * COUT;
-    for (int i = threadIdx.x; i < nW; i += blockDim.x) s_w[i] = p.w[i];
+    constexpr int kh = KS >> 1;
+    const int nW = KS * KS * p.Cin * COUT;
+    for (int i = threadIdx.x; i < nW / 4; i += blockDim.x) reinterpret_cast<float4 *>(s_w)[i] = reinterpret_cast<const float4 *>(p.w)[i];
     __syncthreads();
     int cnt = *p.count;
     if (cnt > p.max_count) cnt = p.max_count;
     const int ncell = p.H * p.W;
     const long long total = (long long)cnt * ncell;
-    const int kh = p.K >> 1, npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
+    const int npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
     const float *in = (const float *)p.in;
-    // two consecutive cells per thread: every weight read from shared memory feeds two FMAs (the kernel is bound by the
-    // broadcast LDS.128s otherwise); a tap that falls outside the tensor contributes fmaf(0, w, acc) = acc
     for (long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x; 2 * pr < total; pr += (long long)gridDim.x * blockDim.x) {
         long long r0[2];
         bool have[2];
@@ -487,53 +488,60 @@ __global__ void __launch_bounds__(128) headconv_f32_kernel(HeadConvArgs p) {
             const int y = cell / p.W, x = cell - y * p.W;
             r0[e] = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
         }
+        // per tap and cell: offset of the row's first piece in the blocked layout
+        // (gaz_conv::f32_blk_index(r, 8 * pc, Cin) = (((r >> 5) * (Cin >> 5) + (pc >> 2)) << 10) + ((pc & 3) << 8) + ((r & 31) << 3));
+        // a tap outside the tensor reads the centre row and is multiplied by 0: fmaf(0, w, acc) = acc
+        uint32_t off[KS * KS][2];
+        float live[KS * KS][2];
+#pragma unroll
+        for (int t = 0; t < KS * KS; t++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const long long r = r0[e] + (t / KS - kh) * p.Wp + (t % KS - kh);
+                const bool ok = r >= 0 && r < p.in_rows;
+                const long long rr = ok ? r : r0[e];
+                off[t][e] = (uint32_t)((((rr >> 5) * cb_per_row) << 10) + ((rr & 31) << 3));
+                live[t][e] = ok ? 1.0f : 0.0f;
+            }
         float acc[2][COUT];
 #pragma unroll
         for (int e = 0; e < 2; e++)
 #pragma unroll
             for (int j = 0; j < COUT; j++) acc[e][j] = p.bias[j];
-        for (int ky = 0; ky < p.K; ky++)
-            for (int kx = 0; kx < p.K; kx++) {
-                const int sh = (ky - kh) * p.Wp + (kx - kh);
-                const long long ra = r0[0] + sh, rb = r0[1] + sh;
-                const bool oka = ra >= 0 && ra < p.in_rows, okb = rb >= 0 && rb < p.in_rows;
-                if (!oka && !okb) continue;
-                const long long ca = oka ? ra : (okb ? rb : 0), cb = okb ? rb : ca;
-                // gaz_conv::f32_blk_index(r, 8 * pc, Cin) = (((r >> 5) * (Cin >> 5) + (pc >> 2)) << 10) + ((pc & 3) << 8) + ((r & 31) << 3)
-                const float *basea = in + ((size_t)((ca >> 5) * cb_per_row) << 10) + (size_t)((ca & 31) << 3);
-                const float *baseb = in + ((size_t)((cb >> 5) * cb_per_row) << 10) + (size_t)((cb & 31) << 3);
-                const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * COUT;
-#pragma unroll 2
-                for (int pc = 0; pc < npiece; pc++) {
-                    float a[2][8];
-                    const size_t po = ((size_t)(pc >> 2) << 10) + (size_t)((pc & 3) << 8);
-                    gaz_conv::ldg256(basea + po, a[0]);
-                    gaz_conv::ldg256(baseb + po, a[1]);
-                    if (!oka) {
+#pragma unroll 1
+        for (int pc = 0; pc < npiece; pc++) {
+            const uint32_t po = ((uint32_t)(pc >> 2) << 10) + ((uint32_t)(pc & 3) << 8);
 #pragma unroll
-                        for (int c = 0; c < 8; c++) a[0][c] = 0.0f;
-                    }
-                    if (!okb) {
+            for (int ky = 0; ky < KS; ky++) {
+                float a[KS][2][8];
 #pragma unroll
-                        for (int c = 0; c < 8; c++) a[1][c] = 0.0f;
-                    }
+                for (int kx = 0; kx < KS; kx++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) gaz_conv::ldg256(in + off[ky * KS + kx][e] + po, a[kx][e]);
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                    const int t = ky * KS + kx;
+                    const float *wp = s_w + (size_t)(t * p.Cin + pc * 8) * COUT;
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
-                        const float4 *w4 = reinterpret_cast<const float4 *>(wp + (size_t)(pc * 8 + c) * COUT);
+                        const float4 *w4 = reinterpret_cast<const float4 *>(wp + c * COUT);
+                        const float a0 = a[kx][0][c] * live[t][0], a1 = a[kx][1][c] * live[t][1];
 #pragma unroll
                         for (int q = 0; q < COUT / 4; q++) {
                             const float4 w = w4[q];
-#pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                acc[e][4 * q] = fmaf(a[e][c], w.x, acc[e][4 * q]);
-                                acc[e][4 * q + 1] = fmaf(a[e][c], w.y, acc[e][4 * q + 1]);
-                                acc[e][4 * q + 2] = fmaf(a[e][c], w.z, acc[e][4 * q + 2]);
-                                acc[e][4 * q + 3] = fmaf(a[e][c], w.w, acc[e][4 * q + 3]);
-                            }
+                            acc[0][4 * q] = fmaf(a0, w.x, acc[0][4 * q]);
+                            acc[0][4 * q + 1] = fmaf(a0, w.y, acc[0][4 * q + 1]);
+                            acc[0][4 * q + 2] = fmaf(a0, w.z, acc[0][4 * q + 2]);
+                            acc[0][4 * q + 3] = fmaf(a0, w.w, acc[0][4 * q + 3]);
+                            acc[1][4 * q] = fmaf(a1, w.x, acc[1][4 * q]);
+                            acc[1][4 * q + 1] = fmaf(a1, w.y, acc[1][4 * q + 1]);
+                            acc[1][4 * q + 2] = fmaf(a1, w.z, acc[1][4 * q + 2]);
+                            acc[1][4 * q + 3] = fmaf(a1, w.w, acc[1][4 * q + 3]);
                         }
                     }
                 }
             }
+        }
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             if (!have[e]) continue;
@@ -1221,11 +1229,13 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
 #undef HC
             if (done) break;
             if (d.cout > 16 || sm > 48 * 1024) return gaz_fail("headconv shape unsupported (cout %d, %zu B weights)", d.cout, sm);
-            if (a.in_f32 && a.layout == 0 && d.cin % 32 == 0 && n->head_f32v && (d.cout == 4 || d.cout == 8 || d.cout == 16)) {
+            if (a.in_f32 && a.layout == 0 && d.cin % 32 == 0 && n->head_f32v && (d.cout == 4 || d.cout == 8) &&
+                (d.ksize == 3 || d.ksize == 1) && ((uintptr_t)a.w & 15) == 0) {
                 const int g3 = n->n_sm * 8;
-                if (d.cout == 4) headconv_f32_kernel<4><<<g3, 128, sm, s>>>(a);
-                else if (d.cout == 8) headconv_f32_kernel<8><<<g3, 128, sm, s>>>(a);
-                else headconv_f32_kernel<16><<<g3, 128, sm, s>>>(a);
+                if (d.cout == 4 && d.ksize == 3) headconv_f32_kernel<4, 3><<<g3, 128, sm, s>>>(a);
+                else if (d.cout == 8 && d.ksize == 3) headconv_f32_kernel<8, 3><<<g3, 128, sm, s>>>(a);
+                else if (d.cout == 4) headconv_f32_kernel<4, 1><<<g3, 128, sm, s>>>(a);
+                else headconv_f32_kernel<8, 1><<<g3, 128, sm, s>>>(a);
                 break;
             }
             headconv_kernel<<<n->n_sm * 16, 128, sm, s>>>(a);
