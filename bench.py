@@ -40,16 +40,16 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     # name: game, mode, games/GPU, sims/move, iteration limit handed to run(), net overrides, c_puct, opening
     "gomoku": dict(game="gomoku", mode="puct", games=16384, sims=800, limit=1200, net={}, head="softmax",
-                   c_puct_init=4.5, opening=112, label="Gomoku 15x15 self-play, PUCT 800 sims/move (x1.5 = 1200 "
+                   c_puct_init=4.5, alpha=0.05, opening=112, label="Gomoku 15x15 self-play, PUCT 800 sims/move (x1.5 = 1200 "
                    "iterations, Self_Play.py:99), 10-block ResNet128+SE bf16, 16384 games/GPU"),
     "connect4": dict(game="connect4", mode="puct", games=4096, sims=800, limit=1200, net={}, head="softmax",
-                     c_puct_init=2.5, opening=None, label="Connect4 6x7 self-play, PUCT 800 sims/move, 5-block "
+                     c_puct_init=2.5, alpha=0.5, opening=None, label="Connect4 6x7 self-play, PUCT 800 sims/move, 5-block "
                      "ResNet128 bf16, 4096 games/GPU"),
     "gumbel": dict(game="gomoku", mode="gumbel", games=16384, sims=64, limit=64, net={}, head="stablemax",
-                   c_puct_init=4.5, opening=112, label="Gomoku 15x15 Gumbel MCTS m=16 n=64 StableMax, 10-block "
+                   c_puct_init=4.5, alpha=None, opening=112, label="Gomoku 15x15 Gumbel MCTS m=16 n=64 StableMax, 10-block "
                    "ResNet128+SE bf16, 16384 games/GPU"),
     "tictactoe": dict(game="tictactoe", mode="puct", games=4096, sims=200, limit=300, net={}, head="softmax",
-                      c_puct_init=2.5, opening=None, label="TicTacToe 3x3 self-play, PUCT 200 sims/move, small "
+                      c_puct_init=1.25, alpha=1.0, opening=None, label="TicTacToe 3x3 self-play, PUCT 200 sims/move, small "
                       "ResNet, 4096 games/GPU"),
 }
 
@@ -130,7 +130,7 @@ class SelfPlayBench:
     """Drives the engine the way Self_Play.play does (two PUCT trees per game, the tree of the side to move
     searches, both are re-rooted after the move; one fresh Gumbel tree per move)."""
 
-    def __init__(self, cfg, n_games, device):
+    def __init__(self, cfg, n_games, device, noise=True):
         from grok_alpha_zero_b200 import netspec
         from grok_alpha_zero_b200.engine import Engine
         from grok_alpha_zero_b200.net import Net
@@ -146,6 +146,17 @@ class SelfPlayBench:
                           activation_fn="stablemax" if self.gumbel else "softmax", device=device)
         self.net = Net(self.spec, self.weights, max_batch=n_games, device=device)
         self.net.attach(self.eng)
+        # exploration noise as Self_Play.py:38-69 configures the searches: Dirichlet(alpha) at every PUCT expansion
+        # (device Philox streams keyed by the global game id), Gumbel(0,1) on the root logits of every Gumbel run
+        self.noise = noise
+        rank = int(os.environ.get("RANK", "0"))
+        self.gumbel_noise = None
+        if noise and not self.gumbel:
+            gid = np.arange(n_games, dtype=np.uint64) + np.uint64(rank * n_games)
+            self.eng.set_tree_keys(np.repeat(gid, self.tpg) * np.uint64(self.tpg) + np.tile(np.arange(self.tpg, dtype=np.uint64), n_games))
+            self.eng.set_noise(cfg["alpha"], 0.25, seed=2024)
+        if noise and self.gumbel:
+            self.gumbel_noise = np.random.default_rng(2024 + rank).gumbel(size=(n_games, 256))
         self.moves = 0
         self.sims_done = 0       # simulations of finished runs
         self.next_player = np.full(n_games, -1, np.int32)
@@ -185,6 +196,9 @@ class SelfPlayBench:
         return lim.reshape(-1)
 
     def _begin_run(self):
+        if self.gumbel_noise is not None:   # MCTS_Gumbel.py:592-594; a fresh draw per move (rows rotate through one table)
+            self.gumbel_noise = np.roll(self.gumbel_noise, 1, axis=0)
+            self.eng.set_gumbel_noise(self.gumbel_noise)
         self.eng.run_begin(self._limits())
         self.launches += 1
 
@@ -357,6 +371,7 @@ def main():
     ap.add_argument("--presearch", type=int, default=-1,
                     help="untimed rounds before warm-up so trees are mid-search (default: past the forced root expansion)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-noise", action="store_true", help="searches without Dirichlet / Gumbel exploration noise")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.impl == "reference":
@@ -377,7 +392,7 @@ def main():
     n_games = args.games or cfg["games"]
     peaks = load_peaks()
 
-    sb = SelfPlayBench(cfg, n_games, local)
+    sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise)
     sb.start()
     presearch = args.presearch
     if presearch < 0:
@@ -465,6 +480,8 @@ def main():
             e2e_sims += got
         assert int(vis.sum()) > 0
     h2d = boards.nbytes + n_games * 16 + sb.eng.n_trees * (4 + 1)   # boards + meta + limits + root mask
+    if sb.gumbel_noise is not None:
+        h2d += sb.eng.n_trees * 256 * 8                              # Gumbel(0,1) root noise table
     d2h = vis.nbytes + val.nbytes + info.nbytes
     e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(sims), float(evals), float(e2e_sims), float(sb.moves)], dtype=torch.float64, device="cuda")
@@ -487,7 +504,10 @@ def main():
                                 presearch_rounds=presearch, weights="random-init he_normal, seed 0",
                                 l2="per-step working set (%.1f GB of activations + trees) is far larger than the 126 MB L2; no flush needed"
                                    % (sb.net.bytes_allocated() / 1e9),
-                                sharding="games by index, no collective on the search path"),
+                                sharding="games by index, no collective on the search path",
+                                noise=("none" if not sb.noise else "Gumbel(0,1) on the root logits (host draw, uploaded per move)"
+                                       if sb.gumbel else "Dirichlet(alpha=%g, eps=0.25) at every expansion, device Philox "
+                                       "streams keyed by global game id (Self_Play.py:38-46)" % cfg["alpha"])),
                     positions_per_s=value / cfg["limit"],
                     nn_evals_per_s=evals_all / (ms_all * 1e-3), sims_per_eval=sims_all / max(1.0, evals_all),
                     net_tflops=evals_all * sb.flops_per_eval / (ms_all * 1e-3) / 1e12,
