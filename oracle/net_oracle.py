@@ -6,9 +6,15 @@ semantics (NHWC, "same" padding, biases everywhere, BatchNorm eps=1e-3 in infere
 Dense-after-Reshape flattening in H,W,C order, exact-erf gelu, softmax in float64 for
 Gomoku/Connect4 - MCTS.py:234 casts it back to float32).
 
-Parity status: UNPINNED at this boundary.  TensorFlow / tf2onnx / onnxruntime (pinned in
+Parity status: WIRING PINNED, ARITHMETIC UNPINNED.  TensorFlow / tf2onnx / onnxruntime (pinned in
 requirements-training-*.txt: 2.18.0 / 1.16.1 / 1.20.1) are not installed here and the reference
-holds no network golden vectors, so the CUDA network is judged against this
+holds no network golden vectors.  What is pinned: tests/golden/net_*.npz hold the
+outputs of the reference's own, unmodified `build_model` functions executed under
+oracle/keras_shim.py (a minimal stand-in for the Keras layers they call) on seeded weights and
+positions; tests/test_net_golden.py holds this restatement to them at fp32 round-off (2e-5), so
+the layer graph - skip connections, pre-activation order, flatten order, head activations and
+dtypes - is the reference's.  What is not: the layer arithmetic on both sides is PyTorch's, not
+TensorFlow's / onnxruntime's.  The CUDA network is judged against the fixtures and against this
 restatement with BASELINE.json's tolerance: policy logits atol 2e-2, value atol 1e-2.
 """
 import os
@@ -61,6 +67,14 @@ class NetOracle:
     def dense(self, x, name):
         return x @ _t(self.W[name + ".kernel"], self.dtype) + _t(self.W[name + ".bias"], self.dtype)
 
+    def se(self, h, n):
+        """Squeeze-Excitation on an NCHW tensor (Net/SE/SE_Block.py:15-23): mean over the cells -> Dense(C/ratio) -> relu
+        -> Dense(C) -> sigmoid -> scale"""
+        s = h.mean(dim=(2, 3))
+        s = F.relu(self.dense(s, n + ".se1"))
+        s = torch.sigmoid(self.dense(s, n + ".se2"))
+        return h * s[:, :, None, None]
+
     @torch.no_grad()
     def forward(self, states):
         spec = self.spec
@@ -79,11 +93,7 @@ class NetOracle:
                 h = self._q(F.relu(self.bn(h, n + ".bn2")))
                 h = self.conv(h, n + ".conv2")
                 if l["se"]:
-                    h = self._qr(h)
-                    s = h.mean(dim=(2, 3))
-                    s = F.relu(self.dense(s, n + ".se1"))
-                    s = torch.sigmoid(self.dense(s, n + ".se2"))
-                    h = h * s[:, :, None, None]
+                    h = self.se(self._qr(h), n)
                 x = self._qr(h + res)
             else:
                 h = x

@@ -1,0 +1,31 @@
+"""GPU suite: the CUDA policy/value network against tests/golden/net_*.npz - outputs of the reference's own
+`build_model` functions traced under oracle/keras_shim.py on the same seeded weights and positions.
+Tolerance = BASELINE.json north_star: policy logits atol 2e-2, value atol 1e-2."""
+import numpy as np
+import pytest
+
+from grok_alpha_zero_b200.net import Net
+from test_net_golden import FIXTURES, load_case
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 2e-2
+VALUE_ATOL = 1e-2
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=lambda p: p.split("net_")[-1][:-4])
+def test_cuda_net_matches_the_traced_reference_model(path):
+    z, meta, spec, W = load_case(path)
+    net = Net(spec, W, max_batch=8)
+    pol, val, lg = net.forward(z["states"], want_logits=True)
+    net.close()
+    err_l = np.abs(lg - z["logits"]).max()
+    err_v = np.abs(val.reshape(-1) - z["value"]).max()
+    err_p = np.abs(pol - z["policy"]).max()
+    print("%s: logits err %.4g (absmax %.3g) value err %.4g policy err %.3g" % (meta, err_l, np.abs(lg).max(), err_v, err_p))
+    assert np.isfinite(lg).all() and np.isfinite(val).all()
+    assert err_l <= LOGIT_ATOL, err_l
+    assert err_v <= VALUE_ATOL, err_v
+    if meta["head"] != "linear":    # probabilities: a logit error e moves a probability p by about e * p
+        assert err_p <= 2 * LOGIT_ATOL * float(z["policy"].max()), err_p
+        np.testing.assert_allclose(pol.sum(-1), 1.0, atol=1e-5)
