@@ -25,7 +25,7 @@ def load_case(path):
     z = np.load(path)
     meta = ast.literal_eval(str(z["meta"]))
     spec = netspec.build_spec(meta["game"], meta["head"], **meta["over"])
-    W = netspec.init_weights(spec, seed=meta["seed_w"])
+    W = netspec.init_weights(spec, seed=meta["seed_w"], residual_gain=meta["residual_gain"])
     return z, meta, spec, W
 
 
