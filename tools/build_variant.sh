@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tests/_build_variant.sh <out.so> [extra nvcc flags...]   -- builds gaz_net.cu of the working tree with extra flags into tests/_emul/<out.so>
+# usage: tools/build_variant.sh <out.so> [extra nvcc flags...]   -- builds gaz_net.cu of the working tree with extra flags into tests/_emul/<out.so>
 set -e
 out=$1; shift
 d=$(mktemp -d)

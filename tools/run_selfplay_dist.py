@@ -1,5 +1,5 @@
 """Manual multi-GPU check (not collected by pytest):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_selfplay_dist.py OUT_DIR
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/run_selfplay_dist.py OUT_DIR
 plays a small Connect4 generation with the CUDA network on every rank and gathers the trajectories to rank 0 over NCCL."""
 import os
 import sys

@@ -1,5 +1,5 @@
 """Small end-to-end run for compute-sanitizer (memcheck): both networks, both search modes, closed loop.
-    compute-sanitizer --tool memcheck python tests/sanitize_small.py
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py
 Not a pytest file: the sanitizer slows kernels by 10-100x, so the sizes are tiny."""
 import os
 import sys
