@@ -360,6 +360,47 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games):
+    """--moves M: the timed region is M whole moves of every game (the first move is warm-up)."""
+    import torch
+    import torch.distributed as dist
+    timed_moves(1)
+    sims0, evals0, l0, m0 = sb.sims_done, sb.evals_total(), sb.launches, sb.moves
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms, rounds = timed_moves(args.moves)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    status = sb.eng.status()
+    if status != 0:
+        raise SystemExit("engine status %d (1 node overflow, 2 slot overflow, 4 LUT miss, 8 bad state)" % status)
+    tot = torch.tensor([float(sb.sims_done - sims0), float(sb.evals_total() - evals0), float(sb.moves - m0),
+                        float(sb.alive.sum())], dtype=torch.float64, device="cuda")
+    mst = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        sims, evals, moves, alive = (float(x) for x in tot.tolist())
+        t = float(mst.item()) * 1e-3
+        print(json.dumps(dict(
+            metric="MCTS simulations/sec", value=sims / t, unit="sims/s", n_gpus=world, steps=rounds, warmup=cfg["limit"],
+            ms_per_step=t * 1e3 / rounds, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=dict(workload=cfg["label"], games_per_gpu=n_games, trees_per_game=sb.tpg,
+                        step="one search round; timed region = %d whole moves of every game after one warm-up move "
+                             "(search, move choice at tau=0, do_action/check_win, prune_tree of both trees, next run)" % args.moves,
+                        noise="on" if sb.noise else "off"),
+            positions_per_s=moves / t, moves_timed=int(moves), games_still_running=int(alive),
+            nn_evals_per_s=evals / t, sims_per_eval=sims / max(1.0, evals), gpu_launches=int(sb.launches - l0),
+            clocks=clocks, hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()))), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,6 +412,9 @@ def main():
     ap.add_argument("--presearch", type=int, default=-1,
                     help="untimed rounds before warm-up so trees are mid-search (default: past the forced root expansion)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--moves", type=int, default=0,
+                    help="time M WHOLE moves per game from the start position (search, move choice, do_action, prune_tree / "
+                         "re-rooting of both trees) instead of K rounds: positions/s measured directly")
     ap.add_argument("--no-noise", action="store_true", help="searches without Dirichlet / Gumbel exploration noise")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -394,7 +438,7 @@ def main():
 
     sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise)
     sb.start()
-    presearch = args.presearch
+    presearch = 0 if args.moves > 0 else args.presearch
     if presearch < 0:
         presearch = {"gomoku": 232, "connect4": 16, "tictactoe": 12}[cfg["game"]] if cfg["mode"] == "puct" else 20
     done = 0
@@ -423,6 +467,25 @@ def main():
             if sb.run_finished():  # reads a counter back: synchronises
                 sb.advance_move()
         return sb.eng.timer_end()
+
+    def timed_moves(m):
+        """m whole moves per game; returns (ms, rounds run)"""
+        sb.eng.timer_begin()
+        rounds = 0
+        for _ in range(m):
+            left = cfg["limit"] if cfg["mode"] == "puct" else cfg["limit"] + 17   # Gumbel: + the uncounted root expansions
+            while True:
+                n = min(64, max(left, 4))
+                sb.rounds(n, sync=False)
+                rounds += n
+                left -= n
+                if left <= 0 and sb.run_finished():
+                    break
+            sb.advance_move()
+        return sb.eng.timer_end(), rounds
+
+    if args.moves > 0:
+        return run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games)
 
     # ---- warm-up + timed region -------------------------------------------------------------------
     timed_rounds(args.warmup)

@@ -1,7 +1,7 @@
-# scratch driver for one gpurun call (A/B of bench variants on one box)
-for c in gomoku connect4 gumbel tictactoe; do timeout 500 python bench.py --config $c --no-cpu-baseline > gpurun_out/bench_${c}_noise.json 2> gpurun_out/bench_${c}_noise.err; echo rc=$?; done
-timeout 500 python bench.py --config gomoku --no-noise --no-cpu-baseline > gpurun_out/bench_gomoku_nonoise.json 2> gpurun_out/bench_gomoku_nonoise.err; echo rc=$?
-for f in gomoku_noise gomoku_nonoise connect4_noise gumbel_noise tictactoe_noise; do python -c "
-import json; d=json.loads(open('gpurun_out/bench_$f.json').read().strip().splitlines()[-1]); r=d['roofline']; print('$f', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), r['frac'], d['clocks']['sm_mhz'], d['sims_per_eval'], d['gpu_launches'])"; done
-tail -3 gpurun_out/bench_*_noise.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 90 --csv --log-file gpurun_out/launches_noise.csv python bench.py --steps 3 --warmup 3 --presearch 8 --no-cpu-baseline > gpurun_out/ncu_noise.log 2>&1; echo ncu rc=$?
+# scratch driver for one gpurun call: whole-move timing (positions/s measured directly)
+timeout 300 python bench.py --config tictactoe --moves 4 > gpurun_out/moves_tictactoe.json 2> gpurun_out/moves_tictactoe.err; echo rc=$?
+timeout 400 python bench.py --config connect4 --moves 6 > gpurun_out/moves_connect4.json 2> gpurun_out/moves_connect4.err; echo rc=$?
+timeout 400 python bench.py --config gumbel --moves 6 > gpurun_out/moves_gumbel.json 2> gpurun_out/moves_gumbel.err; echo rc=$?
+timeout 600 python bench.py --config gomoku --moves 2 > gpurun_out/moves_gomoku.json 2> gpurun_out/moves_gomoku.err; echo rc=$?
+for f in tictactoe connect4 gumbel gomoku; do tail -c 400 gpurun_out/moves_$f.err; python -c "
+import json; d=json.loads(open('gpurun_out/moves_$f.json').read().strip().splitlines()[-1]); print('$f', round(d['value']), round(d['ms_per_step'],3), d['steps'], round(d['positions_per_s'],1), d['moves_timed'], d['games_still_running'], round(d['sims_per_eval'],3), d['clocks']['sm_mhz'])"; done
