@@ -52,9 +52,24 @@ def test_static_functions_match_reference_numba(ref, name):
         assert np.array_equal(np.asarray(b1), np.asarray(b2)) and np.array_equal(np.asarray(q1), np.asarray(q2))
 
 
+def _run_tester(cls, seed):
+    import random
+    from Game_Tester import Game_Tester   # the reference's only executable conformance check (Game_Tester.py:9-576)
+    np.random.seed(seed)
+    random.seed(seed)
+    return Game_Tester(cls).test()
+
+
 @pytest.mark.parametrize("name", ["tictactoe", "connect4", "gomoku"])
 def test_reference_game_tester_accepts_our_game_classes(ref, name, capsys):
-    from Game_Tester import Game_Tester   # the reference's only executable conformance check (Game_Tester.py:9-576)
-    ok = Game_Tester(OURS[name]).test()
+    """The tester plays random games (np.random), so it is seeded.  Its last check drives the reference's own MCTS_Gumbel,
+    whose `run` dereferences `root.child_logit_priors` on a root that has none (MCTS_Gumbel.py:590, AttributeError) in
+    about 5 % of random Connect4 play-outs - with the reference's own Connect4 class and the same seed just as with ours
+    (3 of 60 seeds each, measured).  Such a run is accepted only if the reference's class fails the same way."""
+    ok = _run_tester(OURS[name], 0)
     out = capsys.readouterr().out
+    if ok is False and "MCTS gumbel doesn't work" in out:
+        assert _run_tester(ref.games[name], 0) is False, "the reference tester fails on our class only:\n" + out[-2000:]
+        capsys.readouterr()
+        return
     assert ok is not False, out[-2000:]
