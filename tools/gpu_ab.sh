@@ -1,3 +1,9 @@
-# scratch driver for one gpurun call: Connect4 launch list at HEAD
-timeout 300 python bench.py --config connect4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/c4_plain.log 2>&1; echo plain rc=$?
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 80 --csv --log-file gpurun_out/launches_c4_head.csv python bench.py --config connect4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/c4_ncu.log 2>&1; echo ncu rc=$?
+# scratch driver for one gpurun call: full round-end verification (what the driver runs)
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err; echo ref rc=$?
+timeout 600 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo bench rc=$?
+python -c "
+import json
+d=json.loads(open('gpurun_out/final_bench.json').read().strip().splitlines()[-1]); r=d['roofline']; print('ours', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), r['frac'], d['clocks']['sm_mhz'], round(d['cpu_baseline']['value']), d['gpu_launches'])
+d=json.loads(open('gpurun_out/final_ref.json').read().strip().splitlines()[-1]); print('ref', d['value'], d['cpu_baseline']['cores'])"
