@@ -121,9 +121,9 @@ def tree_caps(cfg):
         if cfg["mode"] == "gumbel":
             return 192, 192 * 225
         return 1664, 340000
-    if cfg["game"] == "connect4":
-        return 4096, 4096 * 7
-    return 1024, 1024 * 9
+    if cfg["game"] == "connect4":   # small nodes (< 100 B): sized for the tail, as Self_Play.BatchedSelfPlay does
+        return 8 * cfg["limit"] + 92, (8 * cfg["limit"] + 92) * 7
+    return 8 * cfg["limit"] + 100, (8 * cfg["limit"] + 100) * 9
 
 
 class SelfPlayBench:

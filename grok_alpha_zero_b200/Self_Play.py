@@ -135,7 +135,11 @@ class BatchedSelfPlay:
         stablemax = bool(build_config.get("use_stablemax"))
         if node_cap is None:
             L = 7 if self.name == "connect4" else self.P
-            node_cap = int(self.limit * (1.4 if self.name == "gomoku" else 3.5)) + 4 * L + 64
+            # Gomoku: the oracle census + 40 %; a node costs 1.3 KB there, so the worst case is not affordable.
+            # Connect4 / TicTacToe: a node costs < 100 B, so size for the tail - an expansion whose position has terminal
+            # replies creates a terminal parent AND its k terminal children (MCTS.py:367-428), and the kept sub-tree of
+            # the previous move comes on top (a 4096-game Connect4 generation overflowed 3.5 x limit)
+            node_cap = (int(self.limit * 1.4) if self.name == "gomoku" else 8 * self.limit) + 4 * L + 64
             if self.gumbel:
                 node_cap = int(self.limit * 1.5) + 2 * L + 64
             slot_cap = node_cap * min(L, 225) + 256 if slot_cap is None else slot_cap
@@ -294,11 +298,11 @@ class BatchedSelfPlay:
     def play(self, progress=None):
         self._seat(list(range(self.n_slots)))
         while self.step():
+            st = self.eng.status()      # checked after every move: a tree pool that overflowed stops growing, so the
+            if st != 0:                 # searches would silently differ from the reference's - fail before more is played
+                raise RuntimeError("engine status %d (1 node overflow, 2 slot overflow): raise node_cap / slot_cap" % st)
             if progress is not None:
                 progress(self)
-        st = self.eng.status()
-        if st != 0:
-            raise RuntimeError("engine status %d (1 node overflow, 2 slot overflow): raise node_cap / slot_cap" % st)
         return self.finished
 
     def close(self):
@@ -373,7 +377,7 @@ def net_spec_from_configs(game_name, build_config, train_config):
     over = {}
     if "num_resnet_layers" in build_config:
         over["num_blocks"] = int(build_config["num_resnet_layers"])
-    if "num_filters" in build_config:
+    if "num_filters" in build_config and game_name != "tictactoe":   # TicTacToe/Build_Model.py:22 hard-codes ResNet_Block(64)
         over["filters"] = int(build_config["num_filters"])
     if "use_se" in build_config:
         over["use_se"] = bool(build_config["use_se"])

@@ -215,6 +215,24 @@ def build_ops(spec, W):
     return B
 
 
+def check_weights(spec, W):
+    """Every array the network reads must be present with the shape `spec` implies: a dictionary built for another
+    build_config would otherwise be re-laid-out into operands of the wrong size."""
+    from .keras_bridge import expected_shapes
+    want = expected_shapes(spec)
+    for l in spec["layers"]:
+        if l["op"] == "block" and l["se"]:
+            r = l["cout"] // 2
+            want.update({l["name"] + ".se1.kernel": (l["cout"], r), l["name"] + ".se1.bias": (r,),
+                         l["name"] + ".se2.kernel": (r, l["cout"]), l["name"] + ".se2.bias": (l["cout"],)})
+    for k, shp in want.items():
+        if k not in W:
+            raise ValueError("network weights: %r is missing (spec %s %s)" % (k, spec["game"], spec["cfg"]))
+        if tuple(np.shape(W[k])) != tuple(shp):
+            raise ValueError("network weights: %r has shape %s, the spec (%s %s) expects %s"
+                             % (k, tuple(np.shape(W[k])), spec["game"], spec["cfg"], tuple(shp)))
+
+
 class Net:
     """CUDA policy/value network.  `forward` is the host-buffer path (parity tests, mailbox server);
     `attach(engine)` wires it to a search engine so leaves never leave HBM."""
@@ -224,6 +242,7 @@ class Net:
         self.spec = spec
         self.H, self.W, self.Cin, self.P = spec["H"], spec["W"], spec["Cin"], spec["P"]
         self.max_batch = max_batch
+        check_weights(spec, weights)
         b = build_ops(spec, weights)
         self.n_ops = len(b.ops)
         self.n_conv_tc = sum(1 for o in b.ops if o["type"] == OP_CONV_TC)

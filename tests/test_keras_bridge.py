@@ -59,3 +59,30 @@ def test_failures_are_loud():
         kb.import_keras_weights(spec, wrong)
     with pytest.raises(ValueError):
         kb.keras_layer_names(netspec.build_spec("gomoku", "softmax"))   # use_se=True: no Keras counterpart
+
+
+def test_net_rejects_weights_of_another_build_config():
+    """Net() validates every array before anything is laid out for the device (no GPU needed to fail)."""
+    from grok_alpha_zero_b200.net import check_weights
+    spec64 = netspec.build_spec("tictactoe", "softmax")
+    spec128 = netspec.build_spec("tictactoe", "softmax", filters=128)
+    W = netspec.init_weights(spec64, seed=1)
+    check_weights(spec64, W)
+    with pytest.raises(ValueError, match="expects"):
+        check_weights(spec128, W)
+    se = netspec.build_spec("gomoku", "softmax", num_blocks=1, use_se=True)
+    Wse = netspec.init_weights(se, seed=1)
+    check_weights(se, Wse)
+    del Wse["block0.se2.bias"]
+    with pytest.raises(ValueError, match="missing"):
+        check_weights(se, Wse)
+
+
+def test_spec_from_reference_configs():
+    """build_config -> netspec as the reference's builders read it: TicTacToe hard-codes ResNet_Block(64)
+    (TicTacToe/Build_Model.py:22) and ignores num_filters; Connect4 / Gomoku use it."""
+    from grok_alpha_zero_b200.Self_Play import net_spec_from_configs
+    bc = {"num_resnet_layers": 2, "num_filters": 128, "use_stablemax": False}
+    assert net_spec_from_configs("tictactoe", bc, {"use_gumbel": False})["cfg"]["filters"] == 64
+    assert net_spec_from_configs("connect4", dict(bc, num_filters=96), {"use_gumbel": False})["cfg"]["filters"] == 96
+    assert net_spec_from_configs("gomoku", bc, {"use_gumbel": True})["policy_head"] == "linear"

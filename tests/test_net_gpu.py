@@ -20,6 +20,7 @@ VALUE_ATOL = 1e-2
 
 CASES = [
     ("tictactoe", "softmax", {}, 37),
+    ("tictactoe", "softmax", dict(filters=128), 300),      # 3x3 boards on the tensor-core path: 16 boards per 256-row tile
     ("connect4", "softmax", {}, 70),
     ("connect4", "stablemax", dict(num_blocks=2), 5),
     ("gomoku", "softmax", dict(num_blocks=1, use_se=False), 9),

@@ -1,9 +1,4 @@
-# scratch driver for one gpurun call: full round-end verification (what the driver runs)
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 300 python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err; echo ref rc=$?
-timeout 600 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo bench rc=$?
-python -c "
-import json
-d=json.loads(open('gpurun_out/final_bench.json').read().strip().splitlines()[-1]); r=d['roofline']; print('ours', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), r['frac'], d['clocks']['sm_mhz'], round(d['cpu_baseline']['value']), d['gpu_launches'])
-d=json.loads(open('gpurun_out/final_ref.json').read().strip().splitlines()[-1]); print('ref', d['value'], d['cpu_baseline']['cores'])"
+# scratch driver for one gpurun call: tensor-core TicTacToe net + full generations through run_self_play
+timeout 300 python -m pytest tests/test_net_gpu.py -q -s -k "tictactoe" 2>&1 | grep -E "err|passed|failed|Error|illegal" | cut -c1-250 | tail
+timeout 120 python tools/selfplay_generation.py tictactoe 256 /tmp/g0 > gpurun_out/gen_ttt.json 2> gpurun_out/gen_ttt.err; echo rc=$?; tail -c 700 gpurun_out/gen_ttt.json; tail -3 gpurun_out/gen_ttt.err
+timeout 600 python tools/selfplay_generation.py connect4 4096 /tmp/g1 > gpurun_out/gen_c4.json 2> gpurun_out/gen_c4.err; echo rc=$?; tail -c 900 gpurun_out/gen_c4.json; tail -3 gpurun_out/gen_c4.err
