@@ -37,8 +37,8 @@ winners = np.array([g["winner"] for g in merged])
 files = {f: os.path.getsize(os.path.join(out, f)) for f in os.listdir(out)}
 print(json.dumps(dict(
     what="run_self_play: one generation, every game to its end, replay file written", game=game, games=len(merged),
-    sims_per_move=sims, iterations_per_move=int(sims * 1.5), net="%d x ResNet128 bf16" % blocks, positions=positions,
-    seconds=round(dt, 2), positions_per_s=round(positions / dt, 1), sims_per_s=round(positions * int(sims * 1.5) / dt, 1),
+    sims_per_move=sims, iterations_per_move=int(sims * 1.5), net="%d x ResNet%d bf16" % (blocks, spec["cfg"]["filters"]), positions=positions,
+    seconds=round(dt, 2), positions_per_s=round(positions / dt, 1), nominal_sims_per_s=round(positions * int(sims * 1.5) / dt, 1),
     mean_game_length=round(positions / max(1, len(merged)), 2),
     winners={"-1": int((winners == -1).sum()), "0": int((winners == 0).sum()), "1": int((winners == 1).sum())},
     replay_files=files)), flush=True)
