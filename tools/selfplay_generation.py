@@ -22,12 +22,20 @@ shutil.rmtree(out, ignore_errors=True)
 os.makedirs(out)
 if game == "connect4":    # Connect4/Connect4.py:4-60 with BASELINE's depth and simulation count
     cls, sims, blocks, max_actions, alpha, cpuct = games.Connect4, 800, 5, 42, 0.5, 2.5
+elif game in ("gomoku", "gumbel"):   # Gomoku/Gomoku.py:5-60 with BASELINE's depth; "gumbel" = configs[3] (m=16, n=64, StableMax)
+    cls, sims, blocks, max_actions, alpha, cpuct = games.Gomoku, (800 if game == "gomoku" else 64), 10, 150, 0.05, 4.5
 else:
     cls, sims, blocks, max_actions, alpha, cpuct = games.TicTacToe, 200, 2, 9, 1.0, 1.25
 bc = {"num_resnet_layers": blocks, "num_filters": 128, "use_stablemax": False}
 tc = dict(MCTS_iteration_limit=sims, use_gumbel=False, c_puct_init=cpuct, dirichlet_alpha=alpha, max_actions=max_actions,
           num_explore_actions_first=2, num_explore_actions_second=1, games_per_generation=n_games, games_per_gpu=n_games)
-spec = net_spec_from_configs(game, bc, tc)
+gname = "gomoku" if game == "gumbel" else game
+if gname == "gomoku":
+    bc["use_se"] = True
+if game == "gumbel":
+    bc["use_stablemax"] = True
+    tc.update(use_gumbel=True, m=16, c_visit=50.0, c_scale=1.0)
+spec = net_spec_from_configs(gname, bc, tc)
 W = netspec.init_weights(spec, seed=0)
 t0 = time.time()
 merged = run_self_play(cls, (bc, tc, {}), out, weights=W, seed=3)
@@ -37,8 +45,8 @@ winners = np.array([g["winner"] for g in merged])
 files = {f: os.path.getsize(os.path.join(out, f)) for f in os.listdir(out)}
 print(json.dumps(dict(
     what="run_self_play: one generation, every game to its end, replay file written", game=game, games=len(merged),
-    sims_per_move=sims, iterations_per_move=int(sims * 1.5), net="%d x ResNet%d bf16" % (blocks, spec["cfg"]["filters"]), positions=positions,
-    seconds=round(dt, 2), positions_per_s=round(positions / dt, 1), nominal_sims_per_s=round(positions * int(sims * 1.5) / dt, 1),
+    sims_per_move=sims, iterations_per_move=int(sims * 1.5) if game != "gumbel" else sims, net="%d x ResNet%d bf16" % (blocks, spec["cfg"]["filters"]), positions=positions,
+    seconds=round(dt, 2), positions_per_s=round(positions / dt, 1), nominal_sims_per_s=round(positions * (int(sims * 1.5) if game != "gumbel" else sims) / dt, 1),
     mean_game_length=round(positions / max(1, len(merged)), 2),
     winners={"-1": int((winners == -1).sum()), "0": int((winners == 0).sum()), "1": int((winners == 1).sum())},
     replay_files=files)), flush=True)
