@@ -115,15 +115,18 @@ class ClockSampler:
 
 
 def tree_caps(cfg):
-    """(node_cap, slot_cap) per tree from the oracle tree census: Gomoku <= ~1350 nodes and
-    <= ~290k child slots per tree at 1200 iterations/move with sub-tree reuse."""
+    """(node_cap, slot_cap) per tree: the rule of Self_Play.BatchedSelfPlay, i.e. pools sized for the tail of WHOLE games
+    (measured peaks at 1200 iterations/move: 2806 nodes / 374 k child slots in 12 emulated Gomoku games), not for the
+    opening the timed region happens to lie in - the HBM footprint in `hbm_bytes` is what a real generation needs."""
+    lim = cfg["limit"]
     if cfg["game"] == "gomoku":
         if cfg["mode"] == "gumbel":
-            return 192, 192 * 225
-        return 1664, 340000
-    if cfg["game"] == "connect4":   # small nodes (< 100 B): sized for the tail, as Self_Play.BatchedSelfPlay does
-        return 8 * cfg["limit"] + 92, (8 * cfg["limit"] + 92) * 7
-    return 8 * cfg["limit"] + 100, (8 * cfg["limit"] + 100) * 9
+            n = int(lim * 1.5) + 2 * 225 + 64
+            return n, n * 225 + 256
+        return 4 * lim + 4 * 225 + 64, 2 * lim * 225 + 256
+    L = 7 if cfg["game"] == "connect4" else 9
+    n = 8 * lim + 4 * L + 64
+    return n, n * L + 256
 
 
 class SelfPlayBench:

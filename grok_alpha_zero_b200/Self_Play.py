@@ -135,11 +135,15 @@ class BatchedSelfPlay:
         stablemax = bool(build_config.get("use_stablemax"))
         if node_cap is None:
             L = 7 if self.name == "connect4" else self.P
-            # Gomoku: the oracle census + 40 %; a node costs 1.3 KB there, so the worst case is not affordable.
-            # Connect4 / TicTacToe: a node costs < 100 B, so size for the tail - an expansion whose position has terminal
-            # replies creates a terminal parent AND its k terminal children (MCTS.py:367-428), and the kept sub-tree of
-            # the previous move comes on top (a 4096-game Connect4 generation overflowed 3.5 x limit)
-            node_cap = (int(self.limit * 1.4) if self.name == "gomoku" else 8 * self.limit) + 4 * L + 64
+            # Pools are sized for the tail of WHOLE games, not for the opening: an expansion whose position has terminal
+            # replies creates a terminal parent and its k terminal children (MCTS.py:367-428), and the sub-tree kept
+            # from the previous move comes on top of the limit new nodes.  Measured peaks per tree (emulated engine, 12
+            # full Gomoku games at 1200 iterations: 2806 nodes / 374 k child slots; a 4096-game Connect4 generation
+            # overflowed 3.5 x limit nodes).  Gomoku: 4 x limit nodes (~100 B each) and 2 x limit x L child slots (5 B
+            # each; only evaluated nodes own L slots) = 3.3 MB per tree; Connect4 / TicTacToe nodes are < 100 B all in.
+            node_cap = (4 if self.name == "gomoku" else 8) * self.limit + 4 * L + 64
+            if slot_cap is None and self.name == "gomoku" and not self.gumbel:
+                slot_cap = 2 * self.limit * L + 256
             if self.gumbel:
                 node_cap = int(self.limit * 1.5) + 2 * L + 64
             slot_cap = node_cap * min(L, 225) + 256 if slot_cap is None else slot_cap
