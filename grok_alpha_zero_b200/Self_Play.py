@@ -165,6 +165,7 @@ class BatchedSelfPlay:
         self.rngs = [None] * self.n_slots
         self.traj = [None] * self.n_slots
         self.finished = []
+        self.pool_rebuilds = 0    # trees given a fresh root because their pool could not hold another move (see _relieve_full_pools)
         self.sims = 0
         self.moves = 0
 
@@ -209,6 +210,25 @@ class BatchedSelfPlay:
 
     def live(self):
         return self.slot_game >= 0
+
+    def _relieve_full_pools(self, cont, next_mover):
+        """The reference's trees are unbounded Python objects; ours live in fixed per-tree pools.  A kept sub-tree grows
+        with the concentration of the search (steady state ~ limit / (1 - share of the played line)), so no static size is
+        safe for every network.  After re-rooting, a tree that is about to search and could not hold one more move's worth
+        (2 nodes per iteration, L child slots per evaluated node) gets a fresh root instead - what `prune_tree` does for an
+        unseen action (MCTS.py:661-671): one evaluation, no reuse for that move.  Counted in `pool_rebuilds`."""
+        e = self.eng
+        sizes = e.tree_sizes().reshape(self.n_slots, self.tpg, 2)
+        nxt = (np.asarray(next_mover) > 0).astype(np.int64)                 # the tree of the side to move runs next
+        mine = sizes[np.arange(self.n_slots), nxt]
+        L = 7 if self.name == "connect4" else self.P
+        full = cont & ((mine[:, 0] + 2 * self.limit > e.node_cap) | (mine[:, 1] + self.limit * L > e.slot_cap))
+        if not full.any():
+            return
+        mask = np.zeros((self.n_slots, self.tpg), np.uint8)
+        mask[np.nonzero(full)[0], nxt[full]] = 1
+        self.pool_rebuilds += int(full.sum())
+        self._serve(e.new_roots(mask.reshape(-1)))
 
     # ---- one move of every live game -------------------------------------------------------------------
     def step(self):
@@ -288,6 +308,8 @@ class BatchedSelfPlay:
         pa = np.repeat(np.where(cont, actions, -1).astype(np.int16), self.tpg)
         create_new = True if self.gumbel else bool(self.tc.get("create_new_root", False))
         self._serve(e.prune(pa, create_new_root=create_new))
+        if not create_new:
+            self._relieve_full_pools(cont, -mover)
         for s, w in done:
             t = self.traj[s]
             self.finished.append(dict(game_id=int(self.slot_game[s]), winner=w, length=len(t["z"]),
@@ -431,6 +453,9 @@ def run_self_play(game_class, configs, folder_path, per_process_wait_time=1e-3, 
     sp = BatchedSelfPlay(game_class, build_config, train_config, ids, int(train_config.get("games_per_gpu", 4096)),
                          device=device, evaluator=evaluator, spec=spec, weights=w, seed=seed, lib=lib)
     finished = sp.play()
+    if sp.pool_rebuilds:
+        print("run_self_play: %d tree(s) restarted from a fresh root because their pool could not hold another move "
+              "(raise node_cap / slot_cap to keep the sub-tree reuse)" % sp.pool_rebuilds)
     sp.close()
     dev = None
     if world > 1:

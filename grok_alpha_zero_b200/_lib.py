@@ -53,6 +53,7 @@ SYMBOLS = {
     "gaz_timer_end": (C.c_int, [_P, _P]),
     "gaz_sync": (C.c_int, [_P]),
     "gaz_status": (C.c_int, [_P]),
+    "gaz_tree_sizes": (C.c_int, [_P, _P]),
     "gaz_bytes_allocated": (C.c_int64, [_P]),
 }
 

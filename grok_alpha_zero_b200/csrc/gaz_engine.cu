@@ -873,6 +873,15 @@ int gaz_status(gaz_engine *e) {
     return s;
 }
 
+int gaz_tree_sizes(gaz_engine *e, int32_t *out) {
+    if (!e || !out) return fail("null argument");
+    const View &v = e->v;
+    std::vector<TreeState> ts((size_t)v.n_trees);
+    if (d2h(ts.data(), v.trees, ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
+    for (int t = 0; t < v.n_trees; t++) { out[2 * t] = ts[t].n_nodes; out[2 * t + 1] = ts[t].n_slots; }
+    return 0;
+}
+
 int64_t gaz_bytes_allocated(gaz_engine *e) { return e ? e->bytes : 0; }
 
 } // extern "C"

@@ -52,6 +52,7 @@ class Engine:
         cfg = _lib.GazConfig(GAMES[game], 1 if mode == "gumbel" else 0, n_games, trees_per_game, node_cap, slot_cap,
                              device, lut_n, c_puct_init, c_puct_base, m, int(activation_fn == "softmax"),
                              c_visit, c_scale)
+        self.node_cap, self.slot_cap = int(node_cap), int(slot_cap)
         h = C.c_void_p()
         self._h = None
         self._ck(self.lib.gaz_create(C.byref(cfg), C.byref(h)))
@@ -227,6 +228,12 @@ class Engine:
 
     def status(self):
         return self._ck(self.lib.gaz_status(self._h))
+
+    def tree_sizes(self):
+        """(n_trees, 2) int32: nodes and child slots in use per tree (pools of node_cap / slot_cap)"""
+        out = np.zeros((self.n_trees, 2), dtype=np.int32)
+        self._ck(self.lib.gaz_tree_sizes(self._h, _p(out)))
+        return out
 
     def bytes_allocated(self):
         return int(self.lib.gaz_bytes_allocated(self._h))

@@ -136,6 +136,10 @@ int gaz_timer_begin(gaz_engine *e);
 int gaz_timer_end(gaz_engine *e, float *ms_out);
 int gaz_sync(gaz_engine *e);
 int gaz_status(gaz_engine *e); /* sticky error bits: 1 node overflow, 2 slot overflow, 4 LUT miss, 8 bad state */
+/* pool occupancy of every tree: out = n_trees x 2 int32 (nodes in use, child slots in use) of the per-tree pools
+ * gaz_config.node_cap / slot_cap.  The reference's trees are unbounded Python objects (MCTS.py:20-72); a host driver
+ * uses this after gaz_prune to give a tree that could not hold one more move's search a fresh root instead. */
+int gaz_tree_sizes(gaz_engine *e, int32_t *out);
 int64_t gaz_bytes_allocated(gaz_engine *e);
 
 #ifdef __cplusplus

@@ -32,8 +32,7 @@ def declared(header):
 @pytest.fixture(scope="module")
 def lib():
     import __graft_entry__ as ge
-    if not os.path.exists(ge.LIB):
-        ge.build()
+    ge.build()            # no-op when the library is newer than every source, rebuilds it otherwise
     return C.CDLL(ge.LIB)
 
 

@@ -87,3 +87,24 @@ def test_batched_self_play_with_cuda_net(tmp_path):
     assert w.games_done() == 12
     run_self_play(games.Connect4, (bc, tc, {}), out, weights=W, seed=9)     # resume rule: nothing left to play
     assert ReplayWriter(out).games_done() == 12
+
+
+def test_pool_relief_on_cuda_matches_the_emulated_engine():
+    """Small tree pools force fresh roots (BatchedSelfPlay._relieve_full_pools, gaz_tree_sizes): the CUDA engine and the
+    host emulation of the same warp code must play identical games, with the same number of rebuilds."""
+    import emul_lib
+    bc = {"num_resnet_layers": 1, "num_filters": 128, "use_stablemax": False}
+    tc = dict(MCTS_iteration_limit=40, use_gumbel=False, c_puct_init=2.5, dirichlet_alpha=0.5, max_actions=42,
+              num_explore_actions_first=1, num_explore_actions_second=1)
+    runs = []
+    for lib in (None, emul_lib.load()):
+        sp = BatchedSelfPlay(games.Connect4, bc, tc, list(range(6)), 6, evaluator="hash", lib=lib, seed=3,
+                             node_cap=150, slot_cap=150 * 7, use_noise=False)
+        fin = {g["game_id"]: g for g in sp.play()}
+        runs.append((fin, sp.pool_rebuilds))
+        sp.close()
+    (a, ra), (b, rb) = runs
+    assert ra == rb and ra > 0
+    for i in range(6):
+        assert a[i]["winner"] == b[i]["winner"] and np.array_equal(a[i]["states"], b[i]["states"])
+        assert np.array_equal(a[i]["policies"], b[i]["policies"])

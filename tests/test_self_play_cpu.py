@@ -171,3 +171,33 @@ def test_world_size_2_gloo_gather_matches_single_process(tmp_path, lib):
     assert set(a.data.keys()) == set(b.data.keys()) and int(a.data["game_stats"][2]) == 6
     for k in a.data:
         assert np.array_equal(a.data[k], b.data[k]), k
+
+
+def test_tree_sizes_and_pool_relief(lib):
+    """gaz_tree_sizes reports the pool occupancy root_stats reports per tree; with pools too small for the sub-tree
+    reuse the driver gives the tree of the side to move a fresh root (MCTS.py:661-671 behaviour for an unseen action)
+    instead of overflowing: the generation finishes with a clean status word."""
+    from grok_alpha_zero_b200.Self_Play import BatchedSelfPlay
+    bc = {"num_resnet_layers": 1, "num_filters": 128, "use_stablemax": False}
+    tc = dict(MCTS_iteration_limit=40, use_gumbel=False, c_puct_init=2.5, dirichlet_alpha=0.5, max_actions=42,
+              num_explore_actions_first=1, num_explore_actions_second=1)
+    n = 5
+    # limit = 60 iterations: one move needs 120 nodes of head-room, so a 150-node pool forces a rebuild as soon as more
+    # than 30 nodes are kept
+    sp = BatchedSelfPlay(games.Connect4, bc, tc, list(range(n)), n, evaluator="hash", lib=lib, seed=3,
+                         node_cap=150, slot_cap=150 * 7)
+    sp._seat(list(range(n)))
+    sz = sp.eng.tree_sizes()
+    assert sz.shape == (2 * n, 2)
+    for t in range(2 * n):
+        st = sp.eng.root_stats(t)
+        assert (int(st["n_nodes"]), int(st["n_slots"])) == tuple(int(x) for x in sz[t])
+    while sp.step():
+        assert sp.eng.status() == 0
+        assert (sp.eng.tree_sizes()[:, 0] <= 150).all()
+    assert len(sp.finished) == n and sp.pool_rebuilds > 0
+    sp.close()
+    # roomy pools: same games, no rebuilds
+    sp = BatchedSelfPlay(games.Connect4, bc, tc, list(range(n)), n, evaluator="hash", lib=lib, seed=3)
+    assert len(sp.play()) == n and sp.pool_rebuilds == 0
+    sp.close()
