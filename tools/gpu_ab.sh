@@ -1,2 +1,9 @@
-# scratch driver for one gpurun call (2 GPUs): Connect4 generation of 8192 games sharded over 2 ranks + NCCL trajectory gather
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/selfplay_generation.py connect4 8192 /tmp/g4 > gpurun_out/gen_c4_2gpu.json 2> gpurun_out/gen_c4_2gpu.err; echo rc=$?; tail -c 600 gpurun_out/gen_c4_2gpu.json; tail -4 gpurun_out/gen_c4_2gpu.err
+# scratch driver for one gpurun call: full round-end verification (what the driver runs)
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err; echo ref rc=$?
+timeout 600 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo bench rc=$?
+python -c "
+import json
+d=json.loads(open('gpurun_out/final_bench.json').read().strip().splitlines()[-1]); r=d['roofline']; print('ours', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), r['frac'], d['clocks']['sm_mhz'], round(d['cpu_baseline']['value']), d['gpu_launches'], d['hbm_bytes'])
+d=json.loads(open('gpurun_out/final_ref.json').read().strip().splitlines()[-1]); print('ref', d['value'], d['cpu_baseline']['cores'])"
