@@ -201,3 +201,18 @@ def test_tree_sizes_and_pool_relief(lib):
     sp = BatchedSelfPlay(games.Connect4, bc, tc, list(range(n)), n, evaluator="hash", lib=lib, seed=3)
     assert len(sp.play()) == n and sp.pool_rebuilds == 0
     sp.close()
+
+
+def test_bench_pools_follow_the_self_play_rule(lib):
+    """bench.py sizes its tree pools with the rule of BatchedSelfPlay, so `hbm_bytes` is what a real generation needs."""
+    import bench
+    from grok_alpha_zero_b200.Self_Play import BatchedSelfPlay
+    classes = {"gomoku": games.Gomoku, "connect4": games.Connect4, "tictactoe": games.TicTacToe}
+    for name, cfg in bench.CONFIGS.items():
+        gumbel = cfg["mode"] == "gumbel"
+        tc = dict(MCTS_iteration_limit=cfg["sims"], use_gumbel=gumbel, c_puct_init=cfg["c_puct_init"], dirichlet_alpha=0.3,
+                  max_actions=10, m=16, c_visit=50.0, c_scale=1.0)
+        sp = BatchedSelfPlay(classes[cfg["game"]], {"use_stablemax": gumbel}, tc, [0], 1, evaluator="hash", lib=lib)
+        assert sp.limit == cfg["limit"]
+        assert (sp.eng.node_cap, sp.eng.slot_cap) == bench.tree_caps(cfg), name
+        sp.close()
