@@ -411,6 +411,9 @@ struct HeadConvArgs {
     __nv_bfloat16 *out_act; // optional: relu(act_scale[f] * out + act_shift[f]) as bf16, same flat order (operand of a
     const float *act_scale, *act_shift; // tensor-core dense layer)
     int act_ld;         // row pitch of out_act in elements (features padded to a multiple of 8 for the TMA pitch rule)
+    // second head of a dual launch (headconv_f32_dual_kernel): same input and shape, own filters / bias / output
+    const float *w2, *bias2;
+    float *out2;
 };
 
 // small convolutions of the heads (C_out <= 16): thread per (leaf, cell), weights in shared memory
@@ -549,6 +552,105 @@ __global__ void __launch_bounds__(128) headconv_f32_kernel(HeadConvArgs p) {
 #pragma unroll
             for (int q = 0; q < COUT / 4; q++)
                 *reinterpret_cast<float4 *>(op + 4 * q) = make_float4(acc[e][4 * q], acc[e][4 * q + 1], acc[e][4 * q + 2], acc[e][4 * q + 3]);
+        }
+    }
+}
+
+// Two head convolutions of the same shape on the same input in ONE pass (Connect4: the policy and the value head both
+// start with a 3x3 C128 -> C8 convolution of the trunk output, Connect4/Build_Model.py:27,48): the filters of both heads
+// sit side by side in shared memory ([tap][Cin][head 1 | head 2]), every 8-channel piece of the input is loaded once and
+// feeds 2 x COUT accumulators per cell.  Each output sees its terms in the order of headconv_f32_kernel, so the results
+// are bit-identical to two single launches; the launch is latency-bound (20 resident warps per SM), so halving the loads
+// per FMA is what pays.
+template <int COUT, int KS>
+__global__ void __launch_bounds__(128) headconv_f32_dual_kernel(HeadConvArgs p) {
+    extern __shared__ __align__(16) float s_w[];   // [tap][Cin][2 * COUT]
+    constexpr int kh = KS >> 1, C2 = 2 * COUT, Q = COUT / 4;
+    const int nrow = KS * KS * p.Cin;
+    for (int i = threadIdx.x; i < nrow * Q; i += blockDim.x) {
+        const int r = i / Q, q = i - r * Q;
+        reinterpret_cast<float4 *>(s_w)[r * 2 * Q + q] = reinterpret_cast<const float4 *>(p.w)[i];
+        reinterpret_cast<float4 *>(s_w)[r * 2 * Q + Q + q] = reinterpret_cast<const float4 *>(p.w2)[i];
+    }
+    __syncthreads();
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int ncell = p.H * p.W;
+    const long long total = (long long)cnt * ncell;
+    const int npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
+    const float *in = (const float *)p.in;
+    for (long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x; 2 * pr < total; pr += (long long)gridDim.x * blockDim.x) {
+        long long r0[2];
+        bool have[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const long long idx = 2 * pr + e;
+            have[e] = idx < total;
+            const long long id2 = have[e] ? idx : 2 * pr;
+            const int b = (int)(id2 / ncell), cell = (int)(id2 - (long long)b * ncell);
+            const int y = cell / p.W, x = cell - y * p.W;
+            r0[e] = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
+        }
+        uint32_t off[KS * KS][2];
+        float live[KS * KS][2];
+#pragma unroll
+        for (int t = 0; t < KS * KS; t++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const long long r = r0[e] + (t / KS - kh) * p.Wp + (t % KS - kh);
+                const bool ok = r >= 0 && r < p.in_rows;
+                const long long rr = ok ? r : r0[e];
+                off[t][e] = (uint32_t)((((rr >> 5) * cb_per_row) << 10) + ((rr & 31) << 3));
+                live[t][e] = ok ? 1.0f : 0.0f;
+            }
+        float acc[2][C2];
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int j = 0; j < COUT; j++) { acc[e][j] = p.bias[j]; acc[e][COUT + j] = p.bias2[j]; }
+#pragma unroll 1
+        for (int pc = 0; pc < npiece; pc++) {
+            const uint32_t po = ((uint32_t)(pc >> 2) << 10) + ((uint32_t)(pc & 3) << 8);
+#pragma unroll
+            for (int ky = 0; ky < KS; ky++) {
+                float a[KS][2][8];
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) gaz_conv::ldg256(in + off[ky * KS + kx][e] + po, a[kx][e]);
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                    const int t = ky * KS + kx;
+                    const float *wp = s_w + (size_t)(t * p.Cin + pc * 8) * C2;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float4 *w4 = reinterpret_cast<const float4 *>(wp + c * C2);
+                        const float a0 = a[kx][0][c] * live[t][0], a1 = a[kx][1][c] * live[t][1];
+#pragma unroll
+                        for (int q = 0; q < 2 * Q; q++) {
+                            const float4 w = w4[q];
+                            acc[0][4 * q] = fmaf(a0, w.x, acc[0][4 * q]);
+                            acc[0][4 * q + 1] = fmaf(a0, w.y, acc[0][4 * q + 1]);
+                            acc[0][4 * q + 2] = fmaf(a0, w.z, acc[0][4 * q + 2]);
+                            acc[0][4 * q + 3] = fmaf(a0, w.w, acc[0][4 * q + 3]);
+                            acc[1][4 * q] = fmaf(a1, w.x, acc[1][4 * q]);
+                            acc[1][4 * q + 1] = fmaf(a1, w.y, acc[1][4 * q + 1]);
+                            acc[1][4 * q + 2] = fmaf(a1, w.z, acc[1][4 * q + 2]);
+                            acc[1][4 * q + 3] = fmaf(a1, w.w, acc[1][4 * q + 3]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (!have[e]) continue;
+            float *o1 = p.out + (size_t)(2 * pr + e) * COUT, *o2 = p.out2 + (size_t)(2 * pr + e) * COUT;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                *reinterpret_cast<float4 *>(o1 + 4 * q) = make_float4(acc[e][4 * q], acc[e][4 * q + 1], acc[e][4 * q + 2], acc[e][4 * q + 3]);
+                *reinterpret_cast<float4 *>(o2 + 4 * q) = make_float4(acc[e][COUT + 4 * q], acc[e][COUT + 4 * q + 1], acc[e][COUT + 4 * q + 2], acc[e][COUT + 4 * q + 3]);
+            }
         }
     }
 }
@@ -944,6 +1046,8 @@ struct NetOp {
     int skip;             // SE op folded into the previous conv
     int block_fused;      // this conv1 runs the whole residual block (gaz_block.cuh) together with the next conv (+SE)
     int in_block;         // this conv2 is executed by the previous op's fused block kernel
+    int dual_partner;     // HEADCONV: index of a later head convolution of the same shape on the same input that this op's
+    int dual_skip;        // launch computes as well (headconv_f32_dual_kernel); dual_skip marks that later op
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
     float *d_par;         // device copy (v3 kernel)
     float *d_se_b1;       // v3 fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
@@ -1188,7 +1292,9 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             break;
         }
         case GAZ_OP_HEADCONV: {
+            if (op.dual_skip) break;
             HeadConvArgs a;
+            a.w2 = a.bias2 = nullptr; a.out2 = nullptr;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize;
             a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32; a.layout = n->conv_t;
             a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
@@ -1199,6 +1305,12 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 a.act_ld = (nx.d.cin + 7) & ~7;
             }
             size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
+            if (op.dual_partner >= 0) {
+                const NetOp &o2 = n->ops[(size_t)op.dual_partner];
+                a.w2 = wfp(n, o2.d.w); a.bias2 = wfp(n, o2.d.bias); a.out2 = (float *)buf(o2.d.out_raw);
+                headconv_f32_dual_kernel<8, 3><<<n->n_sm * 8, 128, 2 * sm, s>>>(a);
+                break;
+            }
             const int cpl = d.cin / 32;
             const int g2 = n->n_sm * 8;
             bool done = true;
@@ -1378,6 +1490,8 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.skip = 0;
         op.block_fused = 0;
         op.in_block = 0;
+        op.dual_partner = -1;
+        op.dual_skip = 0;
         op.stem_tc = 0;
         op.d_stem_w = nullptr;
         op.d_stem_par = nullptr;
@@ -1498,6 +1612,37 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             if (c2.d.in_buf != c1.d.out_a) continue;
             c1.block_fused = 1;
             c2.in_block = 1;
+        }
+    }
+    // two head convolutions of one shape on one fp32 input -> one launch (headconv_f32_dual_kernel); GAZ_HEAD_DUAL=0 keeps
+    // the two single launches
+    {
+        const char *ed = getenv("GAZ_HEAD_DUAL");
+        const bool dual_on = (ed ? atoi(ed) : 1) != 0 && n->head_f32v && !n->conv_t;
+        for (size_t i = 0; dual_on && i < n->ops.size(); i++) {
+            NetOp &o1 = n->ops[i];
+            const gaz_net_op &d1 = o1.d;
+            if (d1.type != GAZ_OP_HEADCONV || o1.dual_skip || o1.dual_partner >= 0) continue;
+            if (d1.cout != 8 || d1.ksize != 3 || d1.cin % 32 != 0 || d1.cin <= 32) continue;
+            if (n->bufs[(size_t)d1.in_buf].kind != GAZ_BUF_ROWS_F32) continue;
+            if (i + 1 < n->ops.size() && n->ops[i + 1].dense_tc) continue;
+            if ((size_t)2 * 9 * d1.cin * 8 * 4 > 200 * 1024 || ((d1.w * 4) & 15) != 0) continue;
+            for (size_t j = i + 1; j < n->ops.size(); j++) {
+                NetOp &o2 = n->ops[j];
+                const gaz_net_op &d2 = o2.d;
+                if (d2.type != GAZ_OP_HEADCONV || d2.in_buf != d1.in_buf || d2.cin != d1.cin || d2.cout != d1.cout ||
+                    d2.ksize != d1.ksize || o2.dual_skip || ((d2.w * 4) & 15) != 0) continue;
+                if (j + 1 < n->ops.size() && n->ops[j + 1].dense_tc) continue;
+                o1.dual_partner = (int)j;
+                o2.dual_skip = 1;
+                const int smem = 2 * 9 * d1.cin * 8 * 4;
+                if (cudaFuncSetAttribute(headconv_f32_dual_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+                    cudaGetLastError();
+                    o1.dual_partner = -1;
+                    o2.dual_skip = 0;
+                }
+                break;
+            }
         }
     }
     // stem on the tensor cores: 3x3 on 2 planes -> 256 filters, tile == board, bf16 outputs only
@@ -1669,7 +1814,7 @@ int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
 int gaz_net_launches_per_forward(gaz_net *n) { // kernels actually launched: ops folded into another op's kernel do not count
     if (!n) return 0;
     int k = 0;
-    for (auto &op : n->ops) k += (op.skip || op.in_block) ? 0 : 1;
+    for (auto &op : n->ops) k += (op.skip || op.in_block || op.dual_skip) ? 0 : 1;
     return k;
 }
 

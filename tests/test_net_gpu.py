@@ -99,9 +99,9 @@ def test_closed_loop_search_with_cuda_net_is_bit_exact(game, over, iters):
 
 
 @pytest.mark.parametrize("env", [{"GAZ_CONV_T": "1"}, {"GAZ_CONV_PAIR": "0"}, {"GAZ_FUSE_BLOCK": "0"}, {"GAZ_HEAD_MMA": "0"},
-                                 {"GAZ_STEM_TC": "0"}, {"GAZ_HEAD_F32V": "0"}],
+                                 {"GAZ_STEM_TC": "0"}, {"GAZ_HEAD_F32V": "0"}, {"GAZ_HEAD_DUAL": "0"}],
                          ids=["transposed-v3", "single-cta", "unfused-blocks", "cuda-core-head-conv", "cuda-core-stem",
-                              "scalar-fp32-head-conv"])
+                              "scalar-fp32-head-conv", "single-head-conv-launches"])
 def test_alternative_conv_kernels_stay_within_tolerance(env, monkeypatch):
     """the experimental channel-on-lanes kernel (gaz_convt.cuh) and the single-CTA form of the board kernel are
     selected by environment switches read at network creation; both must meet the same tolerance"""
@@ -109,3 +109,21 @@ def test_alternative_conv_kernels_stay_within_tolerance(env, monkeypatch):
         monkeypatch.setenv(k, v)
     test_net_matches_fp32_oracle("gomoku", "softmax", dict(num_blocks=2, use_se=True), 9)
     test_net_matches_fp32_oracle("connect4", "softmax", {}, 70)
+
+
+def test_dual_head_convolution_is_bit_identical_to_two_launches(monkeypatch):
+    """Connect4: the policy and value heads' 3x3 C128->C8 convolutions of the trunk output run as ONE launch
+    (headconv_f32_dual_kernel); GAZ_HEAD_DUAL=0 keeps the two single launches.  Same per-output term order => same bits."""
+    spec = netspec.build_spec("connect4", "softmax")
+    W = netspec.init_weights(spec, seed=1)
+    st = net_util.random_states("connect4", 333, seed=4)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GAZ_HEAD_DUAL", flag)
+        net = Net(spec, W, max_batch=512)
+        pol, val, lg = net.forward(st, want_logits=True)
+        outs.append((pol.copy(), val.copy(), lg.copy(), net.n_launches))
+        net.close()
+    assert outs[0][3] == outs[1][3] - 1
+    for a, b in zip(outs[0][:3], outs[1][:3]):
+        np.testing.assert_array_equal(a, b)

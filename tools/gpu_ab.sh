@@ -1,9 +1,5 @@
-# scratch driver for one gpurun call: full round-end verification (what the driver runs)
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 300 python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err; echo ref rc=$?
-timeout 600 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo bench rc=$?
-python -c "
-import json
-d=json.loads(open('gpurun_out/final_bench.json').read().strip().splitlines()[-1]); r=d['roofline']; print('ours', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']), r['frac'], d['clocks']['sm_mhz'], round(d['cpu_baseline']['value']), d['gpu_launches'], d['hbm_bytes'])
-d=json.loads(open('gpurun_out/final_ref.json').read().strip().splitlines()[-1]); print('ref', d['value'], d['cpu_baseline']['cores'])"
+# scratch driver for one gpurun call: dual head convolution (Connect4)
+timeout 120 python tools/check_head_dual.py 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_net_gpu.py tests/test_net_golden_gpu.py -q -x 2>&1 | tail -3
+for v in 1 0 1 0; do GAZ_HEAD_DUAL=$v timeout 300 python bench.py --config connect4 --no-cpu-baseline > gpurun_out/c4_dual$v.json 2> gpurun_out/c4_dual$v.err; python -c "
+import json; d=json.loads(open('gpurun_out/c4_dual$v.json').read().strip().splitlines()[-1]); print('dual=$v', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), d['gpu_launches'])"; done
