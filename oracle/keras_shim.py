@@ -83,10 +83,8 @@ class Sym:
     def __ge__(self, o): return self._bin(o, torch.ge)
 
 
-def _val(a, like=None):
-    if isinstance(a, Sym):
-        return a.value
-    return a
+def _val(a):
+    return a.value if isinstance(a, Sym) else a
 
 
 def _op(fn, *args):
