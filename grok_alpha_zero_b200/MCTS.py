@@ -32,7 +32,7 @@ class MCTS(SearchBase):
                  max_nodes=16384, lib=None):
         self.game = game
         self.session = session
-        self.cache_session = type(session).__name__ == "Cache_Wrapper"
+        self.cache_session = any(c.__name__ == "Cache_Wrapper" for c in type(session).__mro__)   # MCTS.py:102 isinstance
         self.fast_find_win = fast_find_win   # the device look-ahead always scans every reply (same results)
         self.use_njit = use_njit             # accepted for signature compatibility; there is no numba path
         self.c_puct_init = c_puct_init

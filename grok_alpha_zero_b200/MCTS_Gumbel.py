@@ -26,7 +26,7 @@ class MCTS_Gumbel(SearchBase):
                  activation_fn="softmax", fast_find_win=False, max_nodes=8192, lib=None):
         self.game = game
         self.session = session
-        self.cache_session = type(session).__name__ == "Cache_Wrapper"
+        self.cache_session = any(c.__name__ == "Cache_Wrapper" for c in type(session).__mro__)   # MCTS.py:102 isinstance
         self.fast_find_win = fast_find_win
         self.use_gumbel_noise = use_gumbel_noise
         self.use_njit = use_njit

@@ -54,10 +54,11 @@ class ReplayWriter:
 
     def games_done(self):
         if self.use_h5:
-            if not os.path.exists(self.h5_path):
+            try:
+                with _h5.File(self.h5_path, "r") as f:
+                    return int(f["game_stats"][2]) if "game_stats" in f else 0
+            except OSError:         # no file yet (h5py raises FileNotFoundError, an OSError)
                 return 0
-            with _h5.File(self.h5_path, "r") as f:
-                return int(f["game_stats"][2])
         return int(self.data["game_stats"][2])
 
     def add_game(self, boards_aug, policies_aug, values_aug, game_length, winner):
@@ -133,17 +134,19 @@ class BatchedSelfPlay:
         self.limit = int(limit) if self.gumbel else int(limit * 1.5)          # Self_Play.py:99
         self.max_actions = int(train_config["max_actions"])
         stablemax = bool(build_config.get("use_stablemax"))
+        L = 7 if self.name == "connect4" else self.P
+        # iterations a PUCT run can really make: `iteration_limit < n_legal -> 3 * n_legal` (MCTS.py:543-546)
+        self.eff_limit = self.limit if (self.gumbel or self.limit >= L) else 3 * L
         if node_cap is None:
-            L = 7 if self.name == "connect4" else self.P
             # Pools are sized for the tail of WHOLE games, not for the opening: an expansion whose position has terminal
             # replies creates a terminal parent and its k terminal children (MCTS.py:367-428), and the sub-tree kept
             # from the previous move comes on top of the limit new nodes.  Measured peaks per tree (emulated engine, 12
             # full Gomoku games at 1200 iterations: 2806 nodes / 374 k child slots; a 4096-game Connect4 generation
             # overflowed 3.5 x limit nodes).  Gomoku: 4 x limit nodes (~100 B each) and 2 x limit x L child slots (5 B
             # each; only evaluated nodes own L slots) = 3.3 MB per tree; Connect4 / TicTacToe nodes are < 100 B all in.
-            node_cap = (4 if self.name == "gomoku" else 8) * self.limit + 4 * L + 64
+            node_cap = (4 if self.name == "gomoku" else 8) * self.eff_limit + 4 * L + 64
             if slot_cap is None and self.name == "gomoku" and not self.gumbel:
-                slot_cap = 2 * self.limit * L + 256
+                slot_cap = 2 * self.eff_limit * L + 256
             if self.gumbel:
                 node_cap = int(self.limit * 1.5) + 2 * L + 64
             slot_cap = node_cap * min(L, 225) + 256 if slot_cap is None else slot_cap
@@ -222,7 +225,7 @@ class BatchedSelfPlay:
         nxt = (np.asarray(next_mover) > 0).astype(np.int64)                 # the tree of the side to move runs next
         mine = sizes[np.arange(self.n_slots), nxt]
         L = 7 if self.name == "connect4" else self.P
-        full = cont & ((mine[:, 0] + 2 * self.limit > e.node_cap) | (mine[:, 1] + self.limit * L > e.slot_cap))
+        full = cont & ((mine[:, 0] + 2 * self.eff_limit > e.node_cap) | (mine[:, 1] + self.eff_limit * L > e.slot_cap))
         if not full.any():
             return
         mask = np.zeros((self.n_slots, self.tpg), np.uint8)
@@ -298,8 +301,8 @@ class BatchedSelfPlay:
         for s in np.nonzero(live)[0]:
             w = int(winners[s])
             n_act = len(self.traj[s]["z"])
-            if w == -2 and n_act >= self.max_actions:
-                w = 0                                                                      # Self_Play.py:155-157
+            if n_act >= self.max_actions:
+                w = 0      # Self_Play.py:155-157: `if actions_count == max_actions: winner = 0` - a WIN on that ply is a draw too
             if w != -2:
                 done.append((s, w))
         done_slots = [s for s, _ in done]
@@ -405,8 +408,10 @@ def net_spec_from_configs(game_name, build_config, train_config):
         over["num_blocks"] = int(build_config["num_resnet_layers"])
     if "num_filters" in build_config and game_name != "tictactoe":   # TicTacToe/Build_Model.py:22 hard-codes ResNet_Block(64)
         over["filters"] = int(build_config["num_filters"])
-    if "use_se" in build_config:
-        over["use_se"] = bool(build_config["use_se"])
+    # Squeeze-Excitation is opt-in: the reference's builders never wire SE_Block in (Net/ResNet/ResNet_Block.py:27-41) and
+    # its build_config has no such key, so the reference's own configs must give the reference's architecture (and a
+    # keras_bridge checkpoint must load); BASELINE configs[2] asks for it explicitly with use_se=True
+    over["use_se"] = bool(build_config.get("use_se", False))
     return netspec.build_spec(game_name, head, **over)
 
 

@@ -39,6 +39,7 @@ SYMBOLS = {
     "gaz_run_begin": (C.c_int, [_P, _P]),
     "gaz_select": (C.c_int, [_P]),
     "gaz_get_leaves": (C.c_int, [_P, _P, _P]),
+    "gaz_get_leaf_depths": (C.c_int, [_P, _P]),
     "gaz_put_evals": (C.c_int, [_P, _P, _P, C.c_int]),
     "gaz_eval_hash": (C.c_int, [_P, C.c_uint64, C.c_int]),
     "gaz_expand": (C.c_int, [_P]),

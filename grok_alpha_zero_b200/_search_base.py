@@ -66,10 +66,12 @@ class SearchBase:
                 e.eval_net()
             else:
                 states, _ = e.get_leaves()
+                # depth as the reference passes it to Session_Cache.Cache_Wrapper (MCTS.py:346,468-472)
+                depths = e.get_leaf_depths(len(states)) if getattr(self, "cache_session", False) else np.zeros(len(states), np.int32)
                 pol = np.zeros((len(states), self.P), np.float32)
                 val = np.zeros(len(states), np.float32)
                 for i, st in enumerate(states):
-                    p, v = self._host_outputs(st, depth=0)
+                    p, v = self._host_outputs(st, depth=int(depths[i]))
                     pol[i] = self._post_policy(st, p)
                     val[i] = v
                 e.put_evals(pol, val)

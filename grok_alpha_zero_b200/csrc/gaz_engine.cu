@@ -342,6 +342,7 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     e->net = nullptr;
     e->leaf_bound = 0;
     e->round_graph = nullptr; e->round_graph_net = nullptr; e->round_graph_chunks = 0; e->round_graph_warm = 0;
+    e->view_epoch = 0; e->round_graph_epoch = 0;
     View &v = e->v;
     memset(&v, 0, sizeof v);
     v.game = cfg->game;
@@ -429,6 +430,7 @@ int gaz_set_puct_params(gaz_engine *e, float c_init, float c_base) {
     if (!e) return fail("null engine");
     e->v.c_init = c_init;
     e->v.c_base = c_base;
+    e->view_epoch++;
     // C(N) = c_init + ln((N + c_base + 1) / c_base) with the host libm (glibc) so it equals the
     // oracle's / numba's values
     std::vector<double> lut((size_t)e->v.lut_n);
@@ -445,6 +447,7 @@ int gaz_set_gumbel_params(gaz_engine *e, int m, double c_visit, double c_scale, 
     v.c_visit_d = c_visit; v.c_scale_d = c_scale;
     v.use_softmax = use_softmax;
     e->cfg.gumbel_m = m;
+    e->view_epoch++;
     std::vector<TreeState> ts((size_t)v.n_trees);
     if (d2h(ts.data(), v.trees, ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
     for (auto &t : ts) t.g_m = m;
@@ -584,6 +587,18 @@ int gaz_get_leaves(gaz_engine *e, int8_t *states_out, int32_t *trees_out) {
         if (d2h(lr.data(), v.leaves, lr.size() * sizeof(LeafRec), e->stream) != 0) return -1;
         for (int i = 0; i < n; i++) trees_out[i] = lr[(size_t)i].tree;
     }
+    return n;
+}
+
+int gaz_get_leaf_depths(gaz_engine *e, int32_t *depths_out) {
+    if (!e || !depths_out) return fail("null argument");
+    const View &v = e->v;
+    int n = read_leaf_count(e);
+    if (n <= 0) return n;
+    std::vector<LeafRec> lr((size_t)n);
+    if (d2h(lr.data(), v.leaves, lr.size() * sizeof(LeafRec), e->stream) != 0) return -1;
+    // MCTS.py:346 (root: len(game.action_history)) and :468-472 (child: len(node.action_history) of the PARENT node)
+    for (int i = 0; i < n; i++) depths_out[i] = lr[(size_t)i].kind == LEAF_ROOT ? lr[(size_t)i].hist_len : lr[(size_t)i].hist_len - 1;
     return n;
 }
 
@@ -727,6 +742,7 @@ int gaz_gumbel_pi(gaz_engine *e, int tree, float *pi_out) {
 
 int gaz_set_gumbel_noise(gaz_engine *e, const double *noise) {
     if (!e) return fail("null engine");
+    e->view_epoch++;
     if (!noise) { e->v.gumbel_noise = nullptr; return 0; }
     if (!e->d_noise && ealloc(e, &e->d_noise, (size_t)e->v.n_trees * MAXL) != 0) return -1;
     if (h2d(e->d_noise, noise, (size_t)e->v.n_trees * MAXL * sizeof(double), e->stream) != 0) return -1;
@@ -822,6 +838,7 @@ int gaz_gumbel_pi_dense(gaz_engine *e, float *pi_out) {
 
 int gaz_set_tree_keys(gaz_engine *e, const uint64_t *keys) {
     if (!e) return fail("null engine");
+    if ((keys != nullptr) != (e->v.tree_keys != nullptr)) e->view_epoch++;   // the pointer in the View changes
     if (!keys) { e->v.tree_keys = nullptr; return 0; }
     if (!e->d_keys && ealloc(e, &e->d_keys, (size_t)e->v.n_trees) != 0) return -1;
     if (h2d(e->d_keys, keys, (size_t)e->v.n_trees * sizeof(uint64_t), e->stream) != 0) return -1;
@@ -836,6 +853,7 @@ int gaz_set_noise(gaz_engine *e, float dirichlet_alpha, float dirichlet_epsilon,
     e->v.dir_alpha = dirichlet_alpha;
     e->v.dir_eps = dirichlet_epsilon;
     e->v.noise_seed = seed;
+    e->view_epoch++;
     return 0;
 }
 

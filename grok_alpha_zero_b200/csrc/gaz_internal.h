@@ -59,6 +59,9 @@ struct gaz_engine {
     void *round_graph;   // cudaGraphExec_t
     void *round_graph_net;
     int round_graph_chunks, round_graph_warm;
+    // Kernels take the View BY VALUE, so a captured graph bakes in the hyper-parameters and pointers of its capture time.
+    // Every setter that changes e->v bumps view_epoch; run_rounds re-captures when the graph's epoch is stale.
+    unsigned view_epoch, round_graph_epoch;
     int32_t *d_limits;   // [n_trees]
     int16_t *d_actions;  // [n_trees]
     uint8_t *d_mask;     // [n_trees]

@@ -1771,7 +1771,8 @@ static int run_rounds(gaz_engine *e, int n_rounds) {
         if (!use_graph) { if (one_round_eager(e) != 0) return -1; continue; }
         const int bound = e->leaf_bound > 0 ? e->leaf_bound : e->v.n_trees;
         const int chunks = (bound + n->max_batch - 1) / n->max_batch;
-        if (!e->round_graph || e->round_graph_chunks != chunks || e->round_graph_net != (void *)n) {
+        if (!e->round_graph || e->round_graph_chunks != chunks || e->round_graph_net != (void *)n ||
+            e->round_graph_epoch != e->view_epoch) {
             if (e->round_graph_warm < 1) { // first round eagerly: one-time function attributes are set outside a capture
                 if (one_round_eager(e) != 0) return -1;
                 e->round_graph_warm = 1;
@@ -1790,6 +1791,7 @@ static int run_rounds(gaz_engine *e, int n_rounds) {
             e->round_graph = (void *)ex;
             e->round_graph_chunks = chunks;
             e->round_graph_net = (void *)n;
+            e->round_graph_epoch = e->view_epoch;
         }
         CKN(cudaGraphLaunch((cudaGraphExec_t)e->round_graph, e->stream));
     }

@@ -153,6 +153,12 @@ class Engine:
         k = self._ck(self.lib.gaz_get_leaves(self._h, _p(st), _p(tr)))
         return st[:k], tr[:k]
 
+    def get_leaf_depths(self, n=None):
+        """`depth` of every outstanding request as MCTS._compute_outputs passes it to a caching session"""
+        d = np.zeros(self.n_trees if n is None else n, dtype=np.int32)
+        k = self._ck(self.lib.gaz_get_leaf_depths(self._h, _p(d)))
+        return d[:k]
+
     def put_evals(self, policy, value):
         p = np.ascontiguousarray(policy, dtype=np.float32).reshape(-1, self.P)
         v = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)

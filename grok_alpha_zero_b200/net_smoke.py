@@ -6,6 +6,34 @@ import sys
 import numpy as np
 
 
+def run_flagship():
+    """The flagship kernels first, so that they sit at the head of any launch trace of smoke(): one forward pass of a
+    Gomoku 2-block + Squeeze-Excitation network (the layer shapes of BASELINE configs[2]: tcgen05 stem, 1x1 projection, the
+    fused residual-block kernel with SE, C128->C32 head convolutions, mma.sync head convolutions, tensor-core dense) on 6
+    boards, checked against the fp32 restatement with the north-star tolerance."""
+    from . import netspec
+    from .net import Net
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (os.path.join(root, "oracle"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from net_oracle import NetOracle
+    import net_util
+    spec = netspec.build_spec("gomoku", "softmax", num_blocks=2, use_se=True)
+    W = netspec.init_weights(spec, seed=1)
+    st = net_util.random_states("gomoku", 6, seed=4)
+    net = Net(spec, W, max_batch=8)
+    tags = [t[4] for t in net.op_shapes()]
+    assert any(t.startswith("block") for t in tags), "the fused residual-block kernel is not selected: %r" % (tags,)
+    pol, val, lg = net.forward(st, want_logits=True)
+    net.close()
+    ref = NetOracle(spec, W).forward(st)
+    el = float(np.abs(lg - ref["logits"].numpy()).max())
+    ev = float(np.abs(val - ref["value"].numpy().reshape(-1)).max())
+    assert el < 2e-2 and ev < 1e-2, (el, ev)
+    print("flagship net smoke ok: gomoku 2 blocks + SE, max |dlogit| %.4f |dvalue| %.4f" % (el, ev))
+
+
 def run():
     from . import netspec
     from .engine import Engine

@@ -101,6 +101,11 @@ int gaz_select(gaz_engine *e);
 /* the `session.run(["policy","value"], {"inputs": ...})` boundary (MCTS.py:224-235):
  *   states_out: n_leaves * H*W*C int8 (get_input_state_MCTS layout, HWC); trees_out: owning tree */
 int gaz_get_leaves(gaz_engine *e, int8_t *states_out, int32_t *trees_out);
+/* the `depth` the reference hands to a caching session for each outstanding request (MCTS.py:224-235 `kwargs["depth"]`):
+ * len(game.action_history) for a root evaluation (MCTS.py:346), len(node.action_history) of the PARENT node for a child
+ * (MCTS.py:468-472); Session_Cache.Cache_Wrapper.run stores outputs only while depth < max_cache_depth (Session_Cache.py:
+ * 13-26).  depths_out: n_leaves int32, same order as gaz_get_leaves. */
+int gaz_get_leaf_depths(gaz_engine *e, int32_t *depths_out);
 int gaz_put_evals(gaz_engine *e, const float *policy, const float *value, int n);
 /* built-in deterministic evaluator shared with oracle/hash_eval.py (parity runs on the device) */
 int gaz_eval_hash(gaz_engine *e, uint64_t salt, int logits);

@@ -34,6 +34,12 @@ SEED_W, SEED_X = 11, 23
 # with residual gain 0.25 instead of init_weights' default 0.5 - what the SE gate (sigmoid ~ 0.5) does to the bench network -
 # so that a random-init stack stays O(1) and the ABSOLUTE bf16 tolerance keeps its meaning (logits |max| 6.4 -> ~3).
 RES_GAIN = {"gomoku_softmax": 0.25, "gomoku_stablemax": 0.25}
+# "_g1" fixtures: the builders' own initialisation scale - he_normal at gain 1 everywhere (Gomoku/Build_Model.py:10-88,
+# Connect4/Build_Model.py:22-75 pass kernel_initializer="he_normal" with no damping), kernels NOT pre-rounded to bf16.
+# A random ten-block stack then reaches |logit| ~ 150, so these fixtures are judged with the scale-aware tolerance of
+# tests/test_net_golden_gpu.py (the absolute north-star atol cannot hold for 8-bit-significand operands there).
+UNDAMPED = dict(residual_gain=1.0, head_gain=1.0, bf16_kernels=False)
+INIT = {"gomoku_softmax_g1": UNDAMPED, "connect4_softmax_g1": UNDAMPED}
 CASES = [
     ("gomoku_softmax", "gomoku", "softmax", dict(num_blocks=10, use_se=False), dict(use_stablemax=False), dict(use_gumbel=False), 3),
     ("gomoku_stablemax", "gomoku", "stablemax", dict(num_blocks=10, use_se=False), dict(use_stablemax=True), dict(use_gumbel=False), 3),
@@ -42,6 +48,8 @@ CASES = [
     ("connect4_stablemax", "connect4", "stablemax", dict(num_blocks=3), dict(use_stablemax=True), dict(use_gumbel=False), 6),
     ("tictactoe_softmax", "tictactoe", "softmax", dict(num_blocks=2), dict(use_stablemax=False), dict(use_gumbel=False), 8),
     ("tictactoe_linear", "tictactoe", "linear", dict(num_blocks=2), dict(use_stablemax=False), dict(use_gumbel=True), 8),
+    ("gomoku_softmax_g1", "gomoku", "softmax", dict(num_blocks=10, use_se=False), dict(use_stablemax=False), dict(use_gumbel=False), 3),
+    ("connect4_softmax_g1", "connect4", "softmax", dict(num_blocks=5), dict(use_stablemax=False), dict(use_gumbel=False), 6),
 ]
 _BUILDERS = {"gomoku": "Gomoku.Build_Model", "connect4": "Connect4.Build_Model", "tictactoe": "TicTacToe.Build_Model"}
 
@@ -80,7 +88,8 @@ def load_weights(model, spec, W):
 def make_case(name, game, head, over, build_over, train_over, n):
     import net_util
     spec = netspec.build_spec(game, head, **over)
-    W = netspec.init_weights(spec, seed=SEED_W, residual_gain=RES_GAIN.get(name, 0.5))
+    init = dict(INIT.get(name, dict(residual_gain=RES_GAIN.get(name, 0.5))))
+    W = netspec.init_weights(spec, seed=SEED_W, **init)
     states = net_util.random_states(game, n, seed=SEED_X)
     model = reference_model(game, spec, build_over, train_over)
     load_weights(model, spec, W)
@@ -92,7 +101,7 @@ def make_case(name, game, head, over, build_over, train_over, n):
     return dict(states=states, policy=pol.astype(np.float32), value=val.astype(np.float32).reshape(-1),
                 logits=logits.astype(np.float32), policy_dtype=np.array(str(pol.dtype)),
                 meta=np.array(repr(dict(game=game, head=head, over=over, seed_w=SEED_W, seed_x=SEED_X,
-                                         residual_gain=RES_GAIN.get(name, 0.5)))),
+                                         residual_gain=init["residual_gain"], init=init))),
                 layer_names=np.array([l.name for l in model.layers if l._vars]))
 
 

@@ -86,3 +86,21 @@ def test_spec_from_reference_configs():
     assert net_spec_from_configs("tictactoe", bc, {"use_gumbel": False})["cfg"]["filters"] == 64
     assert net_spec_from_configs("connect4", dict(bc, num_filters=96), {"use_gumbel": False})["cfg"]["filters"] == 96
     assert net_spec_from_configs("gomoku", bc, {"use_gumbel": True})["policy_head"] == "linear"
+
+
+def test_reference_configs_build_the_reference_architecture():
+    """`run_self_play(Gomoku, <reference configs>, folder)`: the reference's build_config has no `use_se` key and its
+    builders never wire SE_Block in (Net/ResNet/ResNet_Block.py:27-41), so the spec must be SE-free, must map onto the
+    Keras variable names, and a checkpoint exported through the bridge must load back."""
+    from grok_alpha_zero_b200.Self_Play import net_spec_from_configs
+    ref_build_config = {"num_resnet_layers": 4, "num_filters": 128, "rr_alpha": 0.05, "mixed_precision": None,
+                        "use_stablemax": False}                                    # Gomoku/Gomoku.py:5-12
+    spec = net_spec_from_configs("gomoku", ref_build_config, {"use_gumbel": False})
+    assert spec["cfg"]["use_se"] is False and spec["cfg"]["num_blocks"] == 4
+    vm = kb.keras_variable_map(spec)
+    W = netspec.init_weights(spec, seed=3)
+    assert set(vm) == set(W)                                                       # every array has a Keras name; no SE arrays
+    back = kb.import_keras_weights(spec, kb.export_keras_weights(spec, W))
+    assert all(np.array_equal(back[k], W[k]) for k in W)
+    # opt-in stays possible for the benchmark configuration (BASELINE configs[2])
+    assert net_spec_from_configs("gomoku", dict(ref_build_config, use_se=True), {})["cfg"]["use_se"] is True

@@ -25,12 +25,13 @@ def load_case(path):
     z = np.load(path)
     meta = ast.literal_eval(str(z["meta"]))
     spec = netspec.build_spec(meta["game"], meta["head"], **meta["over"])
-    W = netspec.init_weights(spec, seed=meta["seed_w"], residual_gain=meta["residual_gain"])
+    init = meta.get("init", dict(residual_gain=meta["residual_gain"]))     # "_g1" fixtures: undamped he_normal, fp32 kernels
+    W = netspec.init_weights(spec, seed=meta["seed_w"], **init)
     return z, meta, spec, W
 
 
 def test_fixture_inventory():
-    assert len(FIXTURES) == 7
+    assert len(FIXTURES) == 9
     assert {os.path.basename(f).split("_")[1] for f in FIXTURES} == {"gomoku", "connect4", "tictactoe"}
 
 
@@ -69,4 +70,4 @@ def test_fixtures_are_reproducible_from_the_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "gen_net_golden.py"), "--check"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("ok net_") == 8
+    assert r.stdout.count("ok net_") == 10

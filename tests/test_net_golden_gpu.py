@@ -16,6 +16,12 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_ATOL = 2e-2
 VALUE_ATOL = 1e-2
+# Undamped fixtures ("_g1": he_normal at gain 1 as the builders initialise, fp32 kernels): a random ten-block stack reaches
+# |logit| ~ 150 and bf16 operands (8-bit significands, rounding 2^-9 per operand) cannot hold an ABSOLUTE 2e-2 there -
+# NetOracle(bf16_sim=True) shows it on the CPU with no CUDA involved (DESIGN 1.1 has the table).  They are held to the same
+# RELATIVE accuracy the north-star atol means at |logit| ~ 3: 1.5 % of the largest logit / pre-tanh value.
+LOGIT_RTOL_UNDAMPED = 1.5e-2
+VALUE_ATOL_UNDAMPED = 4e-2
 
 
 @pytest.mark.parametrize("path", FIXTURES, ids=lambda p: p.split("net_")[-1][:-4])
@@ -29,6 +35,12 @@ def test_cuda_net_matches_the_traced_reference_model(path):
     err_p = np.abs(pol - z["policy"]).max()
     print("%s: logits err %.4g (absmax %.3g) value err %.4g policy err %.3g" % (meta, err_l, np.abs(lg).max(), err_v, err_p))
     assert np.isfinite(lg).all() and np.isfinite(val).all()
+    if "init" in meta and meta["init"]["residual_gain"] == 1.0:
+        scale = float(np.abs(z["logits"]).max())
+        assert err_l <= max(LOGIT_ATOL, LOGIT_RTOL_UNDAMPED * scale), (err_l, scale)
+        assert err_v <= VALUE_ATOL_UNDAMPED, err_v
+        assert (lg.argmax(-1) == z["logits"].argmax(-1)).all()
+        return
     assert err_l <= LOGIT_ATOL, err_l
     assert err_v <= VALUE_ATOL, err_v
     if meta["head"] != "linear":    # probabilities: a logit error e moves a probability p by about e * p

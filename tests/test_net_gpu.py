@@ -54,6 +54,38 @@ def test_net_matches_fp32_oracle(game, head, over, n):
     net.close()
 
 
+UNDAMPED = [("gomoku", dict(use_se=False)), ("gomoku", dict(use_se=True)), ("connect4", {})]
+
+
+@pytest.mark.parametrize("game,over", UNDAMPED, ids=lambda c: str(c).replace(" ", ""))
+def test_undamped_he_normal_weights_hold_the_relative_tolerance(game, over):
+    """The builders' own initialisation scale (he_normal at gain 1, kernels not pre-rounded to bf16; Gomoku/Build_Model.py:
+    10-88, Connect4/Build_Model.py:22-75) at BASELINE depth.  Random-init logits reach 15 - 150 there, so the absolute
+    north-star atol cannot hold for bf16 operands; what must hold is the same relative accuracy (1.5 % of the largest
+    logit), finite outputs and the same arg-max.  Measured figures go to gpurun_out/net_undamped.jsonl for DESIGN 1.1."""
+    import json, os
+    spec = netspec.build_spec(game, "linear", **over)
+    W = netspec.init_weights(spec, seed=1, residual_gain=1.0, head_gain=1.0, bf16_kernels=False)
+    st = net_util.random_states(game, 24, seed=4)
+    ref = NetOracle(spec, W).forward(st)
+    net = Net(spec, W, max_batch=32)
+    pol, val, lg = net.forward(st, want_logits=True)
+    net.close()
+    rl = ref["logits"].numpy()
+    err_l, scale = float(np.abs(lg - rl).max()), float(np.abs(rl).max())
+    err_v = float(np.abs(val - ref["value"].numpy().reshape(-1)).max())
+    rec = dict(game=game, over=over, logit_err=err_l, logit_absmax=scale, rel=err_l / scale, value_err=err_v,
+               argmax_equal=bool((lg.argmax(-1) == rl.argmax(-1)).all()))
+    print(rec)
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/net_undamped.jsonl", "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    assert np.isfinite(lg).all() and np.isfinite(val).all()
+    assert err_l <= max(LOGIT_ATOL, 1.5e-2 * scale), rec
+    assert err_v <= 4e-2, rec
+    assert rec["argmax_equal"], rec
+
+
 @pytest.mark.parametrize("game,over,iters", [("connect4", dict(num_blocks=2), 120), ("gomoku", dict(num_blocks=2, use_se=True), 250)])
 def test_closed_loop_search_with_cuda_net_is_bit_exact(game, over, iters):
     """Engine + attached CUDA network (leaves never leave HBM) vs the C oracle calling the SAME CUDA
@@ -127,3 +159,37 @@ def test_dual_head_convolution_is_bit_identical_to_two_launches(monkeypatch):
     assert outs[0][3] == outs[1][3] - 1
     for a, b in zip(outs[0][:3], outs[1][:3]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_setters_take_effect_after_the_round_graph_was_captured(monkeypatch):
+    """Kernels take the engine's View by value, so a captured round graph bakes in c_puct / Dirichlet / Gumbel parameters
+    (ADVICE r1): a setter called after the first `rounds_net` must invalidate the graph.  Run A replays graphs and switches
+    the Dirichlet noise on and c_puct_init up mid-search; run B does the same with graphs disabled (GAZ_GRAPH=0, eager
+    launches read the live View); run C never calls the setters.  A must equal B bit for bit and differ from C."""
+    spec = netspec.build_spec("connect4", "softmax", num_blocks=2)
+    W = netspec.init_weights(spec, seed=2)
+
+    def run(graph, switch):
+        monkeypatch.setenv("GAZ_GRAPH", "1" if graph else "0")
+        net = Net(spec, W, max_batch=16)
+        eng = Engine("connect4", n_games=8, mode="puct", trees_per_game=1, c_puct_init=2.5, iters_hint=200)
+        net.attach(eng)
+        if eng.new_roots() > 0:
+            eng.eval_net()
+            eng.expand()
+        eng.run_begin([120] * 8)
+        eng.rounds_net(12)                       # round 1 eager, round 2 captures, rounds 3.. replay
+        if switch:
+            eng.set_noise(0.5, 0.25, seed=11)
+            eng.set_puct_params(4.0, 19652.0)
+        eng.rounds_net(60)
+        vis, val, info = eng.root_dense()
+        assert eng.status() == 0
+        eng.close(); net.close()
+        return vis.copy(), val.copy(), info.copy()
+
+    a, b, c = run(True, True), run(False, True), run(True, False)
+    assert int(a[2][:, 2].min()) == 72
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert not np.array_equal(a[0], c[0])
