@@ -39,7 +39,8 @@ def test_cuda_net_matches_the_traced_reference_model(path):
         scale = float(np.abs(z["logits"]).max())
         assert err_l <= max(LOGIT_ATOL, LOGIT_RTOL_UNDAMPED * scale), (err_l, scale)
         assert err_v <= VALUE_ATOL_UNDAMPED, err_v
-        assert (lg.argmax(-1) == z["logits"].argmax(-1)).all()
+        pick = np.take_along_axis(z["logits"], lg.argmax(-1)[:, None], 1)[:, 0]
+        assert float((z["logits"].max(-1) - pick).max()) <= 2 * err_l      # logits closer than the error may swap
         return
     assert err_l <= LOGIT_ATOL, err_l
     assert err_v <= VALUE_ATOL, err_v

@@ -74,8 +74,11 @@ def test_undamped_he_normal_weights_hold_the_relative_tolerance(game, over):
     rl = ref["logits"].numpy()
     err_l, scale = float(np.abs(lg - rl).max()), float(np.abs(rl).max())
     err_v = float(np.abs(val - ref["value"].numpy().reshape(-1)).max())
+    # the move our logits prefer must be one the reference rates within the error bound of its own best (two logits closer
+    # than the error may swap: at |logit| ~ 150 that happens)
+    pick = np.take_along_axis(rl, lg.argmax(-1)[:, None], 1)[:, 0]
     rec = dict(game=game, over=over, logit_err=err_l, logit_absmax=scale, rel=err_l / scale, value_err=err_v,
-               argmax_equal=bool((lg.argmax(-1) == rl.argmax(-1)).all()))
+               argmax_equal=bool((lg.argmax(-1) == rl.argmax(-1)).all()), argmax_regret=float((rl.max(-1) - pick).max()))
     print(rec)
     if os.path.isdir("gpurun_out"):
         with open("gpurun_out/net_undamped.jsonl", "a") as f:
@@ -83,7 +86,7 @@ def test_undamped_he_normal_weights_hold_the_relative_tolerance(game, over):
     assert np.isfinite(lg).all() and np.isfinite(val).all()
     assert err_l <= max(LOGIT_ATOL, 1.5e-2 * scale), rec
     assert err_v <= 4e-2, rec
-    assert rec["argmax_equal"], rec
+    assert rec["argmax_regret"] <= 2 * err_l, rec
 
 
 @pytest.mark.parametrize("game,over,iters", [("connect4", dict(num_blocks=2), 120), ("gomoku", dict(num_blocks=2, use_se=True), 250)])
