@@ -1,7 +1,7 @@
-// gaz_conv.cuh -- board-tile implicit-GEMM convolution on tcgen05 (v2 of the trunk convolution).
+// gaz_conv.cuh -- board-tile implicit-GEMM convolution on tcgen05.
 //
 // One persistent CTA walks 256-row tiles of the padded-row activation tensor (Gomoku: 256 rows = exactly one
-// board).  Compared with v1 (one TMA tile per filter tap) this kernel is built around the shared-memory port,
+// board).  The kernel is built around the shared-memory port,
 // which is what bounds an M=128 x N=128 cta_group::1 MMA (8 KB of operand reads per 64-cycle MMA = 128 B/clk):
 //   * the activation SLAB of a tile (24 halo rows + 256 rows + 24 halo rows, 64 channels, SWIZZLE_128B) is
 //     loaded ONCE per 64-channel K-block and all 9 filter taps read it through row-shifted UMMA descriptors
@@ -69,7 +69,6 @@ struct BoardConvArgs {
     // shift_b, 128 floats each.  The epilogue reads them with uniform LDC, which keeps them off the shared-memory
     // port that the MMAs saturate (a broadcast LDS per value cost 25 % of the port in v2.0, ncu r01).
     float par[5 * 128];
-    const float *d_par;       // the same 640 floats in global memory (v3 reads them per lane: a lane-indexed LDC serialises)
     const float *res;         // blocked fp32 residual stream (optional)
     float *out_raw;           // blocked fp32 output (optional)
     __nv_bfloat16 *out_a;     // relu(scale_a * v + shift_a) as bf16 rows (optional)

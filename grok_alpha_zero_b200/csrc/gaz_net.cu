@@ -1,21 +1,17 @@
 // gaz_net.cu -- policy/value network evaluator (include/gaz_net.h).
 //
-// Trunk convolutions (C_in in {64,128,256}, C_out in {32,64,128}) run as implicit GEMMs on the 5th-gen
-// tensor cores: one persistent, warp-specialised kernel per layer
-//   warp 0      TMA producer   - per K-block one 128-row x 64-channel activation tile (row-shifted by the
-//                                filter tap) and one C_out x 64 weight tile, SWIZZLE_128B, mbarrier ring
-//   warp 1      MMA issuer     - tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128
-//   warps 2..5  epilogue       - tcgen05.ld -> bias (+ fp32 residual) -> fp32 residual stream and/or
-//                                relu(BN(.)) bf16 operand(s) of the next layer, zeroing the padding rows
-// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Stem (C_in 2/4), small head convolutions, SE and dense layers are CUDA-core kernels (fp32).
+// Trunk convolutions (C_in in {64,128,256}, C_out in {32,64,128}) run as implicit GEMMs on the 5th-gen tensor cores
+// (tcgen05.mma cta_group::2, bf16 x bf16 -> fp32 in TMEM, operands staged by TMA): gaz_conv.cuh (one convolution per
+// launch, any board geometry), gaz_block.cuh (a whole residual block per launch when a board is one 256-row tile),
+// gaz_stem.cuh (the Gomoku-shaped stem as an implicit GEMM).  This file holds the kernels that are too small for a tcgen05
+// pipeline - stems on 2/4 input planes, head convolutions (mma.sync or CUDA cores), SE fallback, dense layers, policy
+// activation - and the executor that walks the op list of include/gaz_net.h.
 // Reference network definitions: */Build_Model.py, Net/ResNet/ResNet_Block.py:27-41,
 // Net/SE/SE_Block.py:15-23, Net/Stablemax.py:7-11.
 #include "../../include/gaz_net.h"
 #include "gaz_internal.h"
 #include "gaz_tc.cuh"
 #include "gaz_conv.cuh"
-#include "gaz_convt.cuh"
 #include "gaz_block.cuh"
 #include "gaz_stem.cuh"
 
@@ -25,186 +21,12 @@
 
 using namespace gaz_tc;
 using gaz_conv::f32_blk_index;
-using gaz_convt::f32_t_index;
-// fp32 row tensors: layout 0 = 32x32 blocked (gaz_conv.cuh, default), 1 = 8-row interleaved (gaz_convt.cuh, GAZ_CONV_T=1)
-__host__ __device__ __forceinline__ size_t f32_index(long long row, int c, int C, int layout) {
-    return layout ? f32_t_index(row, c, C) : f32_blk_index(row, c, C);
-}
 
 #define CKN(x)                                                                                             \
     do {                                                                                                   \
         cudaError_t _e = (x);                                                                              \
         if (_e != cudaSuccess) return gaz_fail("%s: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
-
-// ====================================================================== tcgen05 conv ==
-struct ConvArgs {
-    const int32_t *count;
-    int max_count;
-    int P_pad, Wp;
-    int taps, kpt; // filter taps (1 or 9), 64-channel K-blocks per tap
-    const float *bias;
-    const float *res;
-    float *out_raw;
-    __nv_bfloat16 *out_a;
-    const float *scale_a, *shift_a;
-    __nv_bfloat16 *out_b;
-    const float *scale_b, *shift_b;
-};
-
-template <int BN> struct ConvCfg {
-    static constexpr int STAGES = BN == 128 ? 6 : 8;
-    static constexpr int A_BYTES = 128 * 64 * 2;
-    static constexpr int B_BYTES = BN * 64 * 2;
-    static constexpr int TMEM_COLS = BN == 128 ? 256 : (BN == 64 ? 128 : 64);
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 512 /*barriers*/ + 5 * BN * 4;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
-    using Cfg = ConvCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = base;
-    uint8_t *sB = base + STAGES * Cfg::A_BYTES;
-    uint64_t *bars = (uint64_t *)(sB + STAGES * Cfg::B_BYTES);
-    uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 4);
-    float *s_par = (float *)(bars + 2 * STAGES + 8); // bias | scale_a | shift_a | scale_b | shift_b
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int cnt = *p.count;
-    if (cnt > p.max_count) cnt = p.max_count;
-    const int valid_rows = cnt * p.P_pad;
-    const int n_mtiles = (valid_rows + 127) >> 7;
-    const int n_kb = p.taps * p.kpt;
-
-    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-        s_par[i] = p.bias ? p.bias[i] : 0.0f;
-        s_par[BN + i] = p.scale_a ? p.scale_a[i] : 1.0f;
-        s_par[2 * BN + i] = p.shift_a ? p.shift_a[i] : 0.0f;
-        s_par[3 * BN + i] = p.scale_b ? p.scale_b[i] : 1.0f;
-        s_par[4 * BN + i] = p.shift_b ? p.shift_b[i] : 0.0f;
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
-        fence_barrier_init();
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) { // ---------------- TMA producer
-            int stage = 0, phase = 0;
-            for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-                for (int kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-                    const int tap = kb / p.kpt, cb = kb - tap * p.kpt;
-                    int shift = 0;
-                    if (p.taps == 9) shift = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
-                    tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, mt * 128 + shift);
-                    tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) { // ---------------- MMA issuer
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-            int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < n_kb; kb++) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                  (uint32_t)((kb | k) != 0));
-                    umma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(&tfull[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            }
-        }
-    } else { // ---------------- epilogue warps 2..5 (TMEM lane quarter = warp % 4)
-        const int q = warp & 3;
-        int acc = 0, acc_phase = 0;
-        for (int mt = blockIdx.x; mt < n_mtiles; mt += gridDim.x) {
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
-            const int row = mt * 128 + q * 32 + lane;
-            const int pos = row % p.P_pad;
-            const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-            const bool live = row < valid_rows && yy != 0 && xx != p.Wp - 1;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ch++) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + s_par[ch * 32 + j];
-                const size_t blk = f32_blk_index(row, ch * 32, BN); // blocked fp32 row tensor (gaz_conv.cuh)
-                if (p.res) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float4 t = *reinterpret_cast<const float4 *>(p.res + blk + (j >> 1) * 256 + (j & 1) * 4);
-                        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-                    }
-                }
-                if (p.out_raw) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        *reinterpret_cast<float4 *>(p.out_raw + blk + (j >> 1) * 256 + (j & 1) * 4) =
-                            live ? make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int o = 0; o < 2; o++) {
-                    __nv_bfloat16 *outp = o == 0 ? p.out_a : p.out_b;
-                    if (!outp) continue;
-                    const float *sc = s_par + (1 + 2 * o) * BN + ch * 32, *sh = s_par + (2 + 2 * o) * BN + ch * 32;
-                    uint4 *op = reinterpret_cast<uint4 *>(outp + (size_t)row * BN + ch * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            int c = 8 * j + 2 * t;
-                            float a0 = fmaxf(fmaf(sc[c], v[c], sh[c]), 0.0f);
-                            float a1 = fmaxf(fmaf(sc[c + 1], v[c + 1], sh[c + 1]), 0.0f);
-                            __nv_bfloat162 h = __floats2bfloat162_rn(live ? a0 : 0.0f, live ? a1 : 0.0f);
-                            w[t] = *reinterpret_cast<uint32_t *>(&h);
-                        }
-                        op[j] = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
 
 // ====================================================================== CUDA-core kernels ==
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -213,7 +35,7 @@ struct StemArgs {
     const int32_t *count;
     int max_count;
     const int8_t *states; // [leaf][H*W*Cin] HWC
-    int H, W, Cin, Cout, K, P_pad, Wp, act, layout;
+    int H, W, Cin, Cout, K, P_pad, Wp, act;
     const float *w;       // [K*K][Cin][Cout]
     const float *bias, *scale, *shift; // conv bias, stem BN affine
     __nv_bfloat16 *out_q; // activation itself in bf16 (operand of a 1x1 projection), optional
@@ -332,10 +154,7 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
             }
             const size_t o = (size_t)row * p.Cout + c0;
             if (p.out_raw) {
-                if (p.layout == 0) *reinterpret_cast<float4 *>(p.out_raw + f32_blk_index(row, c0, p.Cout)) = make_float4(v[0], v[1], v[2], v[3]);
-                else
-#pragma unroll
-                    for (int j = 0; j < 4; j++) p.out_raw[f32_t_index(row, c0 + j, p.Cout)] = v[j];
+                *reinterpret_cast<float4 *>(p.out_raw + f32_blk_index(row, c0, p.Cout)) = make_float4(v[0], v[1], v[2], v[3]);
             }
             if (p.out_q) {
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
@@ -351,7 +170,7 @@ template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(Ste
 
 struct SeArgs {
     const int32_t *count;
-    int max_count, H, W, C, R, P_pad, Wp, layout;
+    int max_count, H, W, C, R, P_pad, Wp;
     const float *c2;  // conv2 output (+bias), fp32 padded rows
     const float *res; // residual stream
     const float *w1, *b1, *w2, *b2; // dense1 [C][R], dense2 [R][C]
@@ -371,7 +190,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
         const long long row0 = (long long)b * p.P_pad;
         float s = 0.0f;
         for (int y = 0; y < p.H; y++)
-            for (int x = 0; x < p.W; x++) s += p.c2[f32_index(row0 + (y + 1) * p.Wp + x, c, p.C, p.layout)];
+            for (int x = 0; x < p.W; x++) s += p.c2[f32_blk_index(row0 + (y + 1) * p.Wp + x, c, p.C)];
         s_mean[c] = s / (float)(p.H * p.W);
         __syncthreads();
         if (c < p.R) {
@@ -389,7 +208,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
         for (int pos = 0; pos < p.P_pad; pos++) {
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
             const bool live = yy != 0 && xx != p.Wp - 1;
-            const size_t ob = f32_index(row0 + pos, c, p.C, p.layout);
+            const size_t ob = f32_blk_index(row0 + pos, c, p.C);
             const size_t o = (size_t)(row0 + pos) * p.C + c;
             float v = live ? fmaf(p.c2[ob], gate, p.res[ob]) : 0.0f;
             if (p.out_raw) p.out_raw[ob] = v;
@@ -402,7 +221,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
 
 struct HeadConvArgs {
     const int32_t *count;
-    int max_count, H, W, Cin, Cout, K, P_pad, Wp, in_f32, layout;
+    int max_count, H, W, Cin, Cout, K, P_pad, Wp, in_f32;
     long long in_rows;  // allocated rows of the input buffer
     const void *in;     // padded rows, bf16 or fp32
     const float *w;     // [K*K][Cin][Cout]
@@ -441,7 +260,7 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
                 const float *wp = s_w + (size_t)((ky * p.K + kx) * p.Cin) * p.Cout;
                 if (p.in_f32) {
                     for (int ci = 0; ci < p.Cin; ci++) {
-                        const float a = ((const float *)p.in)[f32_index(r, ci, p.Cin, p.layout)];
+                        const float a = ((const float *)p.in)[f32_blk_index(r, ci, p.Cin)];
 #pragma unroll
                         for (int j = 0; j < 16; j++) if (j < p.Cout) acc[j] = fmaf(a, wp[ci * p.Cout + j], acc[j]);
                     }
@@ -691,7 +510,7 @@ __global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
 #pragma unroll
             for (int j = 0; j < CPL; j++) {
                 float x_;
-                if (IN_F32) x_ = ((const float *)p.in)[f32_index(r, lane + 32 * j, p.Cin, p.layout)];
+                if (IN_F32) x_ = ((const float *)p.in)[f32_blk_index(r, lane + 32 * j, p.Cin)];
                 else x_ = __bfloat162float(((const __nv_bfloat16 *)p.in)[r * p.Cin + lane + 32 * j]);
                 a[t][j] = ok ? x_ : 0.0f;
             }
@@ -727,78 +546,6 @@ __global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
         // lanes whose low log2(32/COUT) bits are zero hold output channel co_base
         constexpr int REP = 32 / COUT;
         if ((lane & (REP - 1)) == 0) p.out[(size_t)idx * COUT + co_base] = acc[0] + p.bias[co_base];
-    }
-}
-
-// Head convolutions on a 32-channel bf16 row tensor (Gomoku policy_conv1 3x3 32->8, value_conv1 1x1 32->4): one CTA
-// stages a whole board (+ halo rows) in shared memory with coalesced 16-byte loads, then every warp walks cells with
-// lane = input channel, weights in registers and the halving butterfly of headconv_warp_kernel.  Compared with the
-// per-cell global loads of headconv_warp_kernel the 9-fold re-read of the input moves from L2 to shared memory.
-template <int COUT, int K>
-__global__ void __launch_bounds__(128) headconv_board_kernel(HeadConvArgs p) {
-    constexpr int TAPS = K * K, kh = K >> 1;
-    extern __shared__ __align__(16) uint8_t s_board[]; // [(P_pad + 2 * halo)][32] bf16
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int halo = kh * (p.Wp + 1);
-    const int srows = p.P_pad + 2 * halo;
-    float w[TAPS][COUT];
-#pragma unroll
-    for (int t = 0; t < TAPS; t++)
-#pragma unroll
-        for (int co = 0; co < COUT; co++) w[t][co] = p.w[(size_t)(t * 32 + lane) * COUT + co];
-    int cnt = *p.count;
-    if (cnt > p.max_count) cnt = p.max_count;
-    const int ncell = p.H * p.W;
-    const uint4 *gin = reinterpret_cast<const uint4 *>(p.in); // 4 uint4 per 64-byte row
-    uint4 *sin = reinterpret_cast<uint4 *>(s_board);
-    for (int b = blockIdx.x; b < cnt; b += gridDim.x) {
-        __syncthreads();
-        const long long g0 = ((long long)b * p.P_pad - halo) * 4;
-        for (int i = threadIdx.x; i < srows * 4; i += blockDim.x) {
-            const long long gi = g0 + i;
-            sin[i] = (gi >= 0 && gi < p.in_rows * 4) ? gin[gi] : make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
-        const __nv_bfloat16 *sb = reinterpret_cast<const __nv_bfloat16 *>(s_board) + (size_t)halo * 32 + lane;
-        for (int cell = warp; cell < ncell; cell += 4) {
-            const int y = cell / p.W, x = cell - y * p.W;
-            const int r0 = (y + 1) * p.Wp + x;
-            float acc[COUT];
-#pragma unroll
-            for (int co = 0; co < COUT; co++) acc[co] = 0.0f;
-#pragma unroll
-            for (int t = 0; t < TAPS; t++) {
-                const float a = __bfloat162float(sb[(r0 + (t / K - kh) * p.Wp + (t % K - kh)) * 32]);
-#pragma unroll
-                for (int co = 0; co < COUT; co++) acc[co] = fmaf(a, w[t][co], acc[co]);
-            }
-            int n = COUT, co_base = 0;
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) {
-                if (n > 1) {
-                    const int h = n >> 1;
-                    const bool up = (lane & m) != 0;
-#pragma unroll
-                    for (int i = 0; i < COUT / 2; i++)
-                        if (i < h) {
-                            const float send = up ? acc[i] : acc[i + h];
-                            const float keep = up ? acc[i + h] : acc[i];
-                            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-                        }
-                    co_base += up ? h : 0;
-                    n = h;
-                } else {
-                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], m);
-                }
-            }
-            constexpr int REP = 32 / COUT;
-            if ((lane & (REP - 1)) == 0) {
-                const size_t f = (size_t)cell * COUT + co_base;
-                const float vv = acc[0] + p.bias[co_base];
-                if (p.out_act) p.out_act[(size_t)b * p.act_ld + f] = __float2bfloat16_rn(fmaxf(fmaf(p.act_scale[f], vv, p.act_shift[f]), 0.0f));
-                else p.out[(size_t)b * ncell * COUT + f] = vv;
-            }
-        }
     }
 }
 
@@ -1036,11 +783,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 struct NetBuf { int kind, width; void *ptr; size_t bytes; };
 struct NetOp {
     gaz_net_op d;
-    CUtensorMap tmA, tmB; // v1: 128-row activation box
-    CUtensorMap tmA2;     // v2 (conv_board_kernel): 152-row half-slab box
-    CUtensorMap tmB2;     // v2 pair mode: half of the output channels per CTA
-    CUtensorMap tmOa, tmOb; // v2 epilogue: bf16 outputs as 32-row x 32-channel SWIZZLE_64B store boxes
-    CUtensorMap tmWt, tmOta, tmOtb; // v3 (conv_t_kernel): weight box of min(cout,128) rows, 16-row x 32-channel store boxes
+    CUtensorMap tmA2;     // activations: 152-row half-slab box
+    CUtensorMap tmB2;     // weights: half of the output channels per CTA of a pair
+    CUtensorMap tmOa, tmOb; // epilogue: bf16 outputs as 32-row x 32-channel SWIZZLE_64B store boxes
     int fused_se;         // this conv carries the following SE op in its epilogue
     gaz_net_op se;        // ... whose parameters are here
     int skip;             // SE op folded into the previous conv
@@ -1049,8 +794,7 @@ struct NetOp {
     int dual_partner;     // HEADCONV: index of a later head convolution of the same shape on the same input that this op's
     int dual_skip;        // launch computes as well (headconv_f32_dual_kernel); dual_skip marks that later op
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
-    float *d_par;         // device copy (v3 kernel)
-    float *d_se_b1;       // v3 fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
+    float *d_se_b1;       // fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
     // dense layer on the tensor cores (DENSE op fed by a HEADCONV op): bf16 activated input + bf16 [Out][In] weights
     int dense_tc;
     __nv_bfloat16 *d_act; // [rows_dense][In]: written by the producing head convolution
@@ -1058,7 +802,7 @@ struct NetOp {
     int stem_tc;          // stem on the tensor cores (gaz_stem.cuh): d_stem_w / d_stem_par / tmOa (out_a) / tmOb (out_q) are set
     uint16_t *d_stem_w;   // [256][64] bf16 hi | lo split filters
     float *d_stem_par;    // [4][256] BN scale | shift + scale * bias | scale_a | shift_a
-    CUtensorMap tmDA, tmDW, tmDW2;
+    CUtensorMap tmDA, tmDW2;
     long long rows_dense;
 };
 
@@ -1080,16 +824,7 @@ struct gaz_net {
     int logits_buf; // id of the flat buffer holding the policy logits
     // profiling of the tcgen05 conv launches
     int profile;
-    int conv_v1;           // GAZ_CONV_V1=1: use the v1 per-tap kernel (A/B comparison)
-    int base_offset_mode;  // GAZ_DESC_BASE_OFFSET (default 0, see gaz_conv.cuh)
-    int fuse_se;           // GAZ_FUSE_SE (default 1)
-    int conv_pair;         // GAZ_CONV_PAIR (default 1): cta_group::2 CTA pairs
-    int use_graph;         // GAZ_GRAPH (default 1): replay a captured CUDA graph per search round
-    int stem_tc;           // GAZ_STEM_TC (default 1): Gomoku-shaped stem as an implicit GEMM on tcgen05 (gaz_stem.cuh)
-    int head_mma;          // GAZ_HEAD_MMA (default 1): 32-channel head convolutions on mma.sync instead of CUDA cores
-    int head_f32v;         // GAZ_HEAD_F32V (default 1): head convolutions on the fp32 stream with 8-channel vector loads
-    int fuse_block;        // GAZ_FUSE_BLOCK (default 1): conv1 + conv2 + SE of a residual block in one kernel (gaz_block.cuh)
-    int conv_t;            // GAZ_CONV_T=1 (experimental, default 0): channel-on-lanes kernel (gaz_convt.cuh) for cout >= 64 + its fp32 layout
+    int dbg;               // timing-experiment bits of the convolution kernels; always 0 unless built with -DGAZ_BLOCK_CLK
     std::vector<cudaEvent_t> ev;
     size_t ev_used;
     std::vector<int> ev_op;
@@ -1111,28 +846,12 @@ static int make_map(PFN_encodeTiled enc, CUtensorMap *m, void *ptr, uint64_t inn
     return make_map_ex(enc, m, ptr, inner, rows, 64, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN> static int launch_conv(gaz_net *n, NetOp &op, const ConvArgs &a, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CKN(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM));
-        attr_set = true;
-    }
-    conv_tc_kernel<BN><<<n->n_sm, 192, ConvCfg<BN>::SMEM, s>>>(op.tmA, op.tmB, a);
-    return 0;
-}
-
 template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_conv::BoardConvArgs &a, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        CKN(cudaFuncSetAttribute(gaz_conv::conv_board_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gaz_conv::BoardCfg<BN, false>::SMEM));
         CKN(cudaFuncSetAttribute(gaz_conv::conv_board_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gaz_conv::BoardCfg<BN, true>::SMEM));
         attr_set = true;
-    }
-    if (!n->conv_pair) {
-        gaz_conv::conv_board_kernel<BN, false><<<n->n_sm, 384, gaz_conv::BoardCfg<BN, false>::SMEM, s>>>(op.tmA2, op.tmB, op.tmOa, op.tmOb, a);
-        return 0;
     }
     // CTA pairs: clusters of 2 (one TPC), the leader issues cta_group::2 MMAs for both
     cudaLaunchConfig_t cfg;
@@ -1159,7 +878,7 @@ static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *cou
     auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
     gaz_block::BlockArgs a;
     memset(&a, 0, sizeof a);
-    a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.n_cells = n->H * n->W; a.dbg = n->base_offset_mode;
+    a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.n_cells = n->H * n->W; a.dbg = n->dbg;
     a.nkc1 = c1.d.cin / 64;
     memcpy(a.par1, c1.par, sizeof a.par1);   // conv1 bias | BN2 scale | BN2 shift
     memcpy(a.par2, c2.par, sizeof a.par2);
@@ -1185,16 +904,6 @@ static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *cou
     return 0;
 }
 
-static int launch_conv_t(gaz_net *n, NetOp &op, const gaz_conv::BoardConvArgs &a, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CKN(cudaFuncSetAttribute(gaz_convt::conv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_convt::TCfg::SMEM));
-        attr_set = true;
-    }
-    gaz_convt::conv_t_kernel<<<n->n_sm, 640, gaz_convt::TCfg::SMEM, s>>>(op.tmA2, op.tmWt, op.tmOta, op.tmOtb, a, op.d.cout);
-    return 0;
-}
-
 static const float *wfp(gaz_net *n, int64_t off) { return off < 0 ? nullptr : n->wf + off; }
 
 static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, float *policy, float *value, cudaStream_t s) {
@@ -1207,7 +916,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         case GAZ_OP_STEM: {
             StemArgs a;
             a.count = count; a.max_count = n->max_batch; a.states = states;
-            a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize; a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act; a.layout = n->conv_t;
+            a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize; a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act;
             a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.scale = wfp(n, d.scale_b); a.shift = wfp(n, d.shift_b);
             a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
             a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
@@ -1245,23 +954,13 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             int rc;
             if (op.block_fused) {
                 rc = launch_res_block(n, op, n->ops[oi + 1], count, s);
-            } else if (n->conv_v1) {
-                ConvArgs a;
-                a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
-                a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64;
-                a.bias = wfp(n, d.bias); a.res = (const float *)buf(d.res_buf); a.out_raw = (float *)buf(d.out_raw);
-                a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
-                a.out_b = (__nv_bfloat16 *)buf(d.out_b); a.scale_b = wfp(n, d.scale_b); a.shift_b = wfp(n, d.shift_b);
-                rc = d.cout == 128 ? launch_conv<128>(n, op, a, s) : d.cout == 64 ? launch_conv<64>(n, op, a, s)
-                     : d.cout == 32 ? launch_conv<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
             } else {
                 gaz_conv::BoardConvArgs a;
                 memset(&a, 0, sizeof a);
                 a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
-                a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->base_offset_mode;
+                a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->dbg;
                 const gaz_net_op &o = op.fused_se ? op.se : d; // outputs / residual of the fused SE op
                 memcpy(a.par, op.par, sizeof a.par);
-                a.d_par = op.d_par;
                 a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
                 a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.out_b = (__nv_bfloat16 *)buf(o.out_b);
                 if (op.fused_se) {
@@ -1269,9 +968,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                     a.se_w1 = wfp(n, op.se.w2); a.se_b1 = wfp(n, op.se.bias2); a.se_w2 = wfp(n, op.se.w3); a.se_b2 = wfp(n, op.se.bias3);
                     a.se_b1 = op.d_se_b1; // conv bias folded into the dense1 bias (b1 + W1^T bias)
                 }
-                if (n->conv_t && d.cout >= 64) rc = launch_conv_t(n, op, a, s);
-                else if (n->conv_t && (a.res || a.out_raw)) rc = gaz_fail("conv_tc cout %d with fp32 tensors needs the v3 kernel", d.cout);
-                else rc = d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
+                rc = d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
                      : d.cout == 32 ? launch_conv_board<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
             }
             if (rc != 0) return rc;
@@ -1282,7 +979,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             if (op.skip) break;
             SeArgs a;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.C = d.cout; a.R = d.cin;
-            a.P_pad = n->P_pad; a.Wp = n->Wp; a.layout = n->conv_t;
+            a.P_pad = n->P_pad; a.Wp = n->Wp;
             a.c2 = (const float *)buf(d.in_buf); a.res = (const float *)buf(d.res_buf);
             a.w1 = wfp(n, d.w2); a.b1 = wfp(n, d.bias2); a.w2 = wfp(n, d.w3); a.b2 = wfp(n, d.bias3);
             a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a); a.out_b = (__nv_bfloat16 *)buf(d.out_b);
@@ -1296,7 +993,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             HeadConvArgs a;
             a.w2 = a.bias2 = nullptr; a.out2 = nullptr;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize;
-            a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32; a.layout = n->conv_t;
+            a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32;
             a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
             a.out_act = nullptr; a.act_scale = a.act_shift = nullptr; a.act_ld = 0;
             if (oi + 1 < n->ops.size() && n->ops[oi + 1].dense_tc) {
@@ -1319,16 +1016,10 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
               : (void)(headconv_warp_kernel<CPL_, CO_, K_, false><<<g2, 256, 0, s>>>(a)))
             if (d.cin == 32 && !a.in_f32 && ((d.cout == 8 && d.ksize == 3) || (d.cout == 4 && d.ksize == 1))) {
                 const int halo = (d.ksize / 2) * (n->Wp + 1);
-                const size_t smb = (size_t)(n->P_pad + 2 * halo) * 64;
                 const size_t smm = (size_t)(((n->P_pad + 15) / 16) * 16 + 2 * halo) * 64 + (size_t)d.ksize * d.ksize * 2 * 32 * 16;
-                if (n->head_mma && smm <= 48 * 1024 && (d.cout & 1) == 0 && (((d.cout * n->H * n->W + 7) & ~7) & 1) == 0) {
+                if (smm <= 48 * 1024 && (d.cout & 1) == 0 && (((d.cout * n->H * n->W + 7) & ~7) & 1) == 0) {
                     if (d.ksize == 3) headconv_mma_kernel<3><<<n->n_sm * 8, 128, smm, s>>>(a);
                     else headconv_mma_kernel<1><<<n->n_sm * 8, 128, smm, s>>>(a);
-                    break;
-                }
-                if (smb <= 48 * 1024) {
-                    if (d.cout == 8) headconv_board_kernel<8, 3><<<n->n_sm * 8, 128, smb, s>>>(a);
-                    else headconv_board_kernel<4, 1><<<n->n_sm * 8, 128, smb, s>>>(a);
                     break;
                 }
             }
@@ -1341,7 +1032,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
 #undef HC
             if (done) break;
             if (d.cout > 16 || sm > 48 * 1024) return gaz_fail("headconv shape unsupported (cout %d, %zu B weights)", d.cout, sm);
-            if (a.in_f32 && a.layout == 0 && d.cin % 32 == 0 && n->head_f32v && (d.cout == 4 || d.cout == 8) &&
+            if (a.in_f32 && d.cin % 32 == 0 && (d.cout == 4 || d.cout == 8) &&
                 (d.ksize == 3 || d.ksize == 1) && ((uintptr_t)a.w & 15) == 0) {
                 const int g3 = n->n_sm * 8;
                 if (d.cout == 4 && d.ksize == 3) headconv_f32_kernel<4, 3><<<g3, 128, sm, s>>>(a);
@@ -1367,7 +1058,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                     }
                     a.dense = 1; a.n_off = n0; a.flat_out = outp; a.flat_ld = d.cout; a.flat_n = d.cout;
                     NetOp tmp = op; // maps: activations of this dense op, weights
-                    tmp.tmA2 = op.tmDA; tmp.tmB = op.tmDW; tmp.tmB2 = op.tmDW2;
+                    tmp.tmA2 = op.tmDA; tmp.tmB2 = op.tmDW2;
                     if (launch_conv_board<128>(n, tmp, a, s) != 0) return -1;
                 }
                 break;
@@ -1423,27 +1114,10 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     n->device = desc->device;
     n->rows_alloc = (((long long)n->max_batch * n->P_pad + 255) / 256) * 256;
     n->bytes = 0;
-    {
-        const char *e1 = getenv("GAZ_CONV_V1"), *e2 = getenv("GAZ_DESC_BASE_OFFSET"), *e3 = getenv("GAZ_FUSE_SE");
-        n->conv_v1 = e1 && atoi(e1) != 0;
-        n->base_offset_mode = e2 ? atoi(e2) : 0;
-        n->fuse_se = e3 ? atoi(e3) : 1;
-        const char *e4 = getenv("GAZ_CONV_PAIR");
-        n->conv_pair = e4 ? atoi(e4) : 1;
-        const char *e7 = getenv("GAZ_GRAPH");
-        n->use_graph = e7 ? atoi(e7) : 1;
-        const char *e5 = getenv("GAZ_CONV_T");
-        n->conv_t = e5 ? atoi(e5) : 0;
-        if (n->conv_v1) n->conv_t = 0;
-        const char *e6 = getenv("GAZ_FUSE_BLOCK");
-        n->fuse_block = e6 ? atoi(e6) : 1;
-        const char *e8 = getenv("GAZ_HEAD_MMA");
-        n->head_mma = e8 ? atoi(e8) : 1;
-        const char *e10 = getenv("GAZ_HEAD_F32V");
-        n->head_f32v = e10 ? atoi(e10) : 1;
-        const char *e9 = getenv("GAZ_STEM_TC");
-        n->stem_tc = e9 ? atoi(e9) : 1;
-    }
+    n->dbg = 0;
+#ifdef GAZ_BLOCK_CLK   // instrumented A/B builds only (tools/build_variant.sh): timing-experiment bits of the convolution kernels
+    { const char *e = getenv("GAZ_CONV_DBG"); n->dbg = e ? atoi(e) : 0; }
+#endif
     n->profile = 0;
     n->ev_used = 0;
     n->logits_buf = -1;
@@ -1482,8 +1156,6 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     for (int i = 0; i < desc->n_ops; i++) {
         NetOp op;
         op.d = desc->ops[i];
-        memset(&op.tmA, 0, sizeof op.tmA);
-        memset(&op.tmB, 0, sizeof op.tmB);
         memset(&op.tmA2, 0, sizeof op.tmA2);
         memset(&op.tmB2, 0, sizeof op.tmB2);
         op.fused_se = 0;
@@ -1495,7 +1167,6 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.stem_tc = 0;
         op.d_stem_w = nullptr;
         op.d_stem_par = nullptr;
-        op.d_par = nullptr;
         op.d_se_b1 = nullptr;
         op.dense_tc = 0; op.d_act = nullptr; op.d_wt = nullptr; op.rows_dense = 0;
         memset(&op.se, 0, sizeof op.se);
@@ -1511,8 +1182,6 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
                 return gaz_fail("conv_tc op %d: input buffer must be bf16 rows of width cin", i);
             }
             if (make_map(enc, &op.tmA2, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, gaz_conv::SLAB_BOX_ROWS) != 0 ||
-                make_map(enc, &op.tmA, ib.ptr, (uint64_t)d.cin, (uint64_t)n->rows_alloc, 128) != 0 ||
-                make_map(enc, &op.tmB, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout) != 0 ||
                 make_map(enc, &op.tmB2, n->wh + d.w, (uint64_t)d.ksize * d.ksize * d.cin, (uint64_t)d.cout, (uint32_t)d.cout / 2) != 0) {
                 gaz_net_destroy(n);
                 return -1;
@@ -1520,7 +1189,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         }
         if (d.type == GAZ_OP_POLICY_OUT) n->logits_buf = d.in_buf;
         // fold an SE op into the epilogue of the convolution that feeds it (tile == board geometries only)
-        if (d.type == GAZ_OP_SE && !n->conv_v1 && n->fuse_se && n->P_pad == gaz_conv::TILE_ROWS && !n->ops.empty()) {
+        if (d.type == GAZ_OP_SE && n->P_pad == gaz_conv::TILE_ROWS && !n->ops.empty()) {
             NetOp &prev = n->ops.back();
             if (prev.d.type == GAZ_OP_CONV_TC && prev.d.out_raw == d.in_buf && prev.d.out_a < 0 && prev.d.out_b < 0 &&
                 prev.d.res_buf < 0 && prev.d.cout == d.cout && d.cout == 128 && d.cin <= d.cout) {
@@ -1536,8 +1205,6 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     for (size_t oi = 1; oi < n->ops.size(); oi++) {
         NetOp &op = n->ops[oi];
         const gaz_net_op &d = op.d;
-        const char *etc = getenv("GAZ_DENSE_TC");
-        if (etc && atoi(etc) == 0) break;
         if (d.type != GAZ_OP_DENSE || (d.flags & 3) != 3 || (d.flags & 4) || d.act != GAZ_ACT_NONE) continue;
         const NetOp &pr = n->ops[oi - 1];
         if (pr.d.type != GAZ_OP_HEADCONV || pr.d.out_raw != d.in_buf || pr.d.cin != 32) continue;
@@ -1558,7 +1225,6 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         if (alloc((void **)&op.d_wt, wt.size() * 2) != 0) { gaz_net_destroy(n); return -1; }
         CKN(cudaMemcpy(op.d_wt, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         if (make_map(enc, &op.tmDA, op.d_act, (uint64_t)in_pad, (uint64_t)op.rows_dense, gaz_conv::SLAB_BOX_ROWS) != 0 ||
-            make_map(enc, &op.tmDW, op.d_wt, (uint64_t)in_pad, (uint64_t)d.cout, 128) != 0 ||
             make_map(enc, &op.tmDW2, op.d_wt, (uint64_t)in_pad, (uint64_t)d.cout, 64) != 0) { gaz_net_destroy(n); return -1; }
         for (int c = 0; c < 640; c++) op.par[c] = 0.0f;
         for (int o = 0; o < d.cout && o < 640; o++) op.par[o] = desc->wf[d.bias + o]; // bias of up to 640 outputs
@@ -1569,10 +1235,6 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         const gaz_net_op &o = op.fused_se ? op.se : op.d;
         memset(&op.tmOa, 0, sizeof op.tmOa);
         memset(&op.tmOb, 0, sizeof op.tmOb);
-        memset(&op.tmOta, 0, sizeof op.tmOta);
-        memset(&op.tmOtb, 0, sizeof op.tmOtb);
-        if (make_map(enc, &op.tmWt, n->wh + op.d.w, (uint64_t)op.d.ksize * op.d.ksize * op.d.cin, (uint64_t)op.d.cout,
-                     (uint32_t)(op.d.cout < 128 ? op.d.cout : 128)) != 0) { gaz_net_destroy(n); return -1; }
         for (int k = 0; k < 2; k++) {
             const int id = k == 0 ? o.out_a : o.out_b;
             if (id < 0) continue;
@@ -1580,16 +1242,12 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             if (ob.kind != GAZ_BUF_ROWS_BF16 || ob.width != op.d.cout) { gaz_net_destroy(n); return gaz_fail("conv_tc output buffer must be bf16 rows of width cout"); }
             if (make_map_ex(enc, k == 0 ? &op.tmOa : &op.tmOb, ob.ptr, (uint64_t)ob.width, (uint64_t)n->rows_alloc, 32, 32,
                             CU_TENSOR_MAP_SWIZZLE_64B) != 0) { gaz_net_destroy(n); return -1; }
-            if (make_map_ex(enc, k == 0 ? &op.tmOta : &op.tmOtb, ob.ptr, (uint64_t)ob.width, (uint64_t)n->rows_alloc, 32, 16,
-                            CU_TENSOR_MAP_SWIZZLE_NONE) != 0) { gaz_net_destroy(n); return -1; }
         }
         const int64_t offs[5] = {op.d.bias, o.scale_a, o.shift_a, o.scale_b, o.shift_b};
         const float dflt[5] = {0.0f, 1.0f, 0.0f, 1.0f, 0.0f};
         for (int k = 0; k < 5; k++)
             for (int c = 0; c < 128; c++)
                 op.par[k * 128 + c] = (offs[k] >= 0 && c < op.d.cout) ? desc->wf[offs[k] + c] : dflt[k];
-        if (alloc((void **)&op.d_par, sizeof op.par) != 0) { gaz_net_destroy(n); return -1; }
-        CKN(cudaMemcpy(op.d_par, op.par, sizeof op.par, cudaMemcpyHostToDevice));
         if (op.fused_se) {
             const int R = op.se.cin, Cc = op.d.cout;
             std::vector<float> b1((size_t)R);
@@ -1603,7 +1261,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         }
     }
     // whole-block fusion: conv1 (3x3 C128|C256 -> C128, bf16 out only) directly followed by conv2 (3x3 C128->C128 reading it)
-    if (n->fuse_block && n->conv_pair && !n->conv_t && !n->conv_v1 && n->P_pad == gaz_conv::TILE_ROWS && (n->n_sm & ~1) >= 2) {
+    if (n->P_pad == gaz_conv::TILE_ROWS && (n->n_sm & ~1) >= 2) {
         for (size_t oi = 0; oi + 1 < n->ops.size(); oi++) {
             NetOp &c1 = n->ops[oi], &c2 = n->ops[oi + 1];
             if (c1.d.type != GAZ_OP_CONV_TC || c2.d.type != GAZ_OP_CONV_TC || c1.block_fused || c1.in_block) continue;
@@ -1614,12 +1272,9 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             c2.in_block = 1;
         }
     }
-    // two head convolutions of one shape on one fp32 input -> one launch (headconv_f32_dual_kernel); GAZ_HEAD_DUAL=0 keeps
-    // the two single launches
+    // two head convolutions of one shape on one fp32 input -> one launch (headconv_f32_dual_kernel)
     {
-        const char *ed = getenv("GAZ_HEAD_DUAL");
-        const bool dual_on = (ed ? atoi(ed) : 1) != 0 && n->head_f32v && !n->conv_t;
-        for (size_t i = 0; dual_on && i < n->ops.size(); i++) {
+        for (size_t i = 0; i < n->ops.size(); i++) {
             NetOp &o1 = n->ops[i];
             const gaz_net_op &d1 = o1.d;
             if (d1.type != GAZ_OP_HEADCONV || o1.dual_skip || o1.dual_partner >= 0) continue;
@@ -1648,7 +1303,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     // stem on the tensor cores: 3x3 on 2 planes -> 256 filters, tile == board, bf16 outputs only
     for (auto &op : n->ops) {
         const gaz_net_op &d = op.d;
-        if (d.type != GAZ_OP_STEM || !n->stem_tc || n->conv_t || n->conv_v1) continue;
+        if (d.type != GAZ_OP_STEM) continue;
         if (d.ksize != 3 || d.cin != 2 || d.cout != 256 || n->P_pad != 256 || n->H > 16 || n->W > 16 || d.out_raw >= 0) continue;
         if (d.act != GAZ_ACT_NONE && d.act != GAZ_ACT_RELU) continue;
         if (d.out_a < 0 && d.out_b < 0) continue;
@@ -1697,7 +1352,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    for (auto &op : n->ops) { if (op.d_par) cudaFree(op.d_par); if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); }
+    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
@@ -1766,7 +1421,7 @@ static int one_round_eager(gaz_engine *e) {
 // the number of forward chunks or the attached network changes.  Disabled while conv launches are being event-timed.
 static int run_rounds(gaz_engine *e, int n_rounds) {
     gaz_net *n = e->net;
-    const bool use_graph = n->use_graph && !n->profile;
+    const bool use_graph = !n->profile;   // per-launch event timers need eager launches
     for (int r = 0; r < n_rounds; r++) {
         if (!use_graph) { if (one_round_eager(e) != 0) return -1; continue; }
         const int bound = e->leaf_bound > 0 ? e->leaf_bound : e->v.n_trees;

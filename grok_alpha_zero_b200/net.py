@@ -250,10 +250,8 @@ class Net:
         # (type, cin, cout, ksize, tag): tag "se" = convolution whose epilogue carries the following SE op; "block" = conv1
         # that runs the whole residual block (conv1 + conv2 + SE + skip, gaz_block.cuh) and "inblock" = the conv2 it absorbed.
         # Mirrors the fusion rules of gaz_net_create (csrc/gaz_net.cu).
-        import os
         tile_is_board = (spec["H"] + 1) * (spec["W"] + 1) == 256
-        fuse_block = os.environ.get("GAZ_FUSE_BLOCK", "1") != "0" and os.environ.get("GAZ_CONV_PAIR", "1") != "0" and \
-            os.environ.get("GAZ_CONV_T", "0") == "0" and os.environ.get("GAZ_CONV_V1", "0") == "0"
+        fuse_block = True
         self._op_shapes = []
         for i, o in enumerate(b.ops):
             tag = ""

@@ -133,48 +133,19 @@ def test_closed_loop_search_with_cuda_net_is_bit_exact(game, over, iters):
     net.close()
 
 
-@pytest.mark.parametrize("env", [{"GAZ_CONV_T": "1"}, {"GAZ_CONV_PAIR": "0"}, {"GAZ_FUSE_BLOCK": "0"}, {"GAZ_HEAD_MMA": "0"},
-                                 {"GAZ_STEM_TC": "0"}, {"GAZ_HEAD_F32V": "0"}, {"GAZ_HEAD_DUAL": "0"}],
-                         ids=["transposed-v3", "single-cta", "unfused-blocks", "cuda-core-head-conv", "cuda-core-stem",
-                              "scalar-fp32-head-conv", "single-head-conv-launches"])
-def test_alternative_conv_kernels_stay_within_tolerance(env, monkeypatch):
-    """the experimental channel-on-lanes kernel (gaz_convt.cuh) and the single-CTA form of the board kernel are
-    selected by environment switches read at network creation; both must meet the same tolerance"""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    test_net_matches_fp32_oracle("gomoku", "softmax", dict(num_blocks=2, use_se=True), 9)
-    test_net_matches_fp32_oracle("connect4", "softmax", {}, 70)
-
-
-def test_dual_head_convolution_is_bit_identical_to_two_launches(monkeypatch):
-    """Connect4: the policy and value heads' 3x3 C128->C8 convolutions of the trunk output run as ONE launch
-    (headconv_f32_dual_kernel); GAZ_HEAD_DUAL=0 keeps the two single launches.  Same per-output term order => same bits."""
-    spec = netspec.build_spec("connect4", "softmax")
-    W = netspec.init_weights(spec, seed=1)
-    st = net_util.random_states("connect4", 333, seed=4)
-    outs = []
-    for flag in ("1", "0"):
-        monkeypatch.setenv("GAZ_HEAD_DUAL", flag)
-        net = Net(spec, W, max_batch=512)
-        pol, val, lg = net.forward(st, want_logits=True)
-        outs.append((pol.copy(), val.copy(), lg.copy(), net.n_launches))
-        net.close()
-    assert outs[0][3] == outs[1][3] - 1
-    for a, b in zip(outs[0][:3], outs[1][:3]):
-        np.testing.assert_array_equal(a, b)
-
-
-def test_setters_take_effect_after_the_round_graph_was_captured(monkeypatch):
+def test_setters_take_effect_after_the_round_graph_was_captured():
     """Kernels take the engine's View by value, so a captured round graph bakes in c_puct / Dirichlet / Gumbel parameters
     (ADVICE r1): a setter called after the first `rounds_net` must invalidate the graph.  Run A replays graphs and switches
-    the Dirichlet noise on and c_puct_init up mid-search; run B does the same with graphs disabled (GAZ_GRAPH=0, eager
-    launches read the live View); run C never calls the setters.  A must equal B bit for bit and differ from C."""
+    the Dirichlet noise on and c_puct_init up mid-search; run B does the same with eager launches (the per-launch event
+    timers of `Net.profile` switch graph replay off; eager launches read the live View); run C never calls the setters.
+    A must equal B bit for bit and differ from C."""
     spec = netspec.build_spec("connect4", "softmax", num_blocks=2)
     W = netspec.init_weights(spec, seed=2)
 
     def run(graph, switch):
-        monkeypatch.setenv("GAZ_GRAPH", "1" if graph else "0")
         net = Net(spec, W, max_batch=16)
+        if not graph:
+            net.profile(4096)
         eng = Engine("connect4", n_games=8, mode="puct", trees_per_game=1, c_puct_init=2.5, iters_hint=200)
         net.attach(eng)
         if eng.new_roots() > 0:
