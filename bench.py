@@ -54,6 +54,15 @@ CONFIGS = {
 }
 
 
+def kernel_sha16():
+    """hash of the tcgen05 kernel sources: ties profiles/conv_traffic.json (an ncu capture) to the code it was taken on"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("gaz_tc.cuh", "gaz_conv.cuh", "gaz_block.cuh"):
+        h.update(open(os.path.join(ROOT, "grok_alpha_zero_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -297,13 +306,15 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
     launches = groups[key][1] * passes
     avg_ms = groups[key][0] / max(1.0, launches)
     flops, bytes_alg = work(cin, cout, k, tag)
+    # DRAM bytes per launch come from an `ncu --set full` capture (bench.py cannot read DRAM counters itself); the record is
+    # used only if it was taken on THESE kernel sources (hash of the tcgen05 headers) at this batch size, else null
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tp):
         try:
             tkey = "block_3x3_C%d_C%d" % (cin, cout) if tag.startswith("block") else "%dx%d_C%d_C%d%s" % (k, k, cin, cout, "_se" if tag else "")
             t = json.load(open(tp)).get(tkey)
-            if t and t.get("leaves") == int(round(leaves_per_launch)):
+            if t and t.get("leaves") == int(round(leaves_per_launch)) and t.get("kernel_sha16") == kernel_sha16():
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
@@ -419,6 +430,8 @@ def main():
                     help="time M WHOLE moves per game from the start position (search, move choice, do_action, prune_tree / "
                          "re-rooting of both trees) instead of K rounds: positions/s measured directly")
     ap.add_argument("--no-noise", action="store_true", help="searches without Dirichlet / Gumbel exploration noise")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records of the default run (the other BASELINE configurations at N=1, the real generation at N>1)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.impl == "reference":
@@ -436,8 +449,91 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_games = args.games or cfg["games"]
     peaks = load_peaks()
+    line = measure(args, cfg, world, rank, local, peaks, want_cpu=(world == 1 and not args.no_cpu_baseline), full=True)
+    if args.moves > 0:
+        return
+    if args.config == "gomoku" and not args.no_extras:
+        if world == 1:      # the other BASELINE configurations, short runs, same measurement (driver-visible in the one JSON line)
+            subs = {}
+            for name in ("connect4", "gumbel", "tictactoe"):
+                a2 = argparse.Namespace(**vars(args))
+                a2.steps, a2.warmup, a2.games, a2.presearch, a2.config = 20, 3, 0, -1, name
+                sub = measure(a2, dict(CONFIGS[name]), world, rank, local, peaks, want_cpu=False, full=False)
+                subs[name] = dict(workload=sub["config"]["workload"], value=sub["value"], unit=sub["unit"], ms_per_step=sub["ms_per_step"],
+                                  steps=sub["steps"], e2e=sub["e2e"]["value"], positions_per_s=sub["positions_per_s"],
+                                  whole_move=sub["whole_move"], sims_per_eval=sub["sims_per_eval"], net_tflops=sub["net_tflops"],
+                                  net_frac_of_sustained_peak=sub["net_tflops"] / peaks["sustained"],
+                                  roofline=dict((k, sub["roofline"][k]) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel")) if sub["roofline"] else None,
+                                  clocks=sub["clocks"], gpu_launches=sub["gpu_launches"])
+            if rank == 0:
+                line["configs"] = subs
+        else:               # multi-GPU: a short REAL generation with the NCCL trajectory gather and the writer inside the wall clock
+            gen = generation_record(world, rank, local)
+            if rank == 0:
+                line["e2e_generation"] = gen
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def generation_record(world, rank, local):
+    """BASELINE configs[4] in miniature: every rank plays its shard of one generation through the public `run_self_play`
+    (Gumbel MCTS n=64 m=16 StableMax on the 10x128+SE network, games cut off after 6 plies so the record stays short), the
+    finished trajectories are gathered to rank 0 over NCCL and written with the reference schema by the streaming writer."""
+    import shutil
+    import tempfile
+    import time
+    import torch
+    import torch.distributed as dist
+    from grok_alpha_zero_b200 import games as G
+    from grok_alpha_zero_b200.Self_Play import run_self_play
+    per_gpu, plies = 4096, 6
+    bc = dict(num_resnet_layers=10, num_filters=128, use_stablemax=True, use_se=True)
+    tc = dict(MCTS_iteration_limit=64, use_gumbel=True, m=16, c_visit=50.0, c_scale=1.0, max_actions=plies,
+              games_per_generation=per_gpu * world, games_per_gpu=per_gpu, num_explore_actions_first=0, num_explore_actions_second=0,
+              opening_actions=[[[7, 7], 0.333]])
+    folder = tempfile.mkdtemp(prefix="gaz_gen_") if rank == 0 else "/tmp/gaz_gen_unused_%d" % rank
+    tm = {}
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    run_self_play(G.Gomoku, (bc, tc, {}), folder, seed=7, timings=tm)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    v = torch.tensor([tm["play_s"], tm["gather_collective_s"], float(tm["gather_bytes"]), float(tm["moves"]), float(tm["sims"])],
+                     dtype=torch.float64, device="cuda")
+    mx = v.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    rec = None
+    if rank == 0:
+        size = 0
+        for f in os.listdir(folder):
+            size += os.path.getsize(os.path.join(folder, f))
+        shutil.rmtree(folder, ignore_errors=True)
+        positions = float(v[3].item())
+        rec = dict(what="run_self_play: Gomoku Gumbel n=64 m=16 StableMax, 10x128+SE bf16, %d games/GPU x %d GPUs, games cut off after "
+                        "%d plies; NCCL trajectory gather (all_gather of sizes + padded gather to rank 0) and the streaming replay "
+                        "writer (8-fold augmentation through gaz_augment on rank 0's GPU) inside the wall clock" % (per_gpu, world, plies),
+                   games=per_gpu * world, positions=int(positions), wall_s=wall, positions_per_s=positions / wall,
+                   play_s_max=float(mx[0].item()), positions_per_s_search_only=positions / float(mx[0].item()),
+                   gather_collective="torch.distributed all_gather + gather (NCCL)", gather_collective_ms=float(mx[1].item()) * 1e3,
+                   gather_bytes_total=int(v[2].item()), gather_GBps=float(v[2].item()) / max(float(mx[1].item()), 1e-9) / 1e9,
+                   write_s=tm["write_s"], replay_file_bytes=size, datasets_written=int(positions) // plies * 8 * 3,
+                   sims=int(v[4].item()))
+    return rec
+
+
+def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
+    """one configuration: K timed search rounds (device events), the e2e passes through host buffers, one whole timed move
+    (positions/s measured, not derived); returns the JSON line as a dict on every rank (collective reductions inside)"""
+    import torch
+    import torch.distributed as dist
+    n_games = args.games or cfg["games"]
 
     sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise)
     sb.start()
@@ -488,7 +584,8 @@ def main():
         return sb.eng.timer_end(), rounds
 
     if args.moves > 0:
-        return run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games)
+        run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games)
+        return None
 
     # ---- warm-up + timed region -------------------------------------------------------------------
     timed_rounds(args.warmup)
@@ -510,6 +607,27 @@ def main():
     status = sb.eng.status()
     if status != 0:
         raise SystemExit("engine status %d (1 node overflow, 2 slot overflow, 4 LUT miss, 8 bad state)" % status)
+
+    # ---- one WHOLE move of every game, timed: fresh start position, the full run (forced root expansions included), root
+    # statistics, the tau = 0 move, do_action / check_win, prune_tree of both trees, the next run's begin
+    sb.alive[:] = True
+    sb.next_player[:] = -1
+    sb.start()
+    m0 = sb.moves
+    barrier()
+    wm_ms, wm_rounds = timed_moves(1)
+    barrier()
+    wm = torch.tensor([float(sb.moves - m0)], dtype=torch.float64, device="cuda")
+    wmt = torch.tensor([wm_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(wm, op=dist.ReduceOp.SUM)
+        dist.all_reduce(wmt, op=dist.ReduceOp.MAX)
+    whole_move = dict(moves=int(wm.item()), ms=float(wmt.item()), rounds=int(wm_rounds),
+                      what="one whole move of every game from the start position: search run + root statistics + move choice "
+                           "+ do_action/check_win + prune_tree (both trees) + next run begin; device events, max over ranks")
+    positions_per_s = float(wm.item()) / (float(wmt.item()) * 1e-3)
+    if sb.eng.status() != 0:
+        raise SystemExit("engine status %d after the whole-move measurement" % sb.eng.status())
 
     # ---- e2e: host boards in, root statistics out ---------------------------------------------------------
     H, Wd = sb.eng.H, sb.eng.W
@@ -574,7 +692,7 @@ def main():
                                 noise=("none" if not sb.noise else "Gumbel(0,1) on the root logits (host draw, uploaded per move)"
                                        if sb.gumbel else "Dirichlet(alpha=%g, eps=0.25) at every expansion, device Philox "
                                        "streams keyed by global game id (Self_Play.py:38-46)" % cfg["alpha"])),
-                    positions_per_s=value / cfg["limit"],
+                    positions_per_s=positions_per_s, whole_move=whole_move,
                     nn_evals_per_s=evals_all / (ms_all * 1e-3), sims_per_eval=sims_all / max(1.0, evals_all),
                     net_tflops=evals_all * sb.flops_per_eval / (ms_all * 1e-3) / 1e12,
                     e2e=dict(value=e2e_value, unit="sims/s", h2d_bytes_per_step=int(h2d / args.steps),
@@ -583,7 +701,7 @@ def main():
                                   "gaz_root_dense -> host visit counts/value sums/moves; wall clock incl. copies" % args.steps),
                     gpu_launches=int(l1 - l0), clocks=clocks, roofline=roof,
                     hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()))
-        if world == 1 and not args.no_cpu_baseline:
+        if want_cpu:
             try:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import cpu_selfplay
@@ -601,10 +719,12 @@ def main():
             except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = dict(value=None, unit="sims/s", cores=os.cpu_count(), kind="port",
                                             sample="failed: %r" % (ex,))
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    sb.eng.close()
+    sb.net.close()
+    del sb
+    torch.cuda.empty_cache()
+    return line if rank == 0 else dict(config={}, e2e={}, roofline=None, value=0, unit="", ms_per_step=0, steps=0, positions_per_s=0,
+                                       whole_move=None, sims_per_eval=0, net_tflops=0, clocks=None, gpu_launches=0)
 
 
 if __name__ == "__main__":

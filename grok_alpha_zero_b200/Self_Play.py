@@ -37,7 +37,13 @@ class ReplayWriter:
     """`Self_Play_Data` with the reference schema (Self_Play.py:178-208): `game_stats` uint32[6] =
     [max game length, total positions, games, wins(-1), draws, wins(+1)] and per game and augmentation
     `boards_k` (T,H,W,C), `policies_k` (T,P) f32, `values_k` (T,1) f32.  HDF5 when h5py is importable, else
-    `Self_Play_Data.npz` holding the same names."""
+    `Self_Play_Data.npz` holding the same names.
+
+    STREAMING: every game goes to the file when `add_game` is called (an .npz is a zip archive of .npy members, opened in
+    append mode and written uncompressed), so the writer holds only `game_stats` and the dataset counter in memory - a
+    generation of 131072 Gomoku games x 8 augmentations is ~50 GB of datasets.  `game_stats` is written by `flush()`;
+    re-opening a finished archive to append more games (the resume rule of Self_Play.py:267-272) first copies its members,
+    minus `game_stats`, into a fresh archive, because zip members cannot be replaced in place."""
 
     def __init__(self, folder_path):
         self.folder = folder_path
@@ -45,12 +51,30 @@ class ReplayWriter:
         self.h5_path = os.path.join(folder_path, "Self_Play_Data.h5")
         self.npz_path = os.path.join(folder_path, "Self_Play_Data.npz")
         self.use_h5 = _h5 is not None
-        self.data = {}
+        self.stats = np.zeros(6, dtype=np.uint32)
+        self.n_datasets = 0          # (len(file.keys()) - 1) // 3 of the reference
+        self._zip = None
+        self.keys = ["game_stats"]   # creation order (what `file.keys()` lists in the reference's numbering rule)
         if not self.use_h5 and os.path.exists(self.npz_path):
             with np.load(self.npz_path) as z:
-                self.data = {k: z[k] for k in z.files}
-        if not self.use_h5 and "game_stats" not in self.data:
-            self.data["game_stats"] = np.zeros(6, dtype=np.uint32)
+                self.stats = np.asarray(z["game_stats"], dtype=np.uint32).copy()
+                names = [k for k in z.files if k != "game_stats"]
+            self.n_datasets = len(names) // 3
+            self.keys += names
+
+    @property
+    def data(self):
+        """the archive's content as a dict (tests, small files): game_stats + every dataset, in creation order"""
+        if self.use_h5:
+            with _h5.File(self.h5_path, "r") as f:
+                return {k: np.asarray(f[k]) for k in f.keys()}
+        out = {"game_stats": self.stats.copy()}
+        self._close_zip()
+        if os.path.exists(self.npz_path):
+            with np.load(self.npz_path) as z:
+                for k in self.keys[1:]:
+                    out[k] = z[k]
+        return out
 
     def games_done(self):
         if self.use_h5:
@@ -59,7 +83,33 @@ class ReplayWriter:
                     return int(f["game_stats"][2]) if "game_stats" in f else 0
             except OSError:         # no file yet (h5py raises FileNotFoundError, an OSError)
                 return 0
-        return int(self.data["game_stats"][2])
+        return int(self.stats[2])
+
+    def _open_zip(self):
+        import zipfile
+        if self._zip is not None:
+            return self._zip
+        if os.path.exists(self.npz_path):      # resume: carry the datasets over, drop the stale game_stats member
+            tmp = self.npz_path + ".tmp"
+            with zipfile.ZipFile(self.npz_path, "r") as src, zipfile.ZipFile(tmp, "w", zipfile.ZIP_STORED, allowZip64=True) as dst:
+                for info in src.infolist():
+                    if info.filename != "game_stats.npy":
+                        with src.open(info) as fi, dst.open(info.filename, "w", force_zip64=True) as fo:
+                            while True:
+                                blk = fi.read(1 << 24)
+                                if not blk:
+                                    break
+                                fo.write(blk)
+            os.replace(tmp, self.npz_path)
+            self._zip = zipfile.ZipFile(self.npz_path, "a", zipfile.ZIP_STORED, allowZip64=True)
+        else:
+            self._zip = zipfile.ZipFile(self.npz_path, "w", zipfile.ZIP_STORED, allowZip64=True)
+        return self._zip
+
+    def _close_zip(self):
+        if self._zip is not None:
+            self._zip.close()
+            self._zip = None
 
     def add_game(self, boards_aug, policies_aug, values_aug, game_length, winner):
         """boards_aug (A,T,H,W,C), policies_aug (A,T,P), values_aug (A,T,1)"""
@@ -67,48 +117,133 @@ class ReplayWriter:
             with _h5.File(self.h5_path, "a") as f:
                 if "game_stats" not in f:
                     f.create_dataset("game_stats", data=np.zeros(6, dtype=np.uint32))
-                self._add(f, boards_aug, policies_aug, values_aug, game_length, winner, h5=True)
-        else:
-            self._add(self.data, boards_aug, policies_aug, values_aug, game_length, winner, h5=False)
+                st = f["game_stats"]
+                self._bump(st, boards_aug.shape[1], game_length, winner)
+                k0 = (len(f.keys()) - 1) // 3
+                for inc in range(policies_aug.shape[0]):
+                    for name, arr, dt in self._triple(boards_aug, policies_aug, values_aug, inc):
+                        f.create_dataset("%s_%d" % (name, k0 + inc), maxshape=(None, *arr.shape[1:]), dtype=dt, data=arr, chunks=None)
+            return
+        zf = self._open_zip()
+        self._bump(self.stats, boards_aug.shape[1], game_length, winner)
+        k0 = self.n_datasets
+        for inc in range(policies_aug.shape[0]):
+            for name, arr, dt in self._triple(boards_aug, policies_aug, values_aug, inc):
+                key = "%s_%d" % (name, k0 + inc)
+                with zf.open(key + ".npy", "w", force_zip64=True) as fo:
+                    np.lib.format.write_array(fo, np.ascontiguousarray(arr, dtype=dt), allow_pickle=False)
+                self.keys.append(key)
+        self.n_datasets += policies_aug.shape[0]
 
     @staticmethod
-    def _add(f, boards_aug, policies_aug, values_aug, game_length, winner, h5):
-        st = f["game_stats"]
+    def _triple(boards_aug, policies_aug, values_aug, inc):
+        return (("boards", boards_aug[inc], boards_aug.dtype), ("policies", policies_aug[inc], np.float32),
+                ("values", values_aug[inc], np.float32))
+
+    @staticmethod
+    def _bump(st, n_positions, game_length, winner):
         if st[0] < game_length:
             st[0] = game_length
-        st[1] += boards_aug.shape[1]
+        st[1] += n_positions
         st[2] += 1
         st[winner + 4] += 1
-        k0 = (len(f.keys()) - 1) // 3
-        for inc in range(policies_aug.shape[0]):
-            for name, arr, dt in (("boards", boards_aug[inc], boards_aug.dtype), ("policies", policies_aug[inc], np.float32),
-                                  ("values", values_aug[inc], np.float32)):
-                key = "%s_%d" % (name, k0 + inc)
-                if h5:
-                    f.create_dataset(key, maxshape=(None, *arr.shape[1:]), dtype=dt, data=arr, chunks=None)
-                else:
-                    f[key] = np.ascontiguousarray(arr, dtype=dt)
 
     def flush(self):
-        if not self.use_h5:
-            np.savez(self.npz_path, **self.data)
+        """finish the archive: `game_stats` is its last member; the writer can be re-opened to append later"""
+        if self.use_h5:
+            return
+        zf = self._open_zip()
+        with zf.open("game_stats.npy", "w") as fo:
+            np.lib.format.write_array(fo, self.stats, allow_pickle=False)
+        self._close_zip()
 
 
-def finalize_game(game_obj, states, policies, q, z, winner):
-    """Self_Play.py:159-176: z sign / draw rules, value = 0.5 * (z + q), the game's own augmentation."""
-    states = np.asarray(states, dtype=game_obj.board.dtype)
-    policies = np.asarray(policies, dtype=np.float32)
+def game_values(q, z, winner):
+    """Self_Play.py:159-172: z sign / draw rules, value = 0.5 * (z + q) -> (T, 1) float32"""
     q = np.asarray(q, dtype=np.float32).reshape((-1, 1))
     z = np.asarray(z, dtype=np.float32).reshape((-1, 1)).copy()
     if winner == z[-1][0] == -1:
         z *= -1.0
     elif winner == 0:
         z[:] = 0.0
-    values = 0.5 * (z + q)
+    return 0.5 * (z + q)
+
+
+def finalize_game(game_obj, states, policies, q, z, winner):
+    """Self_Play.py:159-176 for one game on the host: targets + the game's own `augment_sample`."""
+    states = np.asarray(states, dtype=game_obj.board.dtype)
+    policies = np.asarray(policies, dtype=np.float32)
+    values = game_values(q, z, winner)
     b_aug, p_aug = game_obj.augment_sample(states, policies)
     b_aug, p_aug = np.asarray(b_aug), np.asarray(p_aug)
     v_aug = np.repeat(np.expand_dims(values, 0), repeats=p_aug.shape[0], axis=0)
     return b_aug, p_aug, v_aug
+
+
+def augmentation_tables(game_obj):
+    """The game's `augment_sample` (Gomoku.py:264-303, Connect4.py:427-445, Tictactoe.py:322-358) as gather tables for
+    `gaz_augment`: out[a][t][j] = in[t][perm[a][j]].  Derived by probing the game's OWN method with one-hot inputs, so a
+    game plugin whose augmentation is a pure re-ordering needs no second implementation.  Returns (perm_state (A, S) int32,
+    perm_policy (A, P) int32) or None when the method is not a permutation (the host path is used then)."""
+    st0 = np.asarray(game_obj.get_input_state())
+    S, P = int(st0.size), int(game_obj.policy_shape[0])
+    T = max(S, P)
+    states = np.zeros((T, S), dtype=game_obj.board.dtype)
+    states[np.arange(S), np.arange(S)] = 1
+    pols = np.zeros((T, P), dtype=np.float32)
+    pols[np.arange(P), np.arange(P)] = 1.0
+    b, p = game_obj.augment_sample(states.reshape((T,) + st0.shape), pols)
+    b, p = np.asarray(b).reshape(-1, T, S), np.asarray(p).reshape(-1, T, P)
+    A = b.shape[0]
+    if p.shape[0] != A or np.any((b != 0).sum(1)[:, :] != 1) or np.any((p != 0).sum(1) != 1):
+        return None
+    perm_s = np.argmax(b != 0, axis=1).astype(np.int32)       # (A, S): which one-hot row lit output position j
+    perm_p = np.argmax(p != 0, axis=1).astype(np.int32)
+    if perm_s.max() >= S or perm_p.max() >= P:
+        return None
+    return perm_s, perm_p
+
+
+def finalize_games(game_obj, games, device=0, lib=None, tables=None, chunk_positions=1 << 16):
+    """Self_Play.py:159-176 for a LIST of finished games: targets on the host (a few flops per position), the 8-fold / 2-fold
+    augmentation of every position as one table-driven gather per chunk on the device (`gaz_augment`).  Yields
+    (game, boards_aug (A,T,H,W,C), policies_aug (A,T,P), values_aug (A,T,1)) in order - a generator, so a streaming writer
+    never holds more than one chunk."""
+    import ctypes as C
+    from . import _lib
+    lib = lib if lib is not None else _lib.load()
+    tables = tables if tables is not None else augmentation_tables(game_obj)
+    st_shape = np.asarray(game_obj.get_input_state()).shape
+    bdt = game_obj.board.dtype
+    if tables is None or bdt != np.int8:
+        for g in games:      # a game whose augmentation is not a re-ordering (or whose boards are not int8): host path
+            yield (g,) + finalize_game(game_obj, g["states"], g["policies"], g["q"], g["z"], g["winner"])
+        return
+    perm_s, perm_p = tables
+    A, S, P = perm_s.shape[0], perm_s.shape[1], perm_p.shape[1]
+    i = 0
+    while i < len(games):
+        j, npos = i, 0
+        while j < len(games) and (j == i or npos + games[j]["length"] <= chunk_positions):
+            npos += games[j]["length"]
+            j += 1
+        st = np.ascontiguousarray(np.concatenate([np.asarray(g["states"], dtype=np.int8).reshape(g["length"], S) for g in games[i:j]]))
+        po = np.ascontiguousarray(np.concatenate([np.asarray(g["policies"], dtype=np.float32).reshape(g["length"], P) for g in games[i:j]]))
+        so = np.empty((A, npos, S), np.int8)
+        pout = np.empty((A, npos, P), np.float32)
+        rc = lib.gaz_augment(int(device), st.ctypes.data_as(C.c_void_p), po.ctypes.data_as(C.c_void_p), npos, S, P,
+                             perm_s.ctypes.data_as(C.c_void_p), perm_p.ctypes.data_as(C.c_void_p), A,
+                             so.ctypes.data_as(C.c_void_p), pout.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            raise RuntimeError(lib.gaz_last_error().decode())
+        off = 0
+        for g in games[i:j]:
+            T = g["length"]
+            values = game_values(g["q"], g["z"], g["winner"])
+            yield (g, so[:, off:off + T].reshape((A, T) + st_shape), pout[:, off:off + T],
+                   np.repeat(np.expand_dims(values, 0), repeats=A, axis=0))
+            off += T
+        i = j
 
 
 # ---------------------------------------------------------------------------------------- the batched driver --
@@ -371,16 +506,20 @@ def unpack_games(buf):
     return out
 
 
-def gather_games(finished, device=None):
+def gather_games(finished, device=None, stats=None):
     """All ranks -> rank 0: lengths by all_gather, then one padded byte buffer per rank by gather (NCCL over NVLink when
     the process group is NCCL and `device` is a CUDA device, gloo on CPU).  Returns the merged list on rank 0, [] elsewhere."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return sorted(finished, key=lambda g: g["game_id"])
+    import time
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cpu") if device is None else torch.device(device)
     buf = torch.from_numpy(pack_games(finished).copy()).to(dev)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
     size = torch.tensor([buf.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, size)
@@ -389,6 +528,10 @@ def gather_games(finished, device=None):
     padded[:buf.numel()] = buf
     outs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
     dist.gather(padded, gather_list=outs, dst=0)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    if stats is not None:    # the collective alone (all_gather of sizes + padded gather), and the payload this rank sent
+        stats.update(collective_s=time.perf_counter() - t0, bytes=int(buf.numel()), padded_bytes=mx)
     if rank != 0:
         return []
     merged = []
@@ -415,32 +558,45 @@ def net_spec_from_configs(game_name, build_config, train_config):
     return netspec.build_spec(game_name, head, **over)
 
 
-def run_self_play(game_class, configs, folder_path, per_process_wait_time=1e-3, weights=None, seed=0, evaluator="net",
-                  lib=None):
+def run_self_play(game_class, configs, folder_path, per_process_wait_time=1e-3, weights=None, seed=None, evaluator="net",
+                  lib=None, timings=None):
     """Same call as the reference's `run_self_play(game_class, configs, folder_path, per_process_wait_time)`; plays
     `games_per_generation - game_stats[2]` games (resume rule of Self_Play.py:267-272) on this rank's share of the
     game ids and appends them to `folder_path/Self_Play_Data` on rank 0.  Extra keys read from train_config:
     `games_per_gpu` (concurrent games per GPU, default 4096).  `weights`: Keras-layout dict or a checkpoint path
-    (default `folder_path/model.npz`, else random init - generation 0 of the reference plays with a random policy)."""
+    (default `folder_path/model.npz`, else random init).  `seed`: None draws one from the OS on rank 0 (the reference
+    reseeds every worker from entropy, Self_Play.py:221) and broadcasts it; an explicit seed makes a run reproducible.
+    `evaluator`: "net" (CUDA network), "hash" (deterministic parity evaluator) or "random" - a uniform-random policy /
+    value per position, what the reference plays generation 0 with (session=None, MCTS.py:236-240).
+    `timings`: optional dict that receives wall-clock seconds per phase and the bytes gathered."""
+    import time
     build_config, train_config = configs[0], configs[1]
     rank, world, device = 0, 1, 0
+    dist = None
     try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
+        import torch.distributed as dist_mod
+        if dist_mod.is_available() and dist_mod.is_initialized():
+            dist = dist_mod
             rank, world = dist.get_rank(), dist.get_world_size()
             device = int(os.environ.get("LOCAL_RANK", rank))
     except Exception:  # noqa: BLE001
-        pass
-    writer = ReplayWriter(folder_path) if rank == 0 else None
-    done = writer.games_done() if rank == 0 else 0
-    if world > 1:
+        dist = None
+
+    def bcast_int(v):
+        if world == 1:
+            return int(v)
         import torch
-        import torch.distributed as dist
-        t = torch.tensor([done], dtype=torch.int64)
+        t = torch.tensor([int(v)], dtype=torch.int64)
         if dist.get_backend() == "nccl":
             t = t.cuda(device)
         dist.broadcast(t, src=0)
-        done = int(t.item())
+        return int(t.item())
+
+    writer = ReplayWriter(folder_path) if rank == 0 else None
+    done = bcast_int(writer.games_done() if rank == 0 else 0)
+    if seed is None:
+        seed = int.from_bytes(os.urandom(4), "little") if rank == 0 else 0
+    seed = bcast_int(seed)
     games_left = int(train_config["games_per_generation"]) - done
     if games_left <= 0:
         print(f"Finished generating {train_config['games_per_generation']} games!")
@@ -455,22 +611,30 @@ def run_self_play(game_class, configs, folder_path, per_process_wait_time=1e-3, 
         else:
             spec = net_spec_from_configs(name, build_config, train_config)
             w = weights if weights is not None else netspec.init_weights(spec, seed=seed)
+    t0 = time.perf_counter()
     sp = BatchedSelfPlay(game_class, build_config, train_config, ids, int(train_config.get("games_per_gpu", 4096)),
-                         device=device, evaluator=evaluator, spec=spec, weights=w, seed=seed, lib=lib)
+                         device=device, evaluator="hash" if evaluator == "random" else evaluator, spec=spec, weights=w, seed=seed,
+                         lib=lib, hash_salt=seed if evaluator == "random" else 0)
     finished = sp.play()
     if sp.pool_rebuilds:
         print("run_self_play: %d tree(s) restarted from a fresh root because their pool could not hold another move "
               "(raise node_cap / slot_cap to keep the sub-tree reuse)" % sp.pool_rebuilds)
+    sims, moves = sp.sims, sp.moves
     sp.close()
+    t1 = time.perf_counter()
     dev = None
     if world > 1:
-        import torch.distributed as dist
         dev = ("cuda:%d" % device) if dist.get_backend() == "nccl" else None
-    merged = gather_games(finished, device=dev)
+    stats = {}
+    merged = gather_games(finished, device=dev, stats=stats)
+    t2 = time.perf_counter()
     if rank == 0:
         proto = game_class()
-        for g in merged:
-            b, p, v = finalize_game(proto, g["states"], g["policies"], g["q"], g["z"], g["winner"])
+        for g, b, p, v in finalize_games(proto, merged, device=device, lib=lib):
             writer.add_game(b, p, v, g["length"], g["winner"])
         writer.flush()
+    t3 = time.perf_counter()
+    if timings is not None:
+        timings.update(play_s=t1 - t0, gather_s=t2 - t1, write_s=t3 - t2, sims=int(sims), moves=int(moves), seed=int(seed),
+                       gather_bytes=int(stats.get("bytes", 0)), gather_collective_s=float(stats.get("collective_s", 0.0)))
     return merged

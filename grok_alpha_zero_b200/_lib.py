@@ -56,6 +56,7 @@ SYMBOLS = {
     "gaz_status": (C.c_int, [_P]),
     "gaz_tree_sizes": (C.c_int, [_P, _P]),
     "gaz_bytes_allocated": (C.c_int64, [_P]),
+    "gaz_augment": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
 }
 
 

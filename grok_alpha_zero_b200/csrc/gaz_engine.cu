@@ -270,6 +270,28 @@ __global__ void __launch_bounds__(THREADS) k_gumbel_pi_dense(View v, float *out)
     WARP_PROLOGUE(v.n_trees)
     gumbel_final_pi_dense(cg, v, widx, sc, out);
 }
+// table-driven augmentation gather: out[a][t][j] = in[t][perm[a][j]] for states (int8) and policies (float)
+__global__ void k_augment(const int8_t *states, const float *policies, long long n_pos, int S, int P, const int32_t *perm_s,
+                          const int32_t *perm_p, int n_aug, int8_t *states_out, float *policies_out) {
+    const long long per_aug_s = n_pos * S, per_aug_p = n_pos * P;
+    const long long total_s = per_aug_s * n_aug, total = total_s + per_aug_p * n_aug;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (i < total_s) {
+            const int a = (int)(i / per_aug_s);
+            const long long r = i - (long long)a * per_aug_s;
+            const long long t = r / S;
+            const int j = (int)(r - t * S);
+            states_out[i] = states[t * S + perm_s[a * S + j]];
+        } else {
+            const long long k = i - total_s;
+            const int a = (int)(k / per_aug_p);
+            const long long r = k - (long long)a * per_aug_p;
+            const long long t = r / P;
+            const int j = (int)(r - t * P);
+            policies_out[k] = policies[t * P + perm_p[a * P + j]];
+        }
+    }
+}
 static inline int grid_warps(int n) { return (n + WARPS - 1) / WARPS; }
 #endif
 
@@ -898,6 +920,53 @@ int gaz_tree_sizes(gaz_engine *e, int32_t *out) {
     if (d2h(ts.data(), v.trees, ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
     for (int t = 0; t < v.n_trees; t++) { out[2 * t] = ts[t].n_nodes; out[2 * t + 1] = ts[t].n_slots; }
     return 0;
+}
+
+int gaz_augment(int device, const int8_t *states, const float *policies, int64_t n_pos, int S, int P, const int32_t *perm_state,
+                const int32_t *perm_policy, int n_aug, int8_t *states_out, float *policies_out) {
+    if (!states || !policies || !perm_state || !perm_policy || !states_out || !policies_out) return fail("null argument");
+    if (n_pos < 0 || S <= 0 || P <= 0 || n_aug <= 0) return fail("bad augmentation shape");
+    for (int i = 0; i < n_aug * S; i++) if (perm_state[i] < 0 || perm_state[i] >= S) return fail("state permutation entry %d out of range", i);
+    for (int i = 0; i < n_aug * P; i++) if (perm_policy[i] < 0 || perm_policy[i] >= P) return fail("policy permutation entry %d out of range", i);
+    if (n_pos == 0) return 0;
+#ifdef GAZ_EMUL
+    (void)device;
+    for (int a = 0; a < n_aug; a++)
+        for (int64_t t = 0; t < n_pos; t++) {
+            for (int j = 0; j < S; j++) states_out[((int64_t)a * n_pos + t) * S + j] = states[t * S + perm_state[a * S + j]];
+            for (int j = 0; j < P; j++) policies_out[((int64_t)a * n_pos + t) * P + j] = policies[t * P + perm_policy[a * P + j]];
+        }
+    return 0;
+#else
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0) return fail("no CUDA device (%s): libgaz_b200 has no CPU path", cudaGetErrorString(ce));
+    CK(cudaSetDevice(device));
+    int8_t *d_s = nullptr, *d_so = nullptr;
+    float *d_p = nullptr, *d_po = nullptr;
+    int32_t *d_ps = nullptr, *d_pp = nullptr;
+    const size_t bs = (size_t)n_pos * S, bp = (size_t)n_pos * P * 4;
+    int rc = 0;
+    auto done = [&](int r) { cudaFree(d_s); cudaFree(d_so); cudaFree(d_p); cudaFree(d_po); cudaFree(d_ps); cudaFree(d_pp); return r; };
+    if (cudaMalloc(&d_s, bs) != cudaSuccess || cudaMalloc(&d_so, bs * n_aug) != cudaSuccess || cudaMalloc(&d_p, bp) != cudaSuccess ||
+        cudaMalloc(&d_po, bp * n_aug) != cudaSuccess || cudaMalloc(&d_ps, (size_t)n_aug * S * 4) != cudaSuccess ||
+        cudaMalloc(&d_pp, (size_t)n_aug * P * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return done(fail("gaz_augment: device allocation of %zu bytes failed (call it on smaller batches)", (bs + bp) * (n_aug + 1)));
+    }
+    cudaStream_t st = nullptr; // the legacy default stream: copies and kernel are ordered, the call is synchronous
+    rc |= cudaMemcpyAsync(d_s, states, bs, cudaMemcpyHostToDevice, st) != cudaSuccess;
+    rc |= cudaMemcpyAsync(d_p, policies, bp, cudaMemcpyHostToDevice, st) != cudaSuccess;
+    rc |= cudaMemcpyAsync(d_ps, perm_state, (size_t)n_aug * S * 4, cudaMemcpyHostToDevice, st) != cudaSuccess;
+    rc |= cudaMemcpyAsync(d_pp, perm_policy, (size_t)n_aug * P * 4, cudaMemcpyHostToDevice, st) != cudaSuccess;
+    k_augment<<<148 * 8, 256, 0, st>>>(d_s, d_p, (long long)n_pos, S, P, d_ps, d_pp, n_aug, d_so, d_po);
+    rc |= cudaGetLastError() != cudaSuccess;
+    rc |= cudaMemcpyAsync(states_out, d_so, bs * n_aug, cudaMemcpyDeviceToHost, st) != cudaSuccess;
+    rc |= cudaMemcpyAsync(policies_out, d_po, bp * n_aug, cudaMemcpyDeviceToHost, st) != cudaSuccess;
+    rc |= cudaStreamSynchronize(st) != cudaSuccess;
+    if (rc) return done(fail("gaz_augment: %s", cudaGetErrorString(cudaGetLastError())));
+    return done(0);
+#endif
 }
 
 int64_t gaz_bytes_allocated(gaz_engine *e) { return e ? e->bytes : 0; }

@@ -14,6 +14,7 @@
 #include "gaz_conv.cuh"
 #include "gaz_block.cuh"
 #include "gaz_stem.cuh"
+#include "gaz_small.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -29,145 +30,6 @@ using gaz_conv::f32_blk_index;
     } while (0)
 
 // ====================================================================== CUDA-core kernels ==
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-
-struct StemArgs {
-    const int32_t *count;
-    int max_count;
-    const int8_t *states; // [leaf][H*W*Cin] HWC
-    int H, W, Cin, Cout, K, P_pad, Wp, act;
-    const float *w;       // [K*K][Cin][Cout]
-    const float *bias, *scale, *shift; // conv bias, stem BN affine
-    __nv_bfloat16 *out_q; // activation itself in bf16 (operand of a 1x1 projection), optional
-    float *out_raw;       // activation itself in fp32 (residual stream), optional
-    __nv_bfloat16 *out_a; // relu(BN_a(activation)) = first block's conv1 operand, optional
-    const float *scale_a, *shift_a;
-};
-
-// One CTA per board at a time (state bytes staged in shared memory); a thread owns 4 consecutive output
-// channels with their K*K*Cin x 4 weights in REGISTERS and walks the board's padded rows, so the inner loop is
-// warp-uniform broadcast LDS of the int8 inputs + FMAs; outputs leave as 8/16-byte vectors.
-template <int K, int CIN> __global__ void __launch_bounds__(256) stem_kernel(StemArgs p) {
-    constexpr int TAPS_CIN = K * K * CIN;
-    constexpr int kh = K >> 1;
-    __shared__ float s_in[18 * 18 * CIN]; // board with a zero border of kh cells, as floats: no bounds checks, no I2F
-    // CIN == 2 (Gomoku, TicTacToe): plane 0 is the constant side-to-move plane (Gomoku.py:173-177), so its contribution is
-    // s0 * (sum of the plane-0 weights of the in-bounds taps), which depends only on how close the cell is to each
-    // border: (2*kh+1)^2 classes.  The table replaces K*K broadcast loads + FMAs per row by one.
-    constexpr int NCLS = (2 * kh + 1);
-    extern __shared__ float s_tab[]; // [NCLS*NCLS][Cout] when the table form is used
-    const bool use_tab = CIN == 2 && p.H >= NCLS && p.W >= NCLS; // a cell is near at most one border per axis
-    const int pitch = (p.W + 2 * kh) * CIN;
-    const int npad = (p.H + 2 * kh) * pitch;
-    const int cpr = p.Cout >> 2;                 // threads per row
-    const int rows_par = blockDim.x / cpr;       // rows processed in parallel
-    const int tc = threadIdx.x % cpr, tr = threadIdx.x / cpr;
-    const int c0 = tc * 4;
-    float4 w[TAPS_CIN];
-#pragma unroll
-    for (int i = 0; i < TAPS_CIN; i++) w[i] = *reinterpret_cast<const float4 *>(p.w + (size_t)i * p.Cout + c0);
-    const float4 bias = *reinterpret_cast<const float4 *>(p.bias + c0);
-    const float4 sc = *reinterpret_cast<const float4 *>(p.scale + c0), sh = *reinterpret_cast<const float4 *>(p.shift + c0);
-    float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), ta = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.out_a) { sa = *reinterpret_cast<const float4 *>(p.scale_a + c0); ta = *reinterpret_cast<const float4 *>(p.shift_a + c0); }
-    int cnt = *p.count;
-    if (cnt > p.max_count) cnt = p.max_count;
-    const long long total_rows = ((long long)cnt * p.P_pad + 255) / 256 * 256;
-    const int n_boards_pad = (int)((total_rows + p.P_pad - 1) / p.P_pad);
-    const int nin = p.H * p.W * CIN;
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) s_in[i] = 0.0f;
-    if (use_tab) {
-        for (int i = threadIdx.x; i < NCLS * NCLS * p.Cout; i += blockDim.x) {
-            const int cls = i / p.Cout, ch = i - cls * p.Cout;
-            const int cy = cls / NCLS, cx = cls - cy * NCLS; // distance class: 0..kh-1 = that many cells from the top/left border,
-            float sum = 0.0f;                                 // kh = interior, kh+1..2kh = (2kh - class) cells from the bottom/right
-            for (int ky = 0; ky < K; ky++)
-                for (int kx = 0; kx < K; kx++) {
-                    const int dy = ky - kh, dx = kx - kh;
-                    const bool oky = cy < kh ? dy >= -cy : (cy > kh ? dy <= 2 * kh - cy : true);
-                    const bool okx = cx < kh ? dx >= -cx : (cx > kh ? dx <= 2 * kh - cx : true);
-                    if (oky && okx) sum += p.w[(size_t)((ky * K + kx) * CIN) * p.Cout + ch];
-                }
-            s_tab[i] = sum;
-        }
-    }
-    for (int b = blockIdx.x; b < n_boards_pad; b += gridDim.x) {
-        __syncthreads();
-        if (b < cnt)
-            for (int i = threadIdx.x; i < nin; i += blockDim.x) {
-                const int cell = i / CIN, ci = i - cell * CIN;
-                const int y = cell / p.W, x = cell - y * p.W;
-                s_in[(y + kh) * pitch + (x + kh) * CIN + ci] = (float)p.states[(size_t)b * nin + i];
-            }
-        __syncthreads();
-        for (int pos = tr; pos < p.P_pad; pos += rows_par) {
-            const long long row = (long long)b * p.P_pad + pos;
-            if (row >= total_rows) break;
-            const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
-            const bool live = b < cnt && yy >= 0 && xx < p.W;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) {
-                const float *wp0 = s_in + yy * pitch + xx * CIN; // top-left of the receptive field (padded coords)
-                if (use_tab) {
-                    const int cy = yy < kh ? yy : (yy >= p.H - kh ? 2 * kh - (p.H - 1 - yy) : kh);
-                    const int cx = xx < kh ? xx : (xx >= p.W - kh ? 2 * kh - (p.W - 1 - xx) : kh);
-                    const float s0 = wp0[kh * pitch + kh * CIN];   // plane 0 at the cell itself (constant over the board)
-                    const float4 t4 = *reinterpret_cast<const float4 *>(s_tab + (size_t)(cy * NCLS + cx) * p.Cout + c0);
-                    acc.x = s0 * t4.x; acc.y = s0 * t4.y; acc.z = s0 * t4.z; acc.w = s0 * t4.w;
-#pragma unroll
-                    for (int ky = 0; ky < K; ky++)
-#pragma unroll
-                        for (int kx = 0; kx < K; kx++) {
-                            const float fs = wp0[ky * pitch + kx * CIN + 1]; // the stone plane: mostly zeros, warp-uniform
-                            if (fs != 0.0f) {
-                                const float4 ww = w[(ky * K + kx) * CIN + 1];
-                                acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
-                                acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
-                            }
-                        }
-                } else {
-#pragma unroll
-                    for (int ky = 0; ky < K; ky++) {
-                        const float *wp = wp0 + ky * pitch;
-#pragma unroll
-                        for (int kx = 0; kx < K; kx++)
-#pragma unroll
-                            for (int ci = 0; ci < CIN; ci++) {
-                                const float fs = wp[kx * CIN + ci]; // warp-uniform broadcast load
-                                const float4 ww = w[(ky * K + kx) * CIN + ci];
-                                acc.x = fmaf(fs, ww.x, acc.x); acc.y = fmaf(fs, ww.y, acc.y);
-                                acc.z = fmaf(fs, ww.z, acc.z); acc.w = fmaf(fs, ww.w, acc.w);
-                            }
-                    }
-                }
-            }
-            float v[4] = {acc.x + bias.x, acc.y + bias.y, acc.z + bias.z, acc.w + bias.w};
-            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-            const float sav[4] = {sa.x, sa.y, sa.z, sa.w}, tav[4] = {ta.x, ta.y, ta.z, ta.w};
-            float a[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float t = fmaf(scv[j], v[j], shv[j]);
-                t = p.act == GAZ_ACT_RELU ? fmaxf(t, 0.0f) : (p.act == GAZ_ACT_GELU ? gelu_exact(t) : t);
-                v[j] = live ? t : 0.0f;
-                a[j] = live ? fmaxf(fmaf(sav[j], t, tav[j]), 0.0f) : 0.0f;
-            }
-            const size_t o = (size_t)row * p.Cout + c0;
-            if (p.out_raw) {
-                *reinterpret_cast<float4 *>(p.out_raw + f32_blk_index(row, c0, p.Cout)) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-            if (p.out_q) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-                *reinterpret_cast<uint2 *>(p.out_q + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-            }
-            if (p.out_a) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0], a[1]), h1 = __floats2bfloat162_rn(a[2], a[3]);
-                *reinterpret_cast<uint2 *>(p.out_a + o) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-            }
-        }
-    }
-}
-
 struct SeArgs {
     const int32_t *count;
     int max_count, H, W, C, R, P_pad, Wp;
@@ -230,9 +92,6 @@ struct HeadConvArgs {
     __nv_bfloat16 *out_act; // optional: relu(act_scale[f] * out + act_shift[f]) as bf16, same flat order (operand of a
     const float *act_scale, *act_shift; // tensor-core dense layer)
     int act_ld;         // row pitch of out_act in elements (features padded to a multiple of 8 for the TMA pitch rule)
-    // second head of a dual launch (headconv_f32_dual_kernel): same input and shape, own filters / bias / output
-    const float *w2, *bias2;
-    float *out2;
 };
 
 // small convolutions of the heads (C_out <= 16): thread per (leaf, cell), weights in shared memory
@@ -276,276 +135,6 @@ __global__ void __launch_bounds__(128) headconv_kernel(HeadConvArgs p) {
         float *op = p.out + (size_t)b * ncell * p.Cout + (size_t)cell * p.Cout;
 #pragma unroll
         for (int j = 0; j < 16; j++) if (j < p.Cout) op[j] = acc[j];
-    }
-}
-
-// Small head convolutions that read the blocked fp32 residual stream directly (Connect4: 3x3 C128 -> C8 on the trunk
-// output, Connect4/Build_Model.py:27,48).  Thread per pair of consecutive cells; every load is one 8-channel piece of the
-// blocked layout (ld.global.v8: the lanes of a warp read contiguous 32-byte pieces), the weights of a piece come from
-// shared memory as broadcast float4s and feed both cells.  Loop order: 8-channel piece outside, taps inside - at any time
-// a CTA works on (cells + halo) x 32 bytes, so the 9-fold re-read of the input by the taps hits L1 instead of L2
-// (tap-outside order: 1 GB of L2 reads per launch at 4096 leaves, 213 us).
-template <int COUT, int KS>
-__global__ void __launch_bounds__(128) headconv_f32_kernel(HeadConvArgs p) {
-    extern __shared__ __align__(16) float s_w[];   // [tap][Cin][COUT]
-    constexpr int kh = KS >> 1;
-    const int nW = KS * KS * p.Cin * COUT;
-    for (int i = threadIdx.x; i < nW / 4; i += blockDim.x) reinterpret_cast<float4 *>(s_w)[i] = reinterpret_cast<const float4 *>(p.w)[i];
-    __syncthreads();
-    int cnt = *p.count;
-    if (cnt > p.max_count) cnt = p.max_count;
-    const int ncell = p.H * p.W;
-    const long long total = (long long)cnt * ncell;
-    const int npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
-    const float *in = (const float *)p.in;
-    for (long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x; 2 * pr < total; pr += (long long)gridDim.x * blockDim.x) {
-        long long r0[2];
-        bool have[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const long long idx = 2 * pr + e;
-            have[e] = idx < total;
-            const long long id2 = have[e] ? idx : 2 * pr;
-            const int b = (int)(id2 / ncell), cell = (int)(id2 - (long long)b * ncell);
-            const int y = cell / p.W, x = cell - y * p.W;
-            r0[e] = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
-        }
-        // per tap and cell: offset of the row's first piece in the blocked layout
-        // (gaz_conv::f32_blk_index(r, 8 * pc, Cin) = (((r >> 5) * (Cin >> 5) + (pc >> 2)) << 10) + ((pc & 3) << 8) + ((r & 31) << 3));
-        // a tap outside the tensor reads the centre row and is multiplied by 0: fmaf(0, w, acc) = acc
-        uint32_t off[KS * KS][2];
-        float live[KS * KS][2];
-#pragma unroll
-        for (int t = 0; t < KS * KS; t++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const long long r = r0[e] + (t / KS - kh) * p.Wp + (t % KS - kh);
-                const bool ok = r >= 0 && r < p.in_rows;
-                const long long rr = ok ? r : r0[e];
-                off[t][e] = (uint32_t)((((rr >> 5) * cb_per_row) << 10) + ((rr & 31) << 3));
-                live[t][e] = ok ? 1.0f : 0.0f;
-            }
-        float acc[2][COUT];
-#pragma unroll
-        for (int e = 0; e < 2; e++)
-#pragma unroll
-            for (int j = 0; j < COUT; j++) acc[e][j] = p.bias[j];
-#pragma unroll 1
-        for (int pc = 0; pc < npiece; pc++) {
-            const uint32_t po = ((uint32_t)(pc >> 2) << 10) + ((uint32_t)(pc & 3) << 8);
-#pragma unroll
-            for (int ky = 0; ky < KS; ky++) {
-                float a[KS][2][8];
-#pragma unroll
-                for (int kx = 0; kx < KS; kx++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) gaz_conv::ldg256(in + off[ky * KS + kx][e] + po, a[kx][e]);
-#pragma unroll
-                for (int kx = 0; kx < KS; kx++) {
-                    const int t = ky * KS + kx;
-                    const float *wp = s_w + (size_t)(t * p.Cin + pc * 8) * COUT;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const float4 *w4 = reinterpret_cast<const float4 *>(wp + c * COUT);
-                        const float a0 = a[kx][0][c] * live[t][0], a1 = a[kx][1][c] * live[t][1];
-#pragma unroll
-                        for (int q = 0; q < COUT / 4; q++) {
-                            const float4 w = w4[q];
-                            acc[0][4 * q] = fmaf(a0, w.x, acc[0][4 * q]);
-                            acc[0][4 * q + 1] = fmaf(a0, w.y, acc[0][4 * q + 1]);
-                            acc[0][4 * q + 2] = fmaf(a0, w.z, acc[0][4 * q + 2]);
-                            acc[0][4 * q + 3] = fmaf(a0, w.w, acc[0][4 * q + 3]);
-                            acc[1][4 * q] = fmaf(a1, w.x, acc[1][4 * q]);
-                            acc[1][4 * q + 1] = fmaf(a1, w.y, acc[1][4 * q + 1]);
-                            acc[1][4 * q + 2] = fmaf(a1, w.z, acc[1][4 * q + 2]);
-                            acc[1][4 * q + 3] = fmaf(a1, w.w, acc[1][4 * q + 3]);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            if (!have[e]) continue;
-            float *op = p.out + (size_t)(2 * pr + e) * COUT;   // [leaf][cell][COUT] = flat index * COUT
-#pragma unroll
-            for (int q = 0; q < COUT / 4; q++)
-                *reinterpret_cast<float4 *>(op + 4 * q) = make_float4(acc[e][4 * q], acc[e][4 * q + 1], acc[e][4 * q + 2], acc[e][4 * q + 3]);
-        }
-    }
-}
-
-// Two head convolutions of the same shape on the same input in ONE pass (Connect4: the policy and the value head both
-// start with a 3x3 C128 -> C8 convolution of the trunk output, Connect4/Build_Model.py:27,48): the filters of both heads
-// sit side by side in shared memory ([tap][Cin][head 1 | head 2]), every 8-channel piece of the input is loaded once and
-// feeds 2 x COUT accumulators per cell.  Each output sees its terms in the order of headconv_f32_kernel, so the results
-// are bit-identical to two single launches; the launch is latency-bound (20 resident warps per SM), so halving the loads
-// per FMA is what pays.
-template <int COUT, int KS>
-__global__ void __launch_bounds__(128) headconv_f32_dual_kernel(HeadConvArgs p) {
-    extern __shared__ __align__(16) float s_w[];   // [tap][Cin][2 * COUT]
-    constexpr int kh = KS >> 1, C2 = 2 * COUT, Q = COUT / 4;
-    const int nrow = KS * KS * p.Cin;
-    for (int i = threadIdx.x; i < nrow * Q; i += blockDim.x) {
-        const int r = i / Q, q = i - r * Q;
-        reinterpret_cast<float4 *>(s_w)[r * 2 * Q + q] = reinterpret_cast<const float4 *>(p.w)[i];
-        reinterpret_cast<float4 *>(s_w)[r * 2 * Q + Q + q] = reinterpret_cast<const float4 *>(p.w2)[i];
-    }
-    __syncthreads();
-    int cnt = *p.count;
-    if (cnt > p.max_count) cnt = p.max_count;
-    const int ncell = p.H * p.W;
-    const long long total = (long long)cnt * ncell;
-    const int npiece = p.Cin >> 3, cb_per_row = p.Cin >> 5;
-    const float *in = (const float *)p.in;
-    for (long long pr = blockIdx.x * (long long)blockDim.x + threadIdx.x; 2 * pr < total; pr += (long long)gridDim.x * blockDim.x) {
-        long long r0[2];
-        bool have[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const long long idx = 2 * pr + e;
-            have[e] = idx < total;
-            const long long id2 = have[e] ? idx : 2 * pr;
-            const int b = (int)(id2 / ncell), cell = (int)(id2 - (long long)b * ncell);
-            const int y = cell / p.W, x = cell - y * p.W;
-            r0[e] = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
-        }
-        uint32_t off[KS * KS][2];
-        float live[KS * KS][2];
-#pragma unroll
-        for (int t = 0; t < KS * KS; t++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const long long r = r0[e] + (t / KS - kh) * p.Wp + (t % KS - kh);
-                const bool ok = r >= 0 && r < p.in_rows;
-                const long long rr = ok ? r : r0[e];
-                off[t][e] = (uint32_t)((((rr >> 5) * cb_per_row) << 10) + ((rr & 31) << 3));
-                live[t][e] = ok ? 1.0f : 0.0f;
-            }
-        float acc[2][C2];
-#pragma unroll
-        for (int e = 0; e < 2; e++)
-#pragma unroll
-            for (int j = 0; j < COUT; j++) { acc[e][j] = p.bias[j]; acc[e][COUT + j] = p.bias2[j]; }
-#pragma unroll 1
-        for (int pc = 0; pc < npiece; pc++) {
-            const uint32_t po = ((uint32_t)(pc >> 2) << 10) + ((uint32_t)(pc & 3) << 8);
-#pragma unroll
-            for (int ky = 0; ky < KS; ky++) {
-                float a[KS][2][8];
-#pragma unroll
-                for (int kx = 0; kx < KS; kx++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) gaz_conv::ldg256(in + off[ky * KS + kx][e] + po, a[kx][e]);
-#pragma unroll
-                for (int kx = 0; kx < KS; kx++) {
-                    const int t = ky * KS + kx;
-                    const float *wp = s_w + (size_t)(t * p.Cin + pc * 8) * C2;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const float4 *w4 = reinterpret_cast<const float4 *>(wp + c * C2);
-                        const float a0 = a[kx][0][c] * live[t][0], a1 = a[kx][1][c] * live[t][1];
-#pragma unroll
-                        for (int q = 0; q < 2 * Q; q++) {
-                            const float4 w = w4[q];
-                            acc[0][4 * q] = fmaf(a0, w.x, acc[0][4 * q]);
-                            acc[0][4 * q + 1] = fmaf(a0, w.y, acc[0][4 * q + 1]);
-                            acc[0][4 * q + 2] = fmaf(a0, w.z, acc[0][4 * q + 2]);
-                            acc[0][4 * q + 3] = fmaf(a0, w.w, acc[0][4 * q + 3]);
-                            acc[1][4 * q] = fmaf(a1, w.x, acc[1][4 * q]);
-                            acc[1][4 * q + 1] = fmaf(a1, w.y, acc[1][4 * q + 1]);
-                            acc[1][4 * q + 2] = fmaf(a1, w.z, acc[1][4 * q + 2]);
-                            acc[1][4 * q + 3] = fmaf(a1, w.w, acc[1][4 * q + 3]);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            if (!have[e]) continue;
-            float *o1 = p.out + (size_t)(2 * pr + e) * COUT, *o2 = p.out2 + (size_t)(2 * pr + e) * COUT;
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-                *reinterpret_cast<float4 *>(o1 + 4 * q) = make_float4(acc[e][4 * q], acc[e][4 * q + 1], acc[e][4 * q + 2], acc[e][4 * q + 3]);
-                *reinterpret_cast<float4 *>(o2 + 4 * q) = make_float4(acc[e][COUT + 4 * q], acc[e][COUT + 4 * q + 1], acc[e][COUT + 4 * q + 2], acc[e][COUT + 4 * q + 3]);
-            }
-        }
-    }
-}
-
-// Head convolutions with few taps*channels: one warp per output cell, lane = input channel (CPL channels per
-// lane, coalesced row loads), weights in registers, COUT partial sums folded across the warp with a halving
-// butterfly (COUT-1 + log2(32/COUT) shuffles instead of 5*COUT).
-template <int CPL, int COUT, int K, bool IN_F32>
-__global__ void __launch_bounds__(256) headconv_warp_kernel(HeadConvArgs p) {
-    constexpr int TAPS = K * K, kh = K >> 1;
-    const int lane = threadIdx.x & 31;
-    float w[TAPS][CPL][COUT];
-#pragma unroll
-    for (int t = 0; t < TAPS; t++)
-#pragma unroll
-        for (int j = 0; j < CPL; j++)
-#pragma unroll
-            for (int co = 0; co < COUT; co++) w[t][j][co] = p.w[(size_t)(t * p.Cin + lane + 32 * j) * COUT + co];
-    int cnt = *p.count;
-    if (cnt > p.max_count) cnt = p.max_count;
-    const int ncell = p.H * p.W;
-    const long long total = (long long)cnt * ncell;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long idx = warp0; idx < total; idx += nwarps) {
-        const int b = (int)(idx / ncell), cell = (int)(idx - (long long)b * ncell);
-        const int y = cell / p.W, x = cell - y * p.W;
-        const long long r0 = (long long)b * p.P_pad + (y + 1) * p.Wp + x;
-        float acc[COUT];
-#pragma unroll
-        for (int co = 0; co < COUT; co++) acc[co] = 0.0f;
-        float a[TAPS][CPL]; // all loads issued before the first FMA (rows outside the buffer are padding: weight 0)
-#pragma unroll
-        for (int t = 0; t < TAPS; t++) {
-            long long r = r0 + (t / K - kh) * p.Wp + (t % K - kh);
-            const bool ok = r >= 0 && r < p.in_rows;
-            r = ok ? r : r0;
-#pragma unroll
-            for (int j = 0; j < CPL; j++) {
-                float x_;
-                if (IN_F32) x_ = ((const float *)p.in)[f32_blk_index(r, lane + 32 * j, p.Cin)];
-                else x_ = __bfloat162float(((const __nv_bfloat16 *)p.in)[r * p.Cin + lane + 32 * j]);
-                a[t][j] = ok ? x_ : 0.0f;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < TAPS; t++)
-#pragma unroll
-            for (int j = 0; j < CPL; j++)
-#pragma unroll
-                for (int co = 0; co < COUT; co++) acc[co] = fmaf(a[t][j], w[t][j][co], acc[co]);
-        // halving butterfly: after the step with mask m a lane keeps the half of its values selected by (lane & m)
-        int n = COUT;
-        int co_base = 0;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            if (n > 1) {
-                const int h = n >> 1;
-                const bool up = (lane & m) != 0;
-#pragma unroll
-                for (int i = 0; i < COUT / 2; i++) {
-                    if (i < h) {
-                        const float send = up ? acc[i] : acc[i + h];
-                        const float keep = up ? acc[i + h] : acc[i];
-                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-                    }
-                }
-                co_base += up ? h : 0;
-                n = h;
-            } else {
-                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], m);
-            }
-        }
-        // lanes whose low log2(32/COUT) bits are zero hold output channel co_base
-        constexpr int REP = 32 / COUT;
-        if ((lane & (REP - 1)) == 0) p.out[(size_t)idx * COUT + co_base] = acc[0] + p.bias[co_base];
     }
 }
 
@@ -791,8 +380,14 @@ struct NetOp {
     int skip;             // SE op folded into the previous conv
     int block_fused;      // this conv1 runs the whole residual block (gaz_block.cuh) together with the next conv (+SE)
     int in_block;         // this conv2 is executed by the previous op's fused block kernel
-    int dual_partner;     // HEADCONV: index of a later head convolution of the same shape on the same input that this op's
-    int dual_skip;        // launch computes as well (headconv_f32_dual_kernel); dual_skip marks that later op
+    int dual_partner;     // HEADCONV: index of a later head convolution on the same fp32 input that this op's launch computes
+    int dual_skip;        // as well (gaz_small::headconv_wide_kernel, N = 16); dual_skip marks that later op
+    int head_wide;        // HEADCONV on the fp32 stream through headconv_wide_kernel: d_frag / d_hbias are set
+    uint4 *d_frag;        // mma.sync B fragments (stem_mma_kernel / headconv_wide_kernel)
+    float *d_hbias;       // [16] biases of the (up to) two heads of a wide head convolution
+    int head_G;           // boards per CTA iteration of the wide head convolution / the mma stem
+    int chain_len;        // DENSE: this op starts a chain of chain_len dense layers run by ONE mlp_chain_kernel launch
+    int chain_skip;       // DENSE executed by an earlier op's chain launch
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
     float *d_se_b1;       // fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
     // dense layer on the tensor cores (DENSE op fed by a HEADCONV op): bf16 activated input + bf16 [Out][In] weights
@@ -801,7 +396,8 @@ struct NetOp {
     __nv_bfloat16 *d_wt;  // [Out][In]
     int stem_tc;          // stem on the tensor cores (gaz_stem.cuh): d_stem_w / d_stem_par / tmOa (out_a) / tmOb (out_q) are set
     uint16_t *d_stem_w;   // [256][64] bf16 hi | lo split filters
-    float *d_stem_par;    // [4][256] BN scale | shift + scale * bias | scale_a | shift_a
+    float *d_stem_par;    // stem_tc: [4][256] BN scale | shift + scale * bias | scale_a | shift_a; mma stem: [5][Cout] conv bias |
+                          // BN scale | BN shift | scale_a | shift_a
     CUtensorMap tmDA, tmDW2;
     long long rows_dense;
 };
@@ -914,15 +510,6 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
         switch (d.type) {
         case GAZ_OP_STEM: {
-            StemArgs a;
-            a.count = count; a.max_count = n->max_batch; a.states = states;
-            a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize; a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act;
-            a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.scale = wfp(n, d.scale_b); a.shift = wfp(n, d.shift_b);
-            a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
-            a.scale_a = wfp(n, d.scale_a); a.shift_a = wfp(n, d.shift_a);
-            const int tc = d.ksize * d.ksize * d.cin;
-            if (d.cout % 4 != 0 || 256 % (d.cout / 4) != 0 || d.cin > 4 || (n->H + 2 * (d.ksize / 2)) > 18 || (n->W + 2 * (d.ksize / 2)) > 18)
-                return gaz_fail("stem shape unsupported (cin %d cout %d)", d.cin, d.cout);
             if (op.stem_tc) {
                 static bool attr_set = false;
                 if (!attr_set) {
@@ -936,13 +523,31 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 gaz_stem::stem_tc_kernel<<<2 * n->n_sm, 256, gaz_stem::Cfg::SMEM, s>>>(op.tmOb, op.tmOa, t);
                 break;
             }
-            int grid = n->n_sm * 4;
-            (void)tc;
-            const size_t tab = d.cin == 2 ? (size_t)d.ksize * d.ksize * d.cout * 4 : 0; // (2*kh+1)^2 classes x Cout floats
-            if (d.ksize == 3 && d.cin == 2) stem_kernel<3, 2><<<grid, 256, tab, s>>>(a);        // Gomoku
-            else if (d.ksize == 3 && d.cin == 4) stem_kernel<3, 4><<<grid, 256, 0, s>>>(a);   // Connect4
-            else if (d.ksize == 5 && d.cin == 2) stem_kernel<5, 2><<<grid, 256, tab, s>>>(a);   // TicTacToe
-            else return gaz_fail("stem k=%d cin=%d unsupported", d.ksize, d.cin);
+            {   // every other stem shape: implicit GEMM on mma.sync (gaz_small.cuh)
+                gaz_small::StemMmaArgs a;
+                a.count = count; a.max_count = n->max_batch; a.states = states; a.H = n->H; a.W = n->W; a.Cout = d.cout;
+                a.P_pad = n->P_pad; a.Wp = n->Wp; a.act = d.act; a.G = op.head_G; a.frags = op.d_frag; a.par = op.d_stem_par;
+                a.out_q = (__nv_bfloat16 *)buf(d.out_b); a.out_raw = (float *)buf(d.out_raw); a.out_a = (__nv_bfloat16 *)buf(d.out_a);
+                const int groups = (int)((n->rows_alloc / n->P_pad + a.G) / a.G);
+                const int grid = groups < 2 * n->n_sm ? groups : 2 * n->n_sm;
+                size_t sm;
+#define STEM_MMA(K_, C_)                                                                                                        \
+    do {                                                                                                                        \
+        sm = gaz_small::StemMmaCfg<K_, C_>::smem(n->H, n->W, d.cout, a.G);                                                       \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            CKN(cudaFuncSetAttribute(gaz_small::stem_mma_kernel<K_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        if (sm > 96 * 1024) return gaz_fail("stem: %zu bytes of shared memory", sm);                                             \
+        gaz_small::stem_mma_kernel<K_, C_><<<grid, 256, sm, s>>>(a);                                                             \
+    } while (0)
+                if (d.ksize == 3 && d.cin == 2) STEM_MMA(3, 2);        // Gomoku-shaped boards with a stem the tcgen05 kernel does not cover
+                else if (d.ksize == 3 && d.cin == 4) STEM_MMA(3, 4);   // Connect4
+                else if (d.ksize == 5 && d.cin == 2) STEM_MMA(5, 2);   // TicTacToe
+                else return gaz_fail("stem k=%d cin=%d unsupported", d.ksize, d.cin);
+#undef STEM_MMA
+            }
             break;
         }
         case GAZ_OP_CONV_TC: {
@@ -990,8 +595,27 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         }
         case GAZ_OP_HEADCONV: {
             if (op.dual_skip) break;
+            if (op.head_wide) {   // fp32 trunk output -> both heads' small convolutions in one mma.sync pass (gaz_small.cuh)
+                gaz_small::HeadWideArgs a;
+                a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.K = d.ksize;
+                a.P_pad = n->P_pad; a.Wp = n->Wp; a.G = op.head_G; a.in_rows = n->rows_alloc; a.in = (const float *)buf(d.in_buf);
+                a.frags = op.d_frag; a.bias = op.d_hbias; a.cout1 = d.cout; a.out1 = (float *)buf(d.out_raw);
+                a.cout2 = 0; a.out2 = nullptr;
+                if (op.dual_partner >= 0) {
+                    const NetOp &o2 = n->ops[(size_t)op.dual_partner];
+                    a.cout2 = o2.d.cout; a.out2 = (float *)buf(o2.d.out_raw);
+                }
+                const size_t sm = gaz_small::head_wide_smem(d.cin, d.ksize, n->P_pad, n->Wp, a.G);
+                static size_t attr_sm = 0;
+                if (sm > attr_sm) {
+                    CKN(cudaFuncSetAttribute(gaz_small::headconv_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    attr_sm = sm;
+                }
+                const int groups = (n->max_batch + a.G - 1) / a.G;
+                gaz_small::headconv_wide_kernel<<<groups < n->n_sm ? groups : n->n_sm, 512, sm, s>>>(a);
+                break;
+            }
             HeadConvArgs a;
-            a.w2 = a.bias2 = nullptr; a.out2 = nullptr;
             a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.Cout = d.cout; a.K = d.ksize;
             a.P_pad = n->P_pad; a.Wp = n->Wp; a.in_f32 = n->bufs[(size_t)d.in_buf].kind == GAZ_BUF_ROWS_F32;
             a.in_rows = n->rows_alloc; a.in = buf(d.in_buf); a.w = wfp(n, d.w); a.bias = wfp(n, d.bias); a.out = (float *)buf(d.out_raw);
@@ -1001,50 +625,43 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 a.out_act = nx.d_act; a.act_scale = wfp(n, nx.d.scale_a); a.act_shift = wfp(n, nx.d.shift_a);
                 a.act_ld = (nx.d.cin + 7) & ~7;
             }
-            size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
-            if (op.dual_partner >= 0) {
-                const NetOp &o2 = n->ops[(size_t)op.dual_partner];
-                a.w2 = wfp(n, o2.d.w); a.bias2 = wfp(n, o2.d.bias); a.out2 = (float *)buf(o2.d.out_raw);
-                headconv_f32_dual_kernel<8, 3><<<n->n_sm * 8, 128, 2 * sm, s>>>(a);
-                break;
-            }
-            const int cpl = d.cin / 32;
-            const int g2 = n->n_sm * 8;
-            bool done = true;
-#define HC(CPL_, CO_, K_) \
-    (a.in_f32 ? (void)(headconv_warp_kernel<CPL_, CO_, K_, true><<<g2, 256, 0, s>>>(a)) \
-              : (void)(headconv_warp_kernel<CPL_, CO_, K_, false><<<g2, 256, 0, s>>>(a)))
+            const size_t sm = (size_t)d.ksize * d.ksize * d.cin * d.cout * 4;
             if (d.cin == 32 && !a.in_f32 && ((d.cout == 8 && d.ksize == 3) || (d.cout == 4 && d.ksize == 1))) {
                 const int halo = (d.ksize / 2) * (n->Wp + 1);
                 const size_t smm = (size_t)(((n->P_pad + 15) / 16) * 16 + 2 * halo) * 64 + (size_t)d.ksize * d.ksize * 2 * 32 * 16;
-                if (smm <= 48 * 1024 && (d.cout & 1) == 0 && (((d.cout * n->H * n->W + 7) & ~7) & 1) == 0) {
+                if (smm <= 48 * 1024 && (((d.cout * n->H * n->W + 7) & ~7) & 1) == 0) {
                     if (d.ksize == 3) headconv_mma_kernel<3><<<n->n_sm * 8, 128, smm, s>>>(a);
                     else headconv_mma_kernel<1><<<n->n_sm * 8, 128, smm, s>>>(a);
                     break;
                 }
             }
-            if (d.cin % 32 != 0) done = false;
-            else if (cpl == 1 && d.cout == 8 && d.ksize == 3) HC(1, 8, 3);
-            else if (cpl == 1 && d.cout == 4 && d.ksize == 1) HC(1, 4, 1);
-            else if (cpl == 2 && d.cout == 8 && d.ksize == 1) HC(2, 8, 1);
-            else if (cpl == 2 && d.cout == 4 && d.ksize == 1) HC(2, 4, 1);
-            else done = false;
-#undef HC
-            if (done) break;
+            if (a.out_act) return gaz_fail("headconv feeding a tensor-core dense layer needs the mma.sync kernel (cin 32)");
             if (d.cout > 16 || sm > 48 * 1024) return gaz_fail("headconv shape unsupported (cout %d, %zu B weights)", d.cout, sm);
-            if (a.in_f32 && d.cin % 32 == 0 && (d.cout == 4 || d.cout == 8) &&
-                (d.ksize == 3 || d.ksize == 1) && ((uintptr_t)a.w & 15) == 0) {
-                const int g3 = n->n_sm * 8;
-                if (d.cout == 4 && d.ksize == 3) headconv_f32_kernel<4, 3><<<g3, 128, sm, s>>>(a);
-                else if (d.cout == 8 && d.ksize == 3) headconv_f32_kernel<8, 3><<<g3, 128, sm, s>>>(a);
-                else if (d.cout == 4) headconv_f32_kernel<4, 1><<<g3, 128, sm, s>>>(a);
-                else headconv_f32_kernel<8, 1><<<g3, 128, sm, s>>>(a);
-                break;
-            }
-            headconv_kernel<<<n->n_sm * 16, 128, sm, s>>>(a);
+            headconv_kernel<<<n->n_sm * 16, 128, sm, s>>>(a);   // generic shapes: thread per cell, fp32 CUDA cores
             break;
         }
         case GAZ_OP_DENSE: {
+            if (op.chain_skip) break;
+            if (op.chain_len > 0) {   // the dense stack behind a head as one launch (gaz_small::mlp_chain_kernel)
+                gaz_small::MlpArgs a;
+                memset(&a, 0, sizeof a);
+                a.count = count; a.max_count = n->max_batch; a.n_layers = op.chain_len; a.in = (const float *)buf(d.in_buf);
+                for (int li = 0; li < op.chain_len; li++) {
+                    const gaz_net_op &dl = n->ops[oi + (size_t)li].d;
+                    gaz_small::MlpLayer &L = a.L[li];
+                    L.In = dl.cin; L.Out = dl.cout; L.pre_affine = dl.flags & 1; L.pre_relu = (dl.flags >> 1) & 1; L.act = dl.act;
+                    L.w = wfp(n, dl.w); L.bias = wfp(n, dl.bias); L.pre_scale = wfp(n, dl.scale_a); L.pre_shift = wfp(n, dl.shift_a);
+                    if (li + 1 == op.chain_len) a.out = (dl.flags & 4) ? value : (float *)buf(dl.out_raw);
+                }
+                const size_t sm = gaz_small::mlp_smem(a);
+                static size_t attr_sm = 48 * 1024;
+                if (sm > attr_sm) {
+                    CKN(cudaFuncSetAttribute(gaz_small::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    attr_sm = sm;
+                }
+                gaz_small::mlp_chain_kernel<<<(n->max_batch + gaz_small::MLP_TL - 1) / gaz_small::MLP_TL, 256, sm, s>>>(a);
+                break;
+            }
             if (op.dense_tc) { // [leaf][In] bf16 x [Out][In] bf16 on the board kernel: rows = leaves, 128 outputs per launch
                 float *outp = (d.flags & 4) ? value : (float *)buf(d.out_raw);
                 for (int n0 = 0; n0 < d.cout; n0 += 128) {
@@ -1164,6 +781,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.in_block = 0;
         op.dual_partner = -1;
         op.dual_skip = 0;
+        op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0;
         op.stem_tc = 0;
         op.d_stem_w = nullptr;
         op.d_stem_par = nullptr;
@@ -1272,33 +890,85 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             c2.in_block = 1;
         }
     }
-    // two head convolutions of one shape on one fp32 input -> one launch (headconv_f32_dual_kernel)
+    // Head convolutions that read the fp32 trunk output (Connect4, TicTacToe) run on headconv_wide_kernel; a second head
+    // convolution with the same input, taps and input channels joins the launch as columns 8..15 (N = 16).
     {
+        auto boards_per_iter = [&](int want_rows) {   // G boards per CTA iteration: G * P_pad a multiple of 16, about want_rows rows
+            int g0 = 1;
+            while ((g0 * n->P_pad) % 16 != 0) g0++;
+            int G = g0;
+            while ((G + g0) * n->P_pad <= want_rows) G += g0;
+            return G;
+        };
         for (size_t i = 0; i < n->ops.size(); i++) {
             NetOp &o1 = n->ops[i];
             const gaz_net_op &d1 = o1.d;
-            if (d1.type != GAZ_OP_HEADCONV || o1.dual_skip || o1.dual_partner >= 0) continue;
-            if (d1.cout != 8 || d1.ksize != 3 || d1.cin % 32 != 0 || d1.cin <= 32) continue;
+            if (d1.type != GAZ_OP_HEADCONV || o1.dual_skip || o1.head_wide) continue;
+            if (d1.cout > 8 || (d1.ksize != 1 && d1.ksize != 3) || d1.cin % 16 != 0 || d1.cin > 256) continue;
             if (n->bufs[(size_t)d1.in_buf].kind != GAZ_BUF_ROWS_F32) continue;
             if (i + 1 < n->ops.size() && n->ops[i + 1].dense_tc) continue;
-            if ((size_t)2 * 9 * d1.cin * 8 * 4 > 200 * 1024 || ((d1.w * 4) & 15) != 0) continue;
+            const int G = boards_per_iter(d1.ksize == 3 ? 224 : 256);
+            if (gaz_small::head_wide_smem(d1.cin, d1.ksize, n->P_pad, n->Wp, G) > 220 * 1024) continue;
+            const gaz_net_op *d2p = nullptr;
             for (size_t j = i + 1; j < n->ops.size(); j++) {
                 NetOp &o2 = n->ops[j];
                 const gaz_net_op &d2 = o2.d;
-                if (d2.type != GAZ_OP_HEADCONV || d2.in_buf != d1.in_buf || d2.cin != d1.cin || d2.cout != d1.cout ||
-                    d2.ksize != d1.ksize || o2.dual_skip || ((d2.w * 4) & 15) != 0) continue;
+                if (d2.type != GAZ_OP_HEADCONV || d2.in_buf != d1.in_buf || d2.cin != d1.cin || d2.cout > 8 || d2.ksize != d1.ksize ||
+                    o2.dual_skip || o2.head_wide) continue;
                 if (j + 1 < n->ops.size() && n->ops[j + 1].dense_tc) continue;
                 o1.dual_partner = (int)j;
                 o2.dual_skip = 1;
-                const int smem = 2 * 9 * d1.cin * 8 * 4;
-                if (cudaFuncSetAttribute(headconv_f32_dual_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-                    cudaGetLastError();
-                    o1.dual_partner = -1;
-                    o2.dual_skip = 0;
-                }
+                d2p = &o2.d;
                 break;
             }
+            const int taps = d1.ksize * d1.ksize, KS = d1.cin / 16;
+            std::vector<gaz_small::Frag> fr((size_t)taps * KS * 2 * 32);
+            for (int tp = 0; tp < taps; tp++)
+                for (int ks = 0; ks < KS; ks++)
+                    for (int nt = 0; nt < 2; nt++) {
+                        const gaz_net_op *dd = nt == 0 ? &d1 : d2p;
+                        for (int lane = 0; lane < 32; lane++) {
+                            auto wfun = [&](int k, int nn) -> float {   // [tap][Cin][Cout] filters of head nt, zero beyond its channels
+                                if (!dd || nn >= dd->cout) return 0.0f;
+                                return desc->wf[dd->w + ((int64_t)tp * dd->cin + k) * dd->cout + nn];
+                            };
+                            fr[(((size_t)tp * KS + ks) * 2 + nt) * 32 + lane] = gaz_small::host_frag(lane, wfun, ks * 16, 0);
+                        }
+                    }
+            float hb[16];
+            for (int c = 0; c < 16; c++) {
+                const gaz_net_op *dd = c < 8 ? &d1 : d2p;
+                hb[c] = (dd && (c & 7) < dd->cout) ? desc->wf[dd->bias + (c & 7)] : 0.0f;
+            }
+            if (alloc((void **)&o1.d_frag, fr.size() * sizeof(gaz_small::Frag)) != 0 || alloc((void **)&o1.d_hbias, sizeof hb) != 0) { gaz_net_destroy(n); return -1; }
+            CKN(cudaMemcpy(o1.d_frag, fr.data(), fr.size() * sizeof(gaz_small::Frag), cudaMemcpyHostToDevice));
+            CKN(cudaMemcpy(o1.d_hbias, hb, sizeof hb, cudaMemcpyHostToDevice));
+            o1.head_wide = 1;
+            o1.head_G = G;
         }
+        // stems the tcgen05 kernel does not cover: fragments + parameters of stem_mma_kernel (set below once stem_tc is known)
+    }
+    // dense chains: consecutive DENSE ops, each reading the previous one's output, that fit a CTA's shared memory
+    for (size_t i = 0; i < n->ops.size(); i++) {
+        NetOp &o1 = n->ops[i];
+        if (o1.d.type != GAZ_OP_DENSE || o1.dense_tc || o1.chain_skip || o1.chain_len) continue;
+        auto fits = [](const gaz_net_op &dd) { return dd.cin <= 512 && dd.cout <= 128; };
+        if (!fits(o1.d)) continue;
+        int len = 1;
+        while (len < 3 && i + (size_t)len < n->ops.size()) {
+            const NetOp &nx = n->ops[i + (size_t)len];
+            const gaz_net_op &pv = n->ops[i + (size_t)len - 1].d;
+            if (nx.d.type != GAZ_OP_DENSE || nx.dense_tc || !fits(nx.d) || (pv.flags & 4) || nx.d.in_buf != pv.out_raw || nx.d.cin != pv.cout) break;
+            // the intermediate buffer must have no other reader (the chain never writes it)
+            bool other = false;
+            for (size_t k = 0; k < n->ops.size(); k++)
+                if (k != i + (size_t)len && (n->ops[k].d.in_buf == pv.out_raw || n->ops[k].d.res_buf == pv.out_raw)) other = true;
+            if (other || pv.out_raw == n->logits_buf) break;
+            len++;
+        }
+        if (len < 2) continue;
+        o1.chain_len = len;
+        for (int k = 1; k < len; k++) n->ops[i + (size_t)k].chain_skip = 1;
     }
     // stem on the tensor cores: 3x3 on 2 planes -> 256 filters, tile == board, bf16 outputs only
     for (auto &op : n->ops) {
@@ -1343,6 +1013,38 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         }
         op.stem_tc = ok ? 1 : 0;
     }
+    for (auto &op : n->ops) {   // every other stem: B fragments (hi | lo) + parameters of gaz_small::stem_mma_kernel
+        const gaz_net_op &d = op.d;
+        if (d.type != GAZ_OP_STEM || op.stem_tc) continue;
+        if (d.cout % 8 != 0 || d.cout > 256 || !((d.ksize == 3 && (d.cin == 2 || d.cin == 4)) || (d.ksize == 5 && d.cin == 2))) {
+            gaz_net_destroy(n);
+            return gaz_fail("stem shape unsupported (k %d cin %d cout %d)", d.ksize, d.cin, d.cout);
+        }
+        const int KK = d.ksize * d.ksize * d.cin, KS = (KK + 15) / 16, NT = d.cout / 8;
+        std::vector<gaz_small::Frag> fr((size_t)KS * NT * 32);
+        for (int ks = 0; ks < KS; ks++)
+            for (int nt = 0; nt < NT; nt++)
+                for (int lane = 0; lane < 32; lane++) {
+                    auto wfun = [&](int k, int nn) -> float { return k < KK ? desc->wf[d.w + (int64_t)k * d.cout + nn] : 0.0f; };
+                    fr[((size_t)ks * NT + nt) * 32 + lane] = gaz_small::host_frag(lane, wfun, ks * 16, nt * 8);
+                }
+        std::vector<float> par((size_t)5 * d.cout);
+        for (int c = 0; c < d.cout; c++) {
+            par[c] = desc->wf[d.bias + c];
+            par[(size_t)d.cout + c] = d.scale_b >= 0 ? desc->wf[d.scale_b + c] : 1.0f;
+            par[(size_t)2 * d.cout + c] = d.shift_b >= 0 ? desc->wf[d.shift_b + c] : 0.0f;
+            par[(size_t)3 * d.cout + c] = d.scale_a >= 0 ? desc->wf[d.scale_a + c] : 1.0f;
+            par[(size_t)4 * d.cout + c] = d.shift_a >= 0 ? desc->wf[d.shift_a + c] : 0.0f;
+        }
+        if (alloc((void **)&op.d_frag, fr.size() * sizeof(gaz_small::Frag)) != 0 || alloc((void **)&op.d_stem_par, par.size() * 4) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(op.d_frag, fr.data(), fr.size() * sizeof(gaz_small::Frag), cudaMemcpyHostToDevice));
+        CKN(cudaMemcpy(op.d_stem_par, par.data(), par.size() * 4, cudaMemcpyHostToDevice));
+        int g0 = 1;
+        while ((g0 * n->P_pad) % 16 != 0) g0++;
+        int G = g0;
+        while ((G + g0) * n->P_pad <= 512) G += g0;    // ~32 m-tiles per iteration: 4 per warp, enough groups to balance the SMs
+        op.head_G = G;
+    }
     CKN(cudaDeviceSynchronize());
     *out = n;
     return 0;
@@ -1352,7 +1054,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); }
+    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); if (op.d_frag) cudaFree(op.d_frag); if (op.d_hbias) cudaFree(op.d_hbias); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
@@ -1471,7 +1173,7 @@ int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
 int gaz_net_launches_per_forward(gaz_net *n) { // kernels actually launched: ops folded into another op's kernel do not count
     if (!n) return 0;
     int k = 0;
-    for (auto &op : n->ops) k += (op.skip || op.in_block || op.dual_skip) ? 0 : 1;
+    for (auto &op : n->ops) k += (op.skip || op.in_block || op.dual_skip || op.chain_skip) ? 0 : 1;
     return k;
 }
 

@@ -147,6 +147,15 @@ int gaz_status(gaz_engine *e); /* sticky error bits: 1 node overflow, 2 slot ove
 int gaz_tree_sizes(gaz_engine *e, int32_t *out);
 int64_t gaz_bytes_allocated(gaz_engine *e);
 
+/* game.augment_sample for a batch of finished trajectories (Self_Play.py:174; Gomoku.py:264-303 and Tictactoe.py:322-358:
+ * the 8 dihedral copies; Connect4.py:427-445: the np.fliplr pair) as a table-driven gather on `device`:
+ *   states_out[a][t][j] = states[t][perm_state[a][j]],  policies_out[a][t][j] = policies[t][perm_policy[a][j]]
+ * for n_pos positions of S = H*W*C state bytes and P policy entries.  The permutation tables are derived by the host from
+ * the game class's own augment_sample (grok_alpha_zero_b200/Self_Play.py:augmentation_tables), so any game plugin's
+ * augmentation that is a pure re-ordering runs here unchanged.  Host buffers in and out; synchronous. */
+int gaz_augment(int device, const int8_t *states, const float *policies, int64_t n_pos, int S, int P, const int32_t *perm_state,
+                const int32_t *perm_policy, int n_aug, int8_t *states_out, float *policies_out);
+
 #ifdef __cplusplus
 }
 #endif

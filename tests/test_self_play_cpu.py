@@ -216,3 +216,55 @@ def test_bench_pools_follow_the_self_play_rule(lib):
         assert sp.limit == cfg["limit"]
         assert (sp.eng.node_cap, sp.eng.slot_cap) == bench.tree_caps(cfg), name
         sp.close()
+
+
+@pytest.mark.parametrize("name", ["tictactoe", "connect4", "gomoku"])
+def test_augmentation_tables_reproduce_the_games_own_method(lib, name):
+    """`gaz_augment` gathers through tables probed from the game class's own `augment_sample`; random trajectories must come
+    out bit-identical to that method (8 dihedral copies for Gomoku / TicTacToe, the np.fliplr pair with its row-flip quirk
+    for Connect4, Connect4.py:441-442)."""
+    from grok_alpha_zero_b200.Self_Play import augmentation_tables, finalize_games
+    cls = {"tictactoe": games.TicTacToe, "connect4": games.Connect4, "gomoku": games.Gomoku}[name]
+    proto = cls()
+    ps, pp = augmentation_tables(proto)
+    S, P = np.asarray(proto.get_input_state()).size, proto.policy_shape[0]
+    assert ps.shape == ({"connect4": 2}.get(name, 8), S) and pp.shape[1] == P
+    assert all(sorted(r) == list(range(S)) for r in ps.tolist()) and all(sorted(r) == list(range(P)) for r in pp.tolist())
+    rng = np.random.default_rng(3)
+    fin = []
+    for gid, T in enumerate((1, 5, 9)):
+        fin.append(dict(game_id=gid, winner=int(rng.integers(-1, 2)), length=T,
+                        states=rng.integers(-1, 2, size=(T,) + np.asarray(proto.get_input_state()).shape).astype(np.int8),
+                        policies=rng.random((T, P), dtype=np.float32), q=rng.random(T, dtype=np.float32) * 2 - 1,
+                        z=np.where(np.arange(T) % 2 == 0, -1.0, 1.0).astype(np.float32)))
+    out = list(finalize_games(proto, fin, lib=lib, chunk_positions=6))     # chunking: 1 + 5 | 9
+    assert [o[0]["game_id"] for o in out] == [0, 1, 2]
+    for g, b, p, v in out:
+        hb, hp, hv = finalize_game(proto, g["states"], g["policies"], g["q"], g["z"], g["winner"])
+        assert b.shape == hb.shape and np.array_equal(b, hb)
+        assert np.array_equal(p.view(np.uint32), np.asarray(hp, np.float32).view(np.uint32))
+        assert np.array_equal(v, hv)
+
+
+def test_streaming_writer_appends_and_resumes(tmp_path):
+    """every add_game reaches the archive at once (nothing but game_stats stays in memory), and a finished archive can be
+    re-opened to append (Self_Play.py:267-272: games_left = games_per_generation - game_stats[2])"""
+    proto = games.TicTacToe()
+    T = 3
+    b = np.zeros((8, T, 3, 3, 2), np.int8)
+    p = np.full((8, T, 9), 1 / 9, np.float32)
+    v = np.zeros((8, T, 1), np.float32)
+    w = ReplayWriter(str(tmp_path))
+    w.add_game(b + 1, p, v, T, -1)
+    assert os.path.getsize(os.path.join(str(tmp_path), "Self_Play_Data.npz")) > 8 * T * 18      # on disk before flush()
+    w.add_game(b + 2, p, v + 0.5, T + 1, 1)
+    w.flush()
+    w2 = ReplayWriter(str(tmp_path))
+    assert w2.games_done() == 2 and w2.n_datasets == 16
+    w2.add_game(b + 3, p, v - 0.5, T, 0)
+    w2.flush()
+    with np.load(os.path.join(str(tmp_path), "Self_Play_Data.npz")) as z:
+        assert len(z.files) == 1 + 3 * 24 and z["game_stats"].tolist() == [T + 1, 3 * T, 3, 1, 1, 1]
+        assert int(z["boards_0"][0, 0, 0, 0]) == 1 and int(z["boards_8"][0, 0, 0, 0]) == 2 and int(z["boards_16"][0, 0, 0, 0]) == 3
+        assert float(z["values_23"][0, 0]) == -0.5
+    assert list(ReplayWriter(str(tmp_path)).data.keys())[:4] == ["game_stats", "boards_0", "policies_0", "values_0"]
