@@ -142,7 +142,7 @@ class SelfPlayBench:
     """Drives the engine the way Self_Play.play does (two PUCT trees per game, the tree of the side to move
     searches, both are re-rooted after the move; one fresh Gumbel tree per move)."""
 
-    def __init__(self, cfg, n_games, device, noise=True):
+    def __init__(self, cfg, n_games, device, noise=True, pool_fraction=1.0):
         from grok_alpha_zero_b200 import netspec
         from grok_alpha_zero_b200.engine import Engine
         from grok_alpha_zero_b200.net import Net
@@ -153,9 +153,12 @@ class SelfPlayBench:
         self.weights = netspec.init_weights(self.spec, seed=0)
         self.flops_per_eval = netspec.flops_per_eval(self.spec)
         node_cap, slot_cap = tree_caps(cfg)
+        # child slots live in an engine-wide page pool (include/gaz_b200.h gaz_config.slot_pool); fraction 1.0 = every tree can
+        # reach its per-tree limit at once, < 1 sizes the pool from the mean occupancy (more games per GPU)
+        slot_pool = 0 if pool_fraction >= 1.0 else int(pool_fraction * n_games * self.tpg * slot_cap)
         self.eng = Engine(cfg["game"], n_games=n_games, mode=cfg["mode"], trees_per_game=self.tpg, node_cap=node_cap,
                           slot_cap=slot_cap, c_puct_init=cfg["c_puct_init"], m=16, c_visit=50.0, c_scale=1.0,
-                          activation_fn="stablemax" if self.gumbel else "softmax", device=device)
+                          activation_fn="stablemax" if self.gumbel else "softmax", device=device, slot_pool=slot_pool)
         self.net = Net(self.spec, self.weights, max_batch=n_games, device=device)
         self.net.attach(self.eng)
         # exploration noise as Self_Play.py:38-69 configures the searches: Dirichlet(alpha) at every PUCT expansion
@@ -430,6 +433,8 @@ def main():
                     help="time M WHOLE moves per game from the start position (search, move choice, do_action, prune_tree / "
                          "re-rooting of both trees) instead of K rounds: positions/s measured directly")
     ap.add_argument("--no-noise", action="store_true", help="searches without Dirichlet / Gumbel exploration noise")
+    ap.add_argument("--pool-fraction", type=float, default=1.0,
+                    help="size of the engine-wide child-slot page pool as a fraction of n_trees * slot_cap (1.0 = static worst case)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the sub-records of the default run (the other BASELINE configurations at N=1, the real generation at N>1)")
     args = ap.parse_args()
@@ -535,7 +540,7 @@ def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
     import torch.distributed as dist
     n_games = args.games or cfg["games"]
 
-    sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise)
+    sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise, pool_fraction=args.pool_fraction)
     sb.start()
     presearch = 0 if args.moves > 0 else args.presearch
     if presearch < 0:
@@ -700,7 +705,8 @@ def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
                              what="per pass: pinned host boards -> gaz_set_games, fresh roots (1 eval each), %d rounds, "
                                   "gaz_root_dense -> host visit counts/value sums/moves; wall clock incl. copies" % args.steps),
                     gpu_launches=int(l1 - l0), clocks=clocks, roofline=roof,
-                    hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()))
+                    hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()),
+                    slot_pool=dict(sb.eng.pool_info(), fraction=args.pool_fraction))
         if want_cpu:
             try:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))

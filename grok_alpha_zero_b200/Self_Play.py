@@ -252,7 +252,7 @@ class BatchedSelfPlay:
 
     def __init__(self, game_class, build_config, train_config, game_ids, n_slots, device=0, evaluator="net",
                  spec=None, weights=None, seed=0, lib=None, hash_salt=0, node_cap=None, slot_cap=None,
-                 use_noise=True):
+                 use_noise=True, slot_pool_fraction=None):
         self.game_class = game_class
         self.proto = game_class()
         self.name = G.game_name_of(self.proto)
@@ -285,8 +285,12 @@ class BatchedSelfPlay:
             if self.gumbel:
                 node_cap = int(self.limit * 1.5) + 2 * L + 64
             slot_cap = node_cap * min(L, 225) + 256 if slot_cap is None else slot_cap
+        # child slots come from an engine-wide page pool; train_config["slot_pool_fraction"] (< 1) sizes it from the mean tree
+        # occupancy instead of the per-tree worst case, so more games fit a GPU (see _relieve_full_pools for the back-stop)
+        frac = slot_pool_fraction if slot_pool_fraction is not None else float(train_config.get("slot_pool_fraction", 1.0))
+        slot_pool = 0 if frac >= 1.0 else int(frac * self.n_slots * self.tpg * slot_cap)
         self.eng = Engine(self.name, n_games=self.n_slots, mode="gumbel" if self.gumbel else "puct",
-                          trees_per_game=self.tpg, node_cap=node_cap, slot_cap=slot_cap,
+                          trees_per_game=self.tpg, node_cap=node_cap, slot_cap=slot_cap, slot_pool=slot_pool,
                           c_puct_init=float(train_config.get("c_puct_init", 2.5)), m=int(train_config.get("m", 16)),
                           c_visit=float(train_config.get("c_visit", 50.0)), c_scale=float(train_config.get("c_scale", 1.0)),
                           activation_fn="stablemax" if stablemax else "softmax", device=device, lib=lib)
@@ -361,6 +365,19 @@ class BatchedSelfPlay:
         mine = sizes[np.arange(self.n_slots), nxt]
         L = 7 if self.name == "connect4" else self.P
         full = cont & ((mine[:, 0] + 2 * self.eff_limit > e.node_cap) | (mine[:, 1] + self.eff_limit * L > e.slot_cap))
+        # shared page pool: the trees about to search must be able to take the pages one more move can need; if the pool is
+        # short the LARGEST kept sub-trees give theirs back (fresh root, counted)
+        pinfo = e.pool_info()
+        if pinfo["pages"] < e.n_trees * pinfo["max_pages_per_tree"]:
+            ps = pinfo["page_slots"]
+            demand = np.where(cont & ~full, -(-(mine[:, 1] + self.eff_limit * L) // ps) - (-(-mine[:, 1] // ps)), 0)
+            short = int(demand.sum()) - pinfo["free"]
+            for s in np.argsort(-mine[:, 1]):
+                if short <= 0:
+                    break
+                if cont[s] and not full[s]:
+                    full[s] = True
+                    short -= int(demand[s]) + int(-(-mine[s, 1] // ps)) - 1
         if not full.any():
             return
         mask = np.zeros((self.n_slots, self.tpg), np.uint8)

@@ -14,7 +14,7 @@ class GazConfig(C.Structure):
     _fields_ = [("game", C.c_int32), ("mode", C.c_int32), ("n_games", C.c_int32), ("trees_per_game", C.c_int32),
                 ("node_cap", C.c_int32), ("slot_cap", C.c_int32), ("device", C.c_int32), ("lut_n", C.c_int32),
                 ("c_puct_init", C.c_float), ("c_puct_base", C.c_float), ("gumbel_m", C.c_int32),
-                ("use_softmax", C.c_int32), ("c_visit", C.c_double), ("c_scale", C.c_double)]
+                ("use_softmax", C.c_int32), ("c_visit", C.c_double), ("c_scale", C.c_double), ("slot_pool", C.c_int64)]
 
 
 # every symbol include/gaz_b200.h declares: name -> (restype, argtypes)
@@ -56,6 +56,7 @@ SYMBOLS = {
     "gaz_status": (C.c_int, [_P]),
     "gaz_tree_sizes": (C.c_int, [_P, _P]),
     "gaz_bytes_allocated": (C.c_int64, [_P]),
+    "gaz_pool_info": (C.c_int, [_P, _P]),
     "gaz_augment": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
 }
 

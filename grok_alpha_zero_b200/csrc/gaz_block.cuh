@@ -53,7 +53,7 @@ using gaz_conv::TILE_ROWS;
 struct BlockArgs {
     const int32_t *count;
     int max_count;
-    int Wp, n_cells, dbg;
+    int Wp, H, P_pad, n_cells, dbg;   // P_pad divides 256: a tile is 256 / P_pad whole boards (Gomoku 1, Connect4 4, TicTacToe 16)
     int nkc1;                 // 64-channel K-blocks of conv1's input (2: C_in = 128, 4: C_in = 256)
     float par1[3 * 128];      // conv1 bias | BN2 scale | BN2 shift          (constant bank, uniform loads)
     float par2[5 * 128];      // conv2 bias | scale_a | shift_a | scale_b | shift_b
@@ -247,7 +247,8 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int pair0 = (int)(blockIdx.x >> 1), pair_step = (int)(gridDim.x >> 1);
     int cnt = *p.count;
     if (cnt > p.max_count) cnt = p.max_count;
-    const int n_tiles = cnt;                      // tile == board
+    const int n_tiles = (int)(((long long)cnt * p.P_pad + TILE_ROWS - 1) / TILE_ROWS);   // a tile = 256 / P_pad whole boards
+    const int bpt = TILE_ROWS / p.P_pad;
     const int n_loop = (n_tiles + 1) / 2;
     const int dbg = p.dbg;
 
@@ -415,7 +416,8 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 const int pos = h * 128 + e1_q * 32 + lane;
-                const bool live = (pos / p.Wp) != 0 && (pos % p.Wp) != p.Wp - 1;
+                const int bp = pos % p.P_pad, yy = bp / p.Wp;
+                const bool live = yy != 0 && yy <= p.H && (bp % p.Wp) != p.Wp - 1 && (2 * lt + rank) * bpt + pos / p.P_pad < cnt;
                 const uint32_t t_sub = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)((it & 1) * 2 * BN + h * BN);
                 e1_half(&acc1_full[h], &e1_done[h], (uint32_t)(it & 1), work, t_sub, par_addr, sH_addr, HALO + pos, live, lane);
             }
@@ -431,9 +433,9 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float *s_part = s_se, *s_mean = s_se + 8 * BN, *s_hp = s_mean + BN, *s_h = s_hp + 256, *s_gate = s_h + 64, *s_bg = s_gate + BN;
         float *s_gp = s_part;
         const float inv_cells = 1.0f / (float)p.n_cells;
-        const int pos = sub * 128 + q * 32 + lane;          // row of the board: the same for every board of this thread
-        const bool live = (pos / p.Wp) != 0 && (pos % p.Wp) != p.Wp - 1;
-        const uint32_t mask = live ? 0xffffffffu : 0u;
+        const int pos = sub * 128 + q * 32 + lane;          // row of the tile: the same for every tile of this thread
+        const int bp = pos % p.P_pad;
+        const bool live_pos = (bp / p.Wp) != 0 && (bp / p.Wp) <= p.H && (bp % p.Wp) != p.Wp - 1;
         const bool use_res = p.res && !(dbg & 8);
         const bool do_se = p.se && !(dbg & 64);
         if (!do_se) { // no gate: out = conv2 + bias (+ residual)
@@ -461,6 +463,8 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float *resp = p.res + rbase;
             float *outp = p.out_raw + rbase;
             const int row0 = t * TILE_ROWS + sub * 128 + q * 32;   // first row of this warp (TMA store coordinate)
+            const bool live = live_pos && t * bpt + pos / p.P_pad < cnt;     // boards past the last one of the batch stay zero
+            const uint32_t mask = live ? 0xffffffffu : 0u;
             float resA[16], resB[16];
             if (use_res) {
 #pragma unroll 1

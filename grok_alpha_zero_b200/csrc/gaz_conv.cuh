@@ -62,7 +62,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_shifted(uint32_t smem_addr, 
 struct BoardConvArgs {
     const int32_t *count;
     int max_count;
-    int P_pad, Wp;
+    int P_pad, Wp, H;         // rows per board (a divisor of 256 or (H+1)*Wp), row pitch W+1, board height: rows of a board beyond
+                              // (H+1)*Wp are dead like the padding row / column
     int taps, kpt;            // filter taps (1 or 9), 64-channel K-blocks per tap
     int base_offset_mode;     // debug bits: 4 = skip the output stores (timing experiment)
     // per-channel parameters travel in the kernel-argument (constant) bank: bias | scale_a | shift_a | scale_b |
@@ -265,7 +266,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const long long row = (long long)t * TILE_ROWS + sub * 128 + q * 32 + lane;
             const int pos = (int)(row % p.P_pad);
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-            const bool live = row < valid_rows && (p.dense || (yy != 0 && xx != p.Wp - 1));
+            const bool live = row < valid_rows && (p.dense || (yy != 0 && yy <= p.H && xx != p.Wp - 1));
             float rnext[32]; // residual of the first output chunk: issued before the accumulator is even ready
             const bool use_res = p.res && !(dbg & 8);
             if (use_res) {

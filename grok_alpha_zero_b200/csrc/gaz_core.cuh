@@ -45,6 +45,9 @@ enum {
     ST_BAD_STATE = 8,
 };
 enum { MAXP = 225, MAXL = 256, MAXNW = 16 };
+// Child-slot storage is PAGED: one pool of PAGE_SLOTS-slot pages per engine, a page table per tree.  A node's block of L <= 256
+// slots never straddles a page, so a block is contiguous in memory; `slot_base` is a VIRTUAL slot index of the tree.
+enum { PAGE_SHIFT = 12, PAGE_SLOTS = 1 << PAGE_SHIFT };
 
 // ------------------------------------------------------------------ records --
 
@@ -87,11 +90,12 @@ struct TreeState {       // 64 B
     int32_t limit;       // effective iteration limit of the current run (0 = idle)
     int32_t pending;     // 1 while a leaf request of this tree is outstanding
     int32_t evals;       // evaluator calls issued by this tree
+    int32_t n_pages;     // slot pages this tree owns (page_table[tree][0 .. n_pages))
     // Gumbel run state (MCTS_Gumbel.py:562-679)
     int32_t g_phase, g_ntop, g_budget, g_cur, g_done_in_child, g_curiter, g_n, g_m;
     int32_t g_state;     // GS_*
     int32_t g_best_slot; // slot of the single survivor once the run is done
-    int32_t pad[6];
+    int32_t pad[5];
 };
 enum { GS_IDLE = 0, GS_HALVE = 1, GS_VISIT = 2, GS_DONE = 3 };
 
@@ -125,6 +129,10 @@ struct View {
     uint32_t *slot_val;
     uint8_t *slot_act;
     uint32_t *slot_child;  // Gumbel only: child node per slot (0xffffffff = None); PUCT reuses slot_val
+    int32_t *page_table;   // [n_trees][max_pages]: physical page of each virtual page of a tree
+    int32_t *free_pages;   // stack of free physical pages, *free_top entries
+    int32_t *free_top;
+    int max_pages, pool_pages;
     TreeState *trees;
     GameState *games;
     int32_t *remap;
@@ -452,8 +460,21 @@ GAZ_HD NodeRec *node_ptr(const View &v, int tree, int n) { return v.nodes + (siz
 GAZ_HD uint32_t *board_ptr(const View &v, int tree, int n) {
     return v.boards + ((size_t)tree * v.node_cap + n) * v.NW;
 }
-GAZ_HD uint32_t *slotv_ptr(const View &v, int tree) { return v.slot_val + (size_t)tree * v.slot_cap; }
-GAZ_HD uint8_t *slota_ptr(const View &v, int tree) { return v.slot_act + (size_t)tree * v.slot_cap; }
+// virtual slot index of a tree -> index into the pooled slot arrays
+GAZ_HD size_t slot_phys(const View &v, int tree, uint32_t vslot) {
+    const int32_t page = v.page_table[(size_t)tree * v.max_pages + (vslot >> PAGE_SHIFT)];
+    return ((size_t)page << PAGE_SHIFT) + (vslot & (PAGE_SLOTS - 1));
+}
+// per-tree views of the pooled arrays, indexed by virtual slot (sv[r.slot_base + i] as before the pool was paged)
+template <class T> struct SlotView {
+    const View *v;
+    T *arr;
+    int tree;
+    GAZ_HD T &operator[](uint32_t vslot) const { return arr[slot_phys(*v, tree, vslot)]; }
+};
+GAZ_HD SlotView<uint32_t> slotv_ptr(const View &v, int tree) { return SlotView<uint32_t>{&v, v.slot_val, tree}; }
+GAZ_HD SlotView<uint8_t> slota_ptr(const View &v, int tree) { return SlotView<uint8_t>{&v, v.slot_act, tree}; }
+GAZ_HD SlotView<uint32_t> slotc_ptr(const View &v, int tree) { return SlotView<uint32_t>{&v, v.slot_child, tree}; }
 
 GAZ_HD float u2f(uint32_t u) {
     float f;
@@ -470,14 +491,14 @@ GAZ_HD uint32_t f2u(float f) {
 // overwrites the prior in slot_val (the prior moves into the child's record); Gumbel: slot_child.
 GAZ_HD int child_at(const View &v, int tree, const NodeRec &r, int i) {
     if (v.gumbel) {
-        uint32_t c = v.slot_child[(size_t)tree * v.slot_cap + r.slot_base + i];
+        uint32_t c = slotc_ptr(v, tree)[r.slot_base + i];
         return c == 0xffffffffu ? -1 : (int)c;
     }
     if (nr_tparent(r) || i < nr_nexp(r)) return (int)slotv_ptr(v, tree)[r.slot_base + i];
     return -1;
 }
 GAZ_HD void set_child(const View &v, int tree, uint32_t slot_base, int i, int child) {
-    if (v.gumbel) v.slot_child[(size_t)tree * v.slot_cap + slot_base + i] = (uint32_t)child;
+    if (v.gumbel) slotc_ptr(v, tree)[slot_base + i] = (uint32_t)child;
     else slotv_ptr(v, tree)[slot_base + i] = (uint32_t)child;
 }
 
@@ -559,11 +580,28 @@ GAZ_HD bool tree_alloc(const CG &cg, const View &v, int tree, int nn, int ns, in
     TreeState &ts = v.trees[tree];
     node0 = ts.n_nodes;
     slot0 = ts.n_slots;
+    if ((slot0 & (PAGE_SLOTS - 1)) + ns > PAGE_SLOTS) slot0 = (slot0 + PAGE_SLOTS - 1) & ~(PAGE_SLOTS - 1);   // blocks never straddle a page
     if (node0 + nn > v.node_cap) { set_status(cg, v, ST_NODE_OVERFLOW); return false; }
     if (slot0 + ns > v.slot_cap) { set_status(cg, v, ST_SLOT_OVERFLOW); return false; }
+    const int need = (slot0 + ns + PAGE_SLOTS - 1) >> PAGE_SHIFT;   // ns <= PAGE_SLOTS: at most one page more than the tree owns
     cg.sync();
-    if (cg.lane == 0) { ts.n_nodes = node0 + nn; ts.n_slots = slot0 + ns; }
+    int ok = 1;
+    if (cg.lane == 0) {
+        if (need > ts.n_pages) {   // take a page from the engine's pool (only pops run concurrently; pages return in k_release)
+#if defined(__CUDA_ARCH__)
+            int idx = atomicSub(v.free_top, 1) - 1;
+            if (idx < 0) { atomicAdd(v.free_top, 1); ok = 0; }
+#else
+            int idx = --(*v.free_top);
+            if (idx < 0) { ++(*v.free_top); ok = 0; }
+#endif
+            if (ok) { v.page_table[(size_t)tree * v.max_pages + ts.n_pages] = v.free_pages[idx]; ts.n_pages++; }
+        }
+        if (ok) { ts.n_nodes = node0 + nn; ts.n_slots = slot0 + ns; }
+    }
+    ok = cg.bcast(ok, 0);
     cg.sync();
+    if (!ok) { set_status(cg, v, ST_SLOT_OVERFLOW); return false; }
     return true;
 }
 
@@ -578,8 +616,8 @@ GAZ_HD int expand_terminal(const CG &cg, const View &v, int tree, int parent, in
     if (!tree_alloc(cg, v, tree, 1 + k, k, n0, s0)) return -1;
     TreeState &ts = v.trees[tree];
     const bool is_root = parent < 0;
-    uint32_t *sv = slotv_ptr(v, tree);
-    uint8_t *sa = slota_ptr(v, tree);
+    auto sv = slotv_ptr(v, tree);
+    auto sa = slota_ptr(v, tree);
     if (cg.lane == 0) {
         NodeRec *T = node_ptr(v, tree, n0);
         T->parent = parent;
@@ -702,7 +740,7 @@ template <class CG> GAZ_HD void puct_select_step(const CG &cg, const View &v, in
     if (ts.limit <= 0 || ts.iter >= ts.limit || ts.pending || ts.root < 0) return;
     int node = ts.root;
     uint32_t N = ts.root_visits;
-    const uint32_t *sv = slotv_ptr(v, tree);
+    const auto sv = slotv_ptr(v, tree);
     NodeRec r = *node_ptr(v, tree, node);
     bool forced = nr_nexp(r) < nr_L(r); // "0 in root.child_visits": MCTS.py:564-570
     for (;;) {
@@ -840,12 +878,12 @@ template <class CG> GAZ_HD void expand_finish(const CG &cg, const View &v, int l
         if (cg.lane == 0) { ts.pending = 0; ts.iter++; }
         return;
     }
-    uint32_t *sv = slotv_ptr(v, tree);
-    uint8_t *sa = slota_ptr(v, tree);
+    auto sv = slotv_ptr(v, tree);
+    auto sa = slota_ptr(v, tree);
     for (int i = cg.lane; i < n; i += cg.width()) {
         sv[s0 + i] = f2u(sc.f[i]);
         sa[s0 + i] = sc.act[i];
-        if (v.gumbel) v.slot_child[(size_t)tree * v.slot_cap + s0 + i] = 0xffffffffu;
+        if (v.gumbel) slotc_ptr(v, tree)[s0 + i] = 0xffffffffu;
     }
     for (int w = cg.lane; w < v.NW; w += cg.width()) board_ptr(v, tree, n0)[w] = L.board[w];
     if (cg.lane == 0) {
@@ -954,9 +992,10 @@ template <class CG> GAZ_HD void compact_tree(const CG &cg, const View &v, int tr
         cg.sync();
     }
     // pass 3: slide slot blocks down, rewriting child indices of the expanded entries
-    uint32_t *sv = slotv_ptr(v, tree);
-    uint8_t *sa = slota_ptr(v, tree);
-    uint32_t *sc_ = v.gumbel ? v.slot_child + (size_t)tree * v.slot_cap : nullptr;
+    auto sv = slotv_ptr(v, tree);
+    auto sa = slota_ptr(v, tree);
+    const auto sc_ = slotc_ptr(v, tree);
+    const bool has_sc = v.gumbel != 0;
     int new_slots = 0;
     for (int n = 0; n < count; n++) {
         NodeRec *r = node_ptr(v, tree, n);
@@ -964,6 +1003,9 @@ template <class CG> GAZ_HD void compact_tree(const CG &cg, const View &v, int tr
         const int old_base = (int)r->slot_base;
         const int nexp = nr_nexp(*r);
         const bool tpar = nr_tparent(*r);
+        // the same no-straddle rule as tree_alloc; packing a sub-sequence of blocks never places one later than before, so
+        // the slide stays in place (write positions <= read positions) and inside the pages the tree already owns
+        if ((new_slots & (PAGE_SLOTS - 1)) + L > PAGE_SLOTS) new_slots = (new_slots + PAGE_SLOTS - 1) & ~(PAGE_SLOTS - 1);
         cg.sync();
         for (int base = 0; base < L; base += W) {
             int i = base + cg.lane;
@@ -972,7 +1014,7 @@ template <class CG> GAZ_HD void compact_tree(const CG &cg, const View &v, int tr
             if (i < L) {
                 val = sv[old_base + i];
                 act = sa[old_base + i];
-                if (sc_) {
+                if (has_sc) {
                     ch = sc_[old_base + i];
                     if (ch != 0xffffffffu) ch = (uint32_t)remap[ch];
                 } else if (tpar || i < nexp) {
@@ -983,7 +1025,7 @@ template <class CG> GAZ_HD void compact_tree(const CG &cg, const View &v, int tr
             if (i < L) {
                 sv[new_slots + i] = val;
                 sa[new_slots + i] = act;
-                if (sc_) sc_[new_slots + i] = ch;
+                if (has_sc) sc_[new_slots + i] = ch;
             }
             cg.sync();
         }
@@ -1004,7 +1046,7 @@ GAZ_HD void prune_step(const CG &cg, const View &v, int tree, int action, int cr
     int found = -1;
     if (!create_new_root && ts.root >= 0) {
         NodeRec r = *node_ptr(v, tree, ts.root);
-        const uint8_t *sa = slota_ptr(v, tree);
+        const auto sa = slota_ptr(v, tree);
         int L = nr_L(r);
         int best = MAXL;
         for (int i = cg.lane; i < L; i += cg.width())
@@ -1062,7 +1104,7 @@ template <class CG> GAZ_HD void softmax_warp(const CG &cg, double *x, int n, flo
 // Loads the per-slot arrays of node r into the scratch.  Returns max visits; *sum_visits = sum.
 template <class CG>
 GAZ_HD uint32_t gumbel_load(const CG &cg, const View &v, int tree, const NodeRec &r, Scratch &sc, uint64_t *sum_visits) {
-    const uint32_t *sv = slotv_ptr(v, tree);
+    const auto sv = slotv_ptr(v, tree);
     int L = nr_L(r);
     uint32_t nb = 0;
     uint64_t s = 0;
@@ -1169,7 +1211,7 @@ template <class CG> GAZ_HD int gumbel_pick(const CG &cg, const View &v, int tree
 template <class CG> GAZ_HD void gumbel_halve(const CG &cg, const View &v, int tree, Scratch &sc) {
     TreeState &ts = v.trees[tree];
     NodeRec r = *node_ptr(v, tree, ts.root);
-    const uint32_t *sv = slotv_ptr(v, tree);
+    const auto sv = slotv_ptr(v, tree);
     uint8_t *ids = v.gm_ids + (size_t)tree * v.gm_cap;
     float *g = v.gm_g + (size_t)tree * v.gm_cap;
     const int m = ts.g_m, n = ts.g_n, phase = ts.g_phase;
@@ -1328,7 +1370,7 @@ template <class CG> GAZ_HD void gumbel_final_pi_dense(const CG &cg, const View &
     uint32_t nb = gumbel_load(cg, v, tree, r, sc, &sv);
     int L = nr_L(r);
     compute_pi_warp(cg, v, L, nb, sv, true, true, sc);
-    const uint8_t *sa = slota_ptr(v, tree);
+    const auto sa = slota_ptr(v, tree);
     for (int i = cg.lane; i < L; i += cg.width()) o[sa[r.slot_base + i]] = sc.f4[i];
     cg.sync();
 }

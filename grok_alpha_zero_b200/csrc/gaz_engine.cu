@@ -126,7 +126,7 @@ GAZ_HD void root_dense_tree(const CG &cg, const View &v, int tree, uint32_t *vis
         return;
     }
     const NodeRec r = *node_ptr(v, tree, ts.root);
-    const uint8_t *sa = slota_ptr(v, tree);
+    const auto sa = slota_ptr(v, tree);
     const int L = nr_L(r);
     uint32_t bestv = 0;
     int besti = L;
@@ -150,6 +150,22 @@ GAZ_HD void root_dense_tree(const CG &cg, const View &v, int tree, uint32_t *vis
         io[2] = ts.iter;
         io[3] = ts.evals;
     }
+}
+
+// Pages a tree owns beyond its allocation cursor go back to the engine's pool (after re-rooting compacted the tree or a
+// fresh root reset it).  Runs as its own pass: inside it pages are only pushed, inside every other kernel only popped.
+GAZ_HD void release_pages(const View &v, int tree) {
+    TreeState &ts = v.trees[tree];
+    const int keep = (ts.n_slots + PAGE_SLOTS - 1) >> PAGE_SHIFT;
+    for (int pg = keep; pg < ts.n_pages; pg++) {
+#if defined(__CUDA_ARCH__)
+        const int pos = atomicAdd(v.free_top, 1);
+#else
+        const int pos = (*v.free_top)++;
+#endif
+        v.free_pages[pos] = v.page_table[(size_t)tree * v.max_pages + pg];
+    }
+    if (ts.n_pages > keep) ts.n_pages = keep;
 }
 
 // Batched upload of live games: cells int8 [n_games][ncell], meta int32 [n_games][4] =
@@ -238,6 +254,10 @@ __global__ void k_remaining(View v, int32_t *counter) {
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, __popc(m));
 }
 __global__ void k_reset_counter(int32_t *c) { *c = 0; }
+__global__ void k_release(View v) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < v.n_trees) release_pages(v, t);
+}
 __global__ void __launch_bounds__(32) k_gumbel_pi(View v, int tree, float *out) {
     __shared__ Scratch sc;
     Coop cg;
@@ -342,7 +362,7 @@ static int read_leaf_count(gaz_engine *e) {
 extern "C" {
 
 const char *gaz_last_error(void) { return g_err.c_str(); }
-int gaz_abi_version(void) { return 1; }
+int gaz_abi_version(void) { return 2; }
 
 int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     if (!cfg || !out) return fail("null argument");
@@ -396,9 +416,23 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     int rc = 0;
     rc |= ealloc(e, &v.nodes, NT * v.node_cap);
     rc |= ealloc(e, &v.boards, NT * v.node_cap * v.NW);
-    rc |= ealloc(e, &v.slot_val, NT * v.slot_cap);
-    rc |= ealloc(e, &v.slot_act, NT * v.slot_cap);
-    if (v.gumbel) rc |= ealloc(e, &v.slot_child, NT * v.slot_cap);
+    // child slots: one pool of pages for the whole engine (gaz_core.cuh); slot_cap is the per-tree VIRTUAL limit.  The default
+    // pool gives every tree its full limit (no sharing risk); cfg->slot_pool sizes it from the expected mean occupancy
+    v.max_pages = (v.slot_cap + PAGE_SLOTS - 1) / PAGE_SLOTS;
+    {
+        int64_t pool = cfg->slot_pool > 0 ? (cfg->slot_pool + PAGE_SLOTS - 1) / PAGE_SLOTS : (int64_t)NT * v.max_pages;
+        if (pool < (int64_t)NT) pool = (int64_t)NT;          // at least one page per tree
+        if (pool > (int64_t)NT * v.max_pages) pool = (int64_t)NT * v.max_pages;
+        if (pool > 0x7fffffff) { delete e; return fail("slot pool of %lld pages is too large", (long long)pool); }
+        v.pool_pages = (int)pool;
+    }
+    const size_t pool_slots = (size_t)v.pool_pages << PAGE_SHIFT;
+    rc |= ealloc(e, &v.slot_val, pool_slots);
+    rc |= ealloc(e, &v.slot_act, pool_slots);
+    if (v.gumbel) rc |= ealloc(e, &v.slot_child, pool_slots);
+    rc |= ealloc(e, &v.page_table, NT * v.max_pages);
+    rc |= ealloc(e, &v.free_pages, (size_t)v.pool_pages);
+    rc |= ealloc(e, &v.free_top, 4);
     rc |= ealloc(e, &v.trees, NT);
     rc |= ealloc(e, &v.games, (size_t)v.n_games);
     rc |= ealloc(e, &v.remap, NT * v.node_cap);
@@ -523,6 +557,13 @@ int gaz_reset_games(gaz_engine *e) {
     for (auto &t : ts) { t.root = -1; t.g_m = e->cfg.gumbel_m; }
     if (h2d(e->v.trees, ts.data(), ts.size() * sizeof(TreeState), e->stream) != 0) return -1;
     if (dev_zero(e->v.leaf_count, sizeof(int32_t), e->stream) != 0) return -1;
+    {   // no tree owns a slot page: the whole pool is free
+        std::vector<int32_t> fp((size_t)e->v.pool_pages);
+        for (int i = 0; i < e->v.pool_pages; i++) fp[(size_t)i] = e->v.pool_pages - 1 - i;   // page 0 is popped first
+        const int32_t top = e->v.pool_pages;
+        if (h2d(e->v.free_pages, fp.data(), fp.size() * sizeof(int32_t), e->stream) != 0) return -1;
+        if (h2d(e->v.free_top, &top, sizeof top, e->stream) != 0) return -1;
+    }
     return stream_sync(e->stream);
 }
 
@@ -566,9 +607,11 @@ int gaz_new_roots(gaz_engine *e, const uint8_t *tree_mask) {
         Coop cg; Scratch sc;
         root_begin(cg, v, t, sc);
     }
+    for (int t = 0; t < v.n_trees; t++) release_pages(v, t);
 #else
     k_reset_counter<<<1, 1, 0, e->stream>>>(v.leaf_count);
     k_new_roots<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, dm);
+    k_release<<<(v.n_trees + 127) / 128, 128, 0, e->stream>>>(v);
     CK(cudaGetLastError());
 #endif
     int nl = read_leaf_count(e);
@@ -688,9 +731,11 @@ int gaz_prune(gaz_engine *e, const int16_t *actions, int create_new_root) {
         Coop cg; Scratch sc;
         prune_step(cg, v, t, e->d_actions[t], create_new_root, sc);
     }
+    for (int t = 0; t < v.n_trees; t++) release_pages(v, t);
 #else
     k_reset_counter<<<1, 1, 0, e->stream>>>(v.leaf_count);
     k_prune<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, e->d_actions, create_new_root);
+    k_release<<<(v.n_trees + 127) / 128, 128, 0, e->stream>>>(v);
     CK(cudaGetLastError());
 #endif
     int nl = read_leaf_count(e);
@@ -711,10 +756,13 @@ int gaz_root_stats(gaz_engine *e, int tree, int16_t *actions, uint32_t *visits, 
     const int L = nr_L(r);
     std::vector<uint32_t> sv((size_t)(L ? L : 1)), sch((size_t)(L ? L : 1));
     std::vector<uint8_t> sa((size_t)(L ? L : 1));
-    if (L > 0) {
-        if (d2h(sv.data(), v.slot_val + (size_t)tree * v.slot_cap + r.slot_base, (size_t)L * 4, e->stream) != 0) return -1;
-        if (d2h(sa.data(), v.slot_act + (size_t)tree * v.slot_cap + r.slot_base, (size_t)L, e->stream) != 0) return -1;
-        if (v.gumbel && d2h(sch.data(), v.slot_child + (size_t)tree * v.slot_cap + r.slot_base, (size_t)L * 4, e->stream) != 0) return -1;
+    if (L > 0) {   // a node's slot block is contiguous inside one page of the pool
+        int32_t page = 0;
+        if (d2h(&page, v.page_table + (size_t)tree * v.max_pages + (r.slot_base >> PAGE_SHIFT), sizeof page, e->stream) != 0) return -1;
+        const size_t off = ((size_t)page << PAGE_SHIFT) + (r.slot_base & (PAGE_SLOTS - 1));
+        if (d2h(sv.data(), v.slot_val + off, (size_t)L * 4, e->stream) != 0) return -1;
+        if (d2h(sa.data(), v.slot_act + off, (size_t)L, e->stream) != 0) return -1;
+        if (v.gumbel && d2h(sch.data(), v.slot_child + off, (size_t)L * 4, e->stream) != 0) return -1;
     }
     int nexp = 0;
     for (int i = 0; i < L; i++) {
@@ -967,6 +1015,14 @@ int gaz_augment(int device, const int8_t *states, const float *policies, int64_t
     if (rc) return done(fail("gaz_augment: %s", cudaGetErrorString(cudaGetLastError())));
     return done(0);
 #endif
+}
+
+int gaz_pool_info(gaz_engine *e, int64_t *out) {
+    if (!e || !out) return fail("null argument");
+    int32_t top = 0;
+    if (d2h(&top, e->v.free_top, sizeof top, e->stream) != 0) return -1;
+    out[0] = e->v.pool_pages; out[1] = top; out[2] = PAGE_SLOTS; out[3] = e->v.max_pages;
+    return 0;
 }
 
 int64_t gaz_bytes_allocated(gaz_engine *e) { return e ? e->bytes : 0; }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) se_kernel(SeArgs p) {
         const float gate = s_gate[c];
         for (int pos = 0; pos < p.P_pad; pos++) {
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
-            const bool live = yy != 0 && xx != p.Wp - 1;
+            const bool live = yy != 0 && yy <= p.H && xx != p.Wp - 1;
             const size_t ob = f32_blk_index(row0 + pos, c, p.C);
             const size_t o = (size_t)(row0 + pos) * p.C + c;
             float v = live ? fmaf(p.c2[ob], gate, p.res[ob]) : 0.0f;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) headconv_mma_kernel(HeadConvArgs p) {
             for (int h = 0; h < 2; h++) {
                 const int pos = mt * 16 + (lane >> 2) + h * 8;
                 const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
-                if (pos >= p.P_pad || yy < 0 || xx >= p.W) continue;
+                if (pos >= p.P_pad || yy < 0 || yy >= p.H || xx >= p.W) continue;
                 const int cell = yy * p.W + xx;
                 const int co = (lane & 3) * 2;           // Cout is even: the channel pair is in or out together
                 if (co >= p.Cout) continue;
@@ -474,7 +474,7 @@ static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *cou
     auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
     gaz_block::BlockArgs a;
     memset(&a, 0, sizeof a);
-    a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.n_cells = n->H * n->W; a.dbg = n->dbg;
+    a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.H = n->H; a.P_pad = n->P_pad; a.n_cells = n->H * n->W; a.dbg = n->dbg;
     a.nkc1 = c1.d.cin / 64;
     memcpy(a.par1, c1.par, sizeof a.par1);   // conv1 bias | BN2 scale | BN2 shift
     memcpy(a.par2, c2.par, sizeof a.par2);
@@ -562,7 +562,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             } else {
                 gaz_conv::BoardConvArgs a;
                 memset(&a, 0, sizeof a);
-                a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp;
+                a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp; a.H = n->H;
                 a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->dbg;
                 const gaz_net_op &o = op.fused_se ? op.se : d; // outputs / residual of the fused SE op
                 memcpy(a.par, op.par, sizeof a.par);
@@ -725,7 +725,11 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     else if (desc->game == GAZ_GAME_CONNECT4) { n->H = 6; n->W = 7; n->Cin = 4; n->P = 7; }
     else { n->H = 15; n->W = 15; n->Cin = 2; n->P = 225; }
     n->Wp = n->W + 1;
+    // rows per board: (H+1) x (W+1) padded positions, rounded up to a divisor of the 256-row tile where possible (Connect4:
+    // 56 -> 64, so a tile is four whole boards and the fused residual-block kernel applies; Gomoku 256, TicTacToe 16); the
+    // extra rows are dead like the padding row and column
     n->P_pad = (n->H + 1) * n->Wp;
+    if (n->P_pad <= 256) { int r = 16; while (r < n->P_pad) r <<= 1; n->P_pad = r; }
     n->max_batch = desc->max_batch;
     n->policy_mode = desc->policy_mode;
     n->device = desc->device;
@@ -879,7 +883,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         }
     }
     // whole-block fusion: conv1 (3x3 C128|C256 -> C128, bf16 out only) directly followed by conv2 (3x3 C128->C128 reading it)
-    if (n->P_pad == gaz_conv::TILE_ROWS && (n->n_sm & ~1) >= 2) {
+    if (gaz_conv::TILE_ROWS % n->P_pad == 0 && (n->n_sm & ~1) >= 2) {   // a tile is a whole number of boards
         for (size_t oi = 0; oi + 1 < n->ops.size(); oi++) {
             NetOp &c1 = n->ops[oi], &c2 = n->ops[oi + 1];
             if (c1.d.type != GAZ_OP_CONV_TC || c2.d.type != GAZ_OP_CONV_TC || c1.block_fused || c1.in_block) continue;

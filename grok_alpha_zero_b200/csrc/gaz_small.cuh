@@ -130,10 +130,13 @@ template <int K, int CIN> __global__ void __launch_bounds__(256, 2) stem_mma_ker
                 const int rr = mt * 16 + g + 8 * h;
                 const int gb = rr / p.P_pad, pos = rr - gb * p.P_pad;
                 const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
-                live[h] = yy >= 0 && xx < p.W && (grp * p.G + gb) < cnt;
+                live[h] = yy >= 0 && yy < p.H && xx < p.W && (grp * p.G + gb) < cnt;
                 base[h] = gb * board_elems + (live[h] ? (yy * WPc + xx) * CIN : 0);
                 grow[h] = (long long)(grp * p.G) * p.P_pad + rr;
             }
+            const bool any_live[2] = {__any_sync(0xffffffffu, live[0]) != 0, __any_sync(0xffffffffu, live[1]) != 0};
+            // blocked fp32 layout (gaz_conv::f32_blk_index): channel 8*nt + 2t of row r sits at rbase + (nt >> 2) * 1024 + (nt & 3) * 256
+            const size_t rbase[2] = {f32_blk_index(grow[0], 2 * t, p.Cout), f32_blk_index(grow[1], 2 * t, p.Cout)};
             for (int nc = 0; nc < NT; nc += 8) {     // 8 n-tiles (64 channels) of accumulators at a time: two CTAs per SM
                 float acc[8][4];
 #pragma unroll
@@ -163,11 +166,17 @@ template <int K, int CIN> __global__ void __launch_bounds__(256, 2) stem_mma_ker
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         if (grow[h] >= total_rows) continue;
+                        if (!any_live[h]) {     // a whole 8-row group of padding (warp-uniform): zeros, no arithmetic
+                            if (p.out_raw) *reinterpret_cast<float2 *>(p.out_raw + rbase[h] + (size_t)((((nc + j) >> 2) << 10) + (((nc + j) & 3) << 8))) = make_float2(0.0f, 0.0f);
+                            if (p.out_q) *reinterpret_cast<uint32_t *>(p.out_q + (size_t)grow[h] * p.Cout + c) = 0u;
+                            if (p.out_a) *reinterpret_cast<uint32_t *>(p.out_a + (size_t)grow[h] * p.Cout + c) = 0u;
+                            continue;
+                        }
                         float v0 = fmaf(sc.x, acc[j][2 * h] + bias.x, sh.x), v1 = fmaf(sc.y, acc[j][2 * h + 1] + bias.y, sh.y);
                         if (p.act == 1) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
                         else if (p.act == 2) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
                         if (!live[h]) { v0 = 0.0f; v1 = 0.0f; }
-                        if (p.out_raw) *reinterpret_cast<float2 *>(p.out_raw + f32_blk_index(grow[h], c, p.Cout)) = make_float2(v0, v1);
+                        if (p.out_raw) *reinterpret_cast<float2 *>(p.out_raw + rbase[h] + (size_t)((((nc + j) >> 2) << 10) + (((nc + j) & 3) << 8))) = make_float2(v0, v1);
                         if (p.out_q) *reinterpret_cast<__nv_bfloat162 *>(p.out_q + (size_t)grow[h] * p.Cout + c) = __floats2bfloat162_rn(v0, v1);
                         if (p.out_a) {
                             const float a0f = live[h] ? fmaxf(fmaf(sa.x, v0, ta.x), 0.0f) : 0.0f, a1f = live[h] ? fmaxf(fmaf(sa.y, v1, ta.y), 0.0f) : 0.0f;
@@ -221,32 +230,48 @@ __global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
         // stage rows [row0 - halo, row0 + G*P_pad + halo) as bf16 hi / lo; padding positions, rows of dead boards and rows
         // outside the tensor become zeros (the fp32 stream may hold don't-care values there)
         const long long row0 = (long long)(grp * p.G) * p.P_pad - halo;
-        for (int i = threadIdx.x; i < srows * CH; i += blockDim.x) {
-            const int pc = i / srows, sr = i - pc * srows;       // consecutive threads: consecutive rows of one 8-channel piece
-            const long long r = row0 + sr;
-            float v[8];
-            bool ok = r >= 0 && r < p.in_rows;
-            if (ok) {
-                const int b = (int)(r / p.P_pad), pos = (int)(r - (long long)b * p.P_pad);
-                ok = b < cnt && pos / p.Wp != 0 && pos % p.Wp != p.Wp - 1;
-            }
-            if (ok) gaz_conv::ldg256(p.in + f32_blk_index(r, pc * 8, p.Cin), v);
-            uint32_t hw[4], lw[4];
+        for (int i0 = threadIdx.x; i0 < srows * CH; i0 += 4 * (int)blockDim.x) {     // four loads in flight per thread
+            float v[4][8];
+            bool ok[4];
+            int pcs[4], srs[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float x0 = ok ? v[2 * e] : 0.0f, x1 = ok ? v[2 * e + 1] : 0.0f;
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * (int)blockDim.x;
+                const int pc = i / srows, sr = i - pc * srows;       // consecutive threads: consecutive rows of one 8-channel piece
+                pcs[u] = pc; srs[u] = sr;
+                const long long r = row0 + sr;
+                ok[u] = i < srows * CH && r >= 0 && r < p.in_rows;
+                if (ok[u]) {
+                    const int b = (int)(r / p.P_pad), pos = (int)(r - (long long)b * p.P_pad);
+                    ok[u] = b < cnt && pos / p.Wp != 0 && pos / p.Wp <= p.H && pos % p.Wp != p.Wp - 1;
+                }
+                if (ok[u]) gaz_conv::ldg256(p.in + f32_blk_index(r, pc * 8, p.Cin), v[u]);
             }
-            const size_t off = (size_t)sr * row_bytes + (size_t)(((pc & ~7) | ((pc ^ sr) & 7)) << 4);
-            *reinterpret_cast<uint4 *>(s_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4 *>(s_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i0 + u * (int)blockDim.x >= srows * CH) continue;
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float x0 = ok[u] ? v[u][2 * e] : 0.0f, x1 = ok[u] ? v[u][2 * e + 1] : 0.0f;
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                    hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                const size_t off = (size_t)srs[u] * row_bytes + (size_t)(((pcs[u] & ~7) | ((pcs[u] ^ srs[u]) & 7)) << 4);
+                *reinterpret_cast<uint4 *>(s_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4 *>(s_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
         }
         __syncthreads();
         for (int mt = warp; mt < n_mt; mt += nwarp) {
-            float acc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
+            // one accumulator per (head, term): six independent MMA chains instead of two chains of three dependent MMAs
+            float ahh[2][4], alh[2][4], ahl[2][4];
+#pragma unroll
+            for (int hd = 0; hd < 2; hd++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) { ahh[hd][e] = 0.0f; alh[hd][e] = 0.0f; ahl[hd][e] = 0.0f; }
             for (int tp = 0; tp < taps; tp++) {
                 const int sr = halo + mt * 16 + a_row + (tp / p.K - kh) * p.Wp + (tp % p.K - kh);
                 const uint32_t rowoff = (uint32_t)(sr * row_bytes);
@@ -261,16 +286,21 @@ __global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
                     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(l0), "=r"(l1), "=r"(l2), "=r"(l3) : "r"(lo_base + coff));
                     const uint4 f0 = fr[ks * 64], f1 = fr[ks * 64 + 32];
-                    mma_bf16_16816(acc[0], h0, h1, h2, h3, f0.x, f0.y);     // hi * hi
-                    mma_bf16_16816(acc[0], l0, l1, l2, l3, f0.x, f0.y);     // lo * hi
-                    mma_bf16_16816(acc[0], h0, h1, h2, h3, f0.z, f0.w);     // hi * lo
+                    mma_bf16_16816(ahh[0], h0, h1, h2, h3, f0.x, f0.y);     // hi * hi
+                    mma_bf16_16816(alh[0], l0, l1, l2, l3, f0.x, f0.y);     // lo * hi
+                    mma_bf16_16816(ahl[0], h0, h1, h2, h3, f0.z, f0.w);     // hi * lo
                     if (p.cout2 > 0) {
-                        mma_bf16_16816(acc[1], h0, h1, h2, h3, f1.x, f1.y);
-                        mma_bf16_16816(acc[1], l0, l1, l2, l3, f1.x, f1.y);
-                        mma_bf16_16816(acc[1], h0, h1, h2, h3, f1.z, f1.w);
+                        mma_bf16_16816(ahh[1], h0, h1, h2, h3, f1.x, f1.y);
+                        mma_bf16_16816(alh[1], l0, l1, l2, l3, f1.x, f1.y);
+                        mma_bf16_16816(ahl[1], h0, h1, h2, h3, f1.z, f1.w);
                     }
                 }
             }
+            float acc[2][4];
+#pragma unroll
+            for (int hd = 0; hd < 2; hd++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[hd][e] = ahh[hd][e] + (alh[hd][e] + ahl[hd][e]);
             // C fragment: acc[.][0..1] = row g, columns 2t, 2t+1; acc[.][2..3] = row g + 8
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -278,7 +308,7 @@ __global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
                 const int gb = rr / p.P_pad, pos = rr - gb * p.P_pad;
                 const int b = grp * p.G + gb;
                 const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
-                if (b >= cnt || yy < 0 || xx >= p.W) continue;
+                if (b >= cnt || yy < 0 || yy >= p.H || xx >= p.W) continue;
                 const int cell = yy * p.W + xx, co = 2 * t;
                 if (co < p.cout1) {
                     float *o = p.out1 + ((size_t)b * ncell + cell) * p.cout1 + co;
@@ -322,6 +352,36 @@ static inline size_t mlp_smem(const MlpArgs &a) {
 // weights of a layer stream through a [MLP_KT][Out] shared-memory tile (the tile is a contiguous piece of the [In][Out]
 // matrix: coalesced loads, the next tile is fetched into registers while the current one is multiplied); a thread owns 4
 // consecutive outputs x `lpg` leaves.  Terms are accumulated in k order.  Requires Out <= 128 (8 prefetch registers).
+template <int LPG>
+__device__ __forceinline__ void mlp_tile(float (&acc)[8][4], const float *s_w, const float *ap0, int kn, int Out, int o0, bool vec) {
+    for (int kk = 0; kk < kn; kk++) {
+        float w4[4];
+        if (vec) {
+            const float4 ww = *reinterpret_cast<const float4 *>(s_w + kk * Out + o0);
+            w4[0] = ww.x; w4[1] = ww.y; w4[2] = ww.z; w4[3] = ww.w;
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) w4[b] = o0 + b < Out ? s_w[kk * Out + o0 + b] : 0.0f;
+        }
+        const float *ap = ap0 + kk * MLP_TL;
+        float av[LPG];
+        if (LPG >= 4) {
+#pragma unroll
+            for (int a = 0; a < LPG; a += 4) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(ap + a);
+                av[a] = t4.x; av[a + 1] = t4.y; av[a + 2] = t4.z; av[a + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < LPG; a++) av[a] = ap[a];
+        }
+#pragma unroll
+        for (int a = 0; a < LPG; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = fmaf(av[a], w4[b], acc[a][b]);
+    }
+}
+
 __global__ void __launch_bounds__(256) mlp_chain_kernel(MlpArgs p) {
     extern __shared__ __align__(16) float s_act[];
     int cnt = *p.count;
@@ -331,17 +391,29 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(MlpArgs p) {
     int mx = 0;
     for (int i = 0; i < p.n_layers; i++) { mx = max(mx, max(p.L[i].In, p.L[i].Out)); }
     float *bufA = s_act, *bufB = s_act + (size_t)mx * MLP_TL, *s_w = s_act + (size_t)2 * mx * MLP_TL;
-    {   // load + pre-activation of the first layer's input: [leaf][In] -> [In][leaf]
+    {   // load + pre-activation of the first layer's input: [leaf][In] -> [In][leaf]; four independent loads in flight per thread
         const MlpLayer &l = p.L[0];
-        for (int i = threadIdx.x; i < l.In * MLP_TL; i += blockDim.x) {
-            const int lf = i / l.In, k = i - lf * l.In;
-            float a = 0.0f;
-            if (leaf0 + lf < cnt) {
-                a = p.in[(size_t)(leaf0 + lf) * l.In + k];
-                if (l.pre_affine) a = fmaf(l.pre_scale[k], a, l.pre_shift[k]);
-                if (l.pre_relu) a = fmaxf(a, 0.0f);
+        const int tot = l.In * MLP_TL;
+        for (int i0 = threadIdx.x; i0 < tot; i0 += 4 * (int)blockDim.x) {
+            float a[4], sc[4], sh[4];
+            int kk[4], lf[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * (int)blockDim.x;
+                lf[u] = i / l.In; kk[u] = i - lf[u] * l.In;
+                const bool ok = i < tot && leaf0 + lf[u] < cnt;
+                a[u] = ok ? p.in[(size_t)(leaf0 + lf[u]) * l.In + kk[u]] : 0.0f;
+                sc[u] = (ok && l.pre_affine) ? l.pre_scale[kk[u]] : 1.0f;
+                sh[u] = (ok && l.pre_affine) ? l.pre_shift[kk[u]] : 0.0f;
             }
-            bufA[k * MLP_TL + lf] = a;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i0 + u * (int)blockDim.x >= tot) continue;
+                float x = l.pre_affine ? fmaf(sc[u], a[u], sh[u]) : a[u];
+                if (l.pre_relu) x = fmaxf(x, 0.0f);
+                if (leaf0 + lf[u] >= cnt) x = 0.0f;
+                bufA[kk[u] * MLP_TL + lf[u]] = x;
+            }
         }
     }
     __syncthreads();
@@ -350,7 +422,8 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(MlpArgs p) {
         const bool last = li + 1 == p.n_layers;
         const int n_o4 = (l.Out + 3) >> 2;                  // threads per leaf group
         const int groups = min((int)blockDim.x / n_o4, MLP_TL);
-        const int lpg = (MLP_TL + groups - 1) / groups;     // leaves per group (<= 8 for Out <= 128)
+        int lpg = (MLP_TL + groups - 1) / groups;           // leaves per group, rounded up to 1 / 2 / 4 / 8 (Out <= 128)
+        lpg = lpg <= 1 ? 1 : (lpg <= 2 ? 2 : (lpg <= 4 ? 4 : 8));
         const int og = threadIdx.x % n_o4, grp = threadIdx.x / n_o4;
         const int o0 = og * 4, lf0 = grp * lpg;
         const bool active = grp < groups && lf0 < MLP_TL;
@@ -380,24 +453,12 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(MlpArgs p) {
             if (k0 + MLP_KT < l.In) fetch(k0 + MLP_KT);
             if (active) {
                 const int kn = min(MLP_KT, l.In - k0);
-                for (int kk = 0; kk < kn; kk++) {
-                    float w4[4];
-                    if (vec) {
-                        const float4 ww = *reinterpret_cast<const float4 *>(s_w + kk * l.Out + o0);
-                        w4[0] = ww.x; w4[1] = ww.y; w4[2] = ww.z; w4[3] = ww.w;
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < 4; b++) w4[b] = o0 + b < l.Out ? s_w[kk * l.Out + o0 + b] : 0.0f;
-                    }
-                    const float *ap = bufA + (k0 + kk) * MLP_TL + lf0;
-#pragma unroll
-                    for (int a = 0; a < 8; a++) {
-                        if (a < lpg && lf0 + a < MLP_TL) {
-                            const float av = ap[a];
-#pragma unroll
-                            for (int b = 0; b < 4; b++) acc[a][b] = fmaf(av, w4[b], acc[a][b]);
-                        }
-                    }
+                const float *ap0 = bufA + k0 * MLP_TL + lf0;
+                switch (lpg) {     // static trip counts: the generic predicated form spent 6x the useful instructions
+                case 1: mlp_tile<1>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                case 2: mlp_tile<2>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                case 4: mlp_tile<4>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                default: mlp_tile<8>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
                 }
             }
             __syncthreads();

@@ -37,7 +37,7 @@ def default_caps(game, iters, mode="puct"):
 class Engine:
     def __init__(self, game, n_games=1, mode="puct", trees_per_game=1, node_cap=None, slot_cap=None,
                  c_puct_init=2.5, c_puct_base=19652.0, m=16, c_visit=50.0, c_scale=0.1, activation_fn="softmax",
-                 device=0, lut_n=1 << 20, iters_hint=1200, lib=None):
+                 device=0, lut_n=1 << 20, iters_hint=1200, lib=None, slot_pool=0):
         self.lib = lib if lib is not None else _lib.load()
         self.game = game
         self.H, self.W, self.C, self.P = DIMS[game]
@@ -51,7 +51,7 @@ class Engine:
             slot_cap = slot_cap or sc
         cfg = _lib.GazConfig(GAMES[game], 1 if mode == "gumbel" else 0, n_games, trees_per_game, node_cap, slot_cap,
                              device, lut_n, c_puct_init, c_puct_base, m, int(activation_fn == "softmax"),
-                             c_visit, c_scale)
+                             c_visit, c_scale, int(slot_pool))
         self.node_cap, self.slot_cap = int(node_cap), int(slot_cap)
         h = C.c_void_p()
         self._h = None
@@ -240,6 +240,12 @@ class Engine:
         out = np.zeros((self.n_trees, 2), dtype=np.int32)
         self._ck(self.lib.gaz_tree_sizes(self._h, _p(out)))
         return out
+
+    def pool_info(self):
+        """slot page pool: dict(pages, free, page_slots, max_pages_per_tree)"""
+        out = np.zeros(4, dtype=np.int64)
+        self._ck(self.lib.gaz_pool_info(self._h, _p(out)))
+        return dict(pages=int(out[0]), free=int(out[1]), page_slots=int(out[2]), max_pages_per_tree=int(out[3]))
 
     def bytes_allocated(self):
         return int(self.lib.gaz_bytes_allocated(self._h))

@@ -250,15 +250,21 @@ class Net:
         # (type, cin, cout, ksize, tag): tag "se" = convolution whose epilogue carries the following SE op; "block" = conv1
         # that runs the whole residual block (conv1 + conv2 + SE + skip, gaz_block.cuh) and "inblock" = the conv2 it absorbed.
         # Mirrors the fusion rules of gaz_net_create (csrc/gaz_net.cu).
-        tile_is_board = (spec["H"] + 1) * (spec["W"] + 1) == 256
-        fuse_block = True
+        p_pad = (spec["H"] + 1) * (spec["W"] + 1)       # rows per board, rounded up to a divisor of the 256-row tile (gaz_net_create)
+        if p_pad <= 256:
+            r = 16
+            while r < p_pad:
+                r <<= 1
+            p_pad = r
+        tile_is_board = p_pad == 256
+        fuse_block = 256 % p_pad == 0
         self._op_shapes = []
         for i, o in enumerate(b.ops):
             tag = ""
             if o["type"] == OP_CONV_TC and i + 1 < len(b.ops) and b.ops[i + 1]["type"] == OP_SE and tile_is_board:
                 tag = "se"
             self._op_shapes.append([o["type"], o["cin"], o["cout"], o["ksize"], tag])
-        if tile_is_board and fuse_block:
+        if fuse_block:
             for i in range(len(b.ops) - 1):
                 o, o2 = b.ops[i], b.ops[i + 1]
                 if o["type"] == OP_CONV_TC and o2["type"] == OP_CONV_TC and (o["cin"], o["cout"], o["ksize"]) in ((128, 128, 3), (256, 128, 3)) and \

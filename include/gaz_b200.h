@@ -32,7 +32,7 @@ typedef struct gaz_config {
     int32_t n_games;         /* concurrent games (Self_Play.py:346-363 runs one per process) */
     int32_t trees_per_game;  /* 2 = mcts1/mcts2 of Self_Play.py:39-57, 1 = a single MCTS     */
     int32_t node_cap;        /* nodes per tree                                               */
-    int32_t slot_cap;        /* child slots per tree                                         */
+    int32_t slot_cap;        /* child slots per tree (virtual limit; storage is paged, see slot_pool) */
     int32_t device;          /* CUDA device ordinal                                          */
     int32_t lut_n;           /* entries of the host-built C(N) table (MCTS.py:181-182)       */
     float c_puct_init;       /* MCTS.py:82  */
@@ -41,6 +41,10 @@ typedef struct gaz_config {
     int32_t use_softmax;     /* activation_fn == "softmax" (MCTS_Gumbel.py:162,185) */
     double c_visit;          /* MCTS_Gumbel.py:160 */
     double c_scale;          /* MCTS_Gumbel.py:161 */
+    int64_t slot_pool;       /* child slots in the engine-wide page pool; 0 = n_trees * slot_cap (every tree can reach its
+                              * limit at once).  The reference's trees are unbounded Python objects (MCTS.py:20-72); here a
+                              * tree takes 4096-slot pages from one pool as it grows and returns them when prune_tree
+                              * compacts it, so the pool can be sized from the MEAN tree occupancy, not the worst case. */
 } gaz_config;
 
 const char *gaz_last_error(void);
@@ -145,6 +149,8 @@ int gaz_status(gaz_engine *e); /* sticky error bits: 1 node overflow, 2 slot ove
  * gaz_config.node_cap / slot_cap.  The reference's trees are unbounded Python objects (MCTS.py:20-72); a host driver
  * uses this after gaz_prune to give a tree that could not hold one more move's search a fresh root instead. */
 int gaz_tree_sizes(gaz_engine *e, int32_t *out);
+/* the slot page pool: out[0] pages in the pool, out[1] pages free now, out[2] slots per page, out[3] page-table entries per tree */
+int gaz_pool_info(gaz_engine *e, int64_t *out);
 int64_t gaz_bytes_allocated(gaz_engine *e);
 
 /* game.augment_sample for a batch of finished trajectories (Self_Play.py:174; Gomoku.py:264-303 and Tictactoe.py:322-358:
