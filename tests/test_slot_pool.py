@@ -69,3 +69,18 @@ def test_pool_size_does_not_change_results_emulated():
 @pytest.mark.gpu
 def test_pool_size_does_not_change_results_cuda():
     check_pool_independence(None)
+
+
+@pytest.mark.gpu
+def test_cuda_equals_the_width_1_emulation_through_prune_tree():
+    """compute-sanitizer is not available on the pool, and the CPU suite runs the warp code with a
+    cooperative width of 1, where lane races cannot exist.  This is the lane-race self-check for `compact_tree` and the
+    scratch reuse: twelve trees searched, re-rooted (in-place compaction: the read - sync - write chunks) and searched again
+    on the GPU, 32 lanes per tree and four trees per CTA, must equal the width-1 emulation bit for bit at every move."""
+    import emul_lib
+    cuda = play(None, 0, n_games=7, moves=4)
+    emul = play(emul_lib.load(), 0, n_games=7, moves=4)
+    assert cuda[2] == 0 and emul[2] == 0
+    for a, b in zip(cuda[0], emul[0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2], b[2])
+    assert np.array_equal(cuda[3], emul[3]) and cuda[1] == emul[1]        # tree sizes and the pool's free-page history
