@@ -142,7 +142,7 @@ class SelfPlayBench:
     """Drives the engine the way Self_Play.play does (two PUCT trees per game, the tree of the side to move
     searches, both are re-rooted after the move; one fresh Gumbel tree per move)."""
 
-    def __init__(self, cfg, n_games, device, noise=True, pool_fraction=1.0):
+    def __init__(self, cfg, n_games, device, noise=True, pool_fraction=1.0, eval_cache=0):
         from grok_alpha_zero_b200 import netspec
         from grok_alpha_zero_b200.engine import Engine
         from grok_alpha_zero_b200.net import Net
@@ -159,6 +159,8 @@ class SelfPlayBench:
         self.eng = Engine(cfg["game"], n_games=n_games, mode=cfg["mode"], trees_per_game=self.tpg, node_cap=node_cap,
                           slot_cap=slot_cap, c_puct_init=cfg["c_puct_init"], m=16, c_visit=50.0, c_scale=1.0,
                           activation_fn="stablemax" if self.gumbel else "softmax", device=device, slot_pool=slot_pool)
+        if eval_cache > 0:   # parity-safe evaluation dedup (per-game scope): OFF for the headline, reported separately
+            self.eng.enable_eval_cache(eval_cache, shared=False)
         self.net = Net(self.spec, self.weights, max_batch=n_games, device=device)
         self.net.attach(self.eng)
         # exploration noise as Self_Play.py:38-69 configures the searches: Dirichlet(alpha) at every PUCT expansion
@@ -178,6 +180,8 @@ class SelfPlayBench:
         self.alive = np.ones(n_games, bool)
         self.launches = 0
         self.per_round_launches = 3 + 1 + self.net.n_launches  # counter reset, select, expand + chunk count + network kernels
+        if eval_cache > 0:
+            self.per_round_launches += 2                       # cache look-up and fill passes
 
     # ---- Self_Play.play pieces -------------------------------------------------------------
     def start(self):
@@ -253,8 +257,9 @@ class SelfPlayBench:
         return int(sel[self.alive, 2].sum())
 
     def evals_total(self):
+        """evaluations the NETWORK performed: leaf requests minus the evaluation-cache hits"""
         _, _, info = self.eng.root_dense(want_values=False)
-        return int(info[:, 3].astype(np.int64).sum())
+        return int(info[:, 3].astype(np.int64).sum()) - self.eng.eval_cache_stats()["hits"]
 
     def total_sims(self):
         return self.sims_done + self.sims_in_flight()
@@ -433,6 +438,8 @@ def main():
                     help="time M WHOLE moves per game from the start position (search, move choice, do_action, prune_tree / "
                          "re-rooting of both trees) instead of K rounds: positions/s measured directly")
     ap.add_argument("--no-noise", action="store_true", help="searches without Dirichlet / Gumbel exploration noise")
+    ap.add_argument("--eval-cache", type=int, default=0,
+                    help="entries of the device-side evaluation cache (per-game scope; 0 = off, the default and the headline)")
     ap.add_argument("--pool-fraction", type=float, default=1.0,
                     help="size of the engine-wide child-slot page pool as a fraction of n_trees * slot_cap (1.0 = static worst case)")
     ap.add_argument("--no-extras", action="store_true",
@@ -471,6 +478,15 @@ def main():
                                   net_frac_of_sustained_peak=sub["net_tflops"] / peaks["sustained"],
                                   roofline=dict((k, sub["roofline"][k]) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel")) if sub["roofline"] else None,
                                   clocks=sub["clocks"], gpu_launches=sub["gpu_launches"])
+            # the parity-safe evaluation cache (Session_Cache's role, per-game scope) on Connect4, where transpositions are
+            # common; the headline and the sub-records above run without it
+            a3 = argparse.Namespace(**vars(args))
+            a3.steps, a3.warmup, a3.games, a3.presearch, a3.config, a3.eval_cache = 200, 3, 0, 600, "connect4", 1 << 23
+            sub = measure(a3, dict(CONFIGS["connect4"]), world, rank, local, peaks, want_cpu=False, full=False)
+            subs["connect4_eval_cache"] = dict(workload=sub["config"]["workload"] + ", evaluation cache of 2^23 entries (per game)",
+                                               value=sub["value"], ms_per_step=sub["ms_per_step"], steps=sub["steps"],
+                                               presearch_rounds=600, sims_per_eval=sub["sims_per_eval"], nn_evals_per_s=sub["nn_evals_per_s"],
+                                               eval_cache=sub["eval_cache"], positions_per_s=sub["positions_per_s"])
             if rank == 0:
                 line["configs"] = subs
         else:               # multi-GPU: a short REAL generation with the NCCL trajectory gather and the writer inside the wall clock
@@ -540,7 +556,7 @@ def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
     import torch.distributed as dist
     n_games = args.games or cfg["games"]
 
-    sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise, pool_fraction=args.pool_fraction)
+    sb = SelfPlayBench(cfg, n_games, local, noise=not args.no_noise, pool_fraction=args.pool_fraction, eval_cache=args.eval_cache)
     sb.start()
     presearch = 0 if args.moves > 0 else args.presearch
     if presearch < 0:
@@ -706,7 +722,10 @@ def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
                                   "gaz_root_dense -> host visit counts/value sums/moves; wall clock incl. copies" % args.steps),
                     gpu_launches=int(l1 - l0), clocks=clocks, roofline=roof,
                     hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()),
-                    slot_pool=dict(sb.eng.pool_info(), fraction=args.pool_fraction))
+                    slot_pool=dict(sb.eng.pool_info(), fraction=args.pool_fraction),
+                    eval_cache=(dict(sb.eng.eval_cache_stats(), scope="per game",
+                                     note="hits are leaf requests served from the table; nn_evals_per_s / net_tflops / sims_per_eval "
+                                          "count only what the network evaluated") if args.eval_cache > 0 else None))
         if want_cpu:
             try:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))

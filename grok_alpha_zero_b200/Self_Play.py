@@ -294,6 +294,10 @@ class BatchedSelfPlay:
                           c_puct_init=float(train_config.get("c_puct_init", 2.5)), m=int(train_config.get("m", 16)),
                           c_visit=float(train_config.get("c_visit", 50.0)), c_scale=float(train_config.get("c_scale", 1.0)),
                           activation_fn="stablemax" if stablemax else "softmax", device=device, lib=lib)
+        # train_config["eval_cache_entries"] > 0: device-side evaluation cache (what max_cache_depth / Session_Cache.Cache_Wrapper
+        # are to the reference, Self_Play.py:233-235); "eval_cache_shared": one table for all games instead of per-game entries
+        if int(train_config.get("eval_cache_entries", 0) or 0) > 0:
+            self.eng.enable_eval_cache(int(train_config["eval_cache_entries"]), shared=bool(train_config.get("eval_cache_shared", False)))
         self.net = None
         if evaluator == "net":
             from .net import Net
@@ -534,6 +538,10 @@ def gather_games(finished, device=None, stats=None):
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cpu") if device is None else torch.device(device)
     buf = torch.from_numpy(pack_games(finished).copy()).to(dev)
+    # the first gather on a process group builds its point-to-point channels (~0.1 s): a one-byte gather takes that hit so
+    # that `collective_s` times the payload exchange
+    warm = torch.zeros(1, dtype=torch.uint8, device=dev)
+    dist.gather(warm, gather_list=[torch.zeros(1, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None, dst=0)
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
     t0 = time.perf_counter()

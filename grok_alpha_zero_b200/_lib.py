@@ -57,6 +57,8 @@ SYMBOLS = {
     "gaz_tree_sizes": (C.c_int, [_P, _P]),
     "gaz_bytes_allocated": (C.c_int64, [_P]),
     "gaz_pool_info": (C.c_int, [_P, _P]),
+    "gaz_eval_cache_enable": (C.c_int, [_P, C.c_int64, C.c_int]),
+    "gaz_eval_cache_stats": (C.c_int, [_P, _P]),
     "gaz_augment": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
 }
 

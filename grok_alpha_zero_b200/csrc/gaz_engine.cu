@@ -45,15 +45,17 @@ GAZ_HD uint64_t mix64(uint64_t z) {
 }
 #define GAZ_GOLD 0x9E3779B97F4A7C15ULL
 
-template <class CG> GAZ_HD void hash_eval_leaf(const CG &cg, const View &v, int leaf, uint64_t salt, int logits) {
+template <class CG>
+GAZ_HD void hash_eval_leaf(const CG &cg, const View &v, int leaf, uint64_t salt, int logits, const int8_t *states, float *policy,
+                           float *value) {
     const int n = v.ncell * v.C;
-    const int8_t *st = v.leaf_state + (size_t)leaf * n;
+    const int8_t *st = states + (size_t)leaf * n;
     uint64_t acc = 0;
     for (int i = cg.lane; i < n; i += cg.width())
         acc += (uint64_t)(int64_t)(st[i] + 2) * mix64((uint64_t)(i + 1) * GAZ_GOLD);
     acc = cg.sum64(acc);
     uint64_t h0 = mix64(acc + salt * 0xD1B54A32D192ED03ULL);
-    float *pol = v.policy + (size_t)leaf * v.P;
+    float *pol = policy + (size_t)leaf * v.P;
     for (int i = cg.lane; i < v.P; i += cg.width()) {
         uint64_t r = mix64(h0 + (uint64_t)(i + 1) * GAZ_GOLD);
         uint32_t k = (uint32_t)(((r >> 52) << 8) | (uint64_t)i) + 1u;
@@ -61,8 +63,111 @@ template <class CG> GAZ_HD void hash_eval_leaf(const CG &cg, const View &v, int 
     }
     if (cg.lane == 0) {
         uint64_t rv = mix64(h0 + 0x5851F42D4C957F2DULL);
-        v.value[leaf] = (float)(rv >> 40) * 0x1p-23f - 1.0f;
+        value[leaf] = (float)(rv >> 40) * 0x1p-23f - 1.0f;
     }
+}
+
+// ---- evaluation cache ----------------------------------------------------------------------------------------
+struct CacheView {
+    long long entries;
+    int scope, S, P;
+    int8_t *state;
+    unsigned long long *tag;
+    float *pol, *val;
+    int32_t *claim, *miss_idx, *miss_count;
+    int8_t *packed_state;
+    float *packed_pol, *packed_val;
+    unsigned long long *stats;
+    int epoch;
+};
+template <class CG> GAZ_HD unsigned long long cache_hash(const CG &cg, const View &v, const CacheView &c, int leaf) {
+    const int8_t *st = v.leaf_state + (size_t)leaf * c.S;
+    uint64_t acc = 0;
+    for (int i = cg.lane; i < c.S; i += cg.width())
+        acc += (uint64_t)(int64_t)(st[i] + 2) * mix64((uint64_t)(i + 1) * 0xC2B2AE3D27D4EB4FULL);
+    acc = cg.sum64(acc);
+    if (c.scope == 0) {   // per game: positions of different games never share an entry
+        const int tree = v.leaves[leaf].tree;
+        const uint64_t gkey = v.tree_keys ? v.tree_keys[tree] / (uint64_t)v.trees_per_game : (uint64_t)(tree / v.trees_per_game);
+        acc += mix64(gkey + 0x9E3779B97F4A7C15ULL);
+    }
+    return mix64(acc) | 0x8000000000000000ULL;
+}
+// one leaf request: hit -> outputs copied to the leaf's slots; miss -> appended to the packed list the evaluator serves
+template <class CG> GAZ_HD void cache_lookup_leaf(const CG &cg, const View &v, const CacheView &c, int leaf) {
+    const unsigned long long h = cache_hash(cg, v, c, leaf);
+    const long long slot = (long long)(h % (unsigned long long)c.entries);
+    const int8_t *st = v.leaf_state + (size_t)leaf * c.S;
+    bool same = c.tag[slot] == h;
+    if (same) {   // the full state decides: a hash collision can never return another position's outputs
+        const int8_t *cs = c.state + (size_t)slot * c.S;
+        int diff = 0;
+        for (int i = cg.lane; i < c.S; i += cg.width()) diff |= cs[i] != st[i];
+        same = cg.sum(diff) == 0;
+    }
+    if (same) {
+        const float *cp = c.pol + (size_t)slot * c.P;
+        float *po = v.policy + (size_t)leaf * c.P;
+        for (int i = cg.lane; i < c.P; i += cg.width()) po[i] = cp[i];
+        if (cg.lane == 0) v.value[leaf] = c.val[slot];
+    } else {
+        int m = 0;
+        if (cg.lane == 0) {
+#if defined(__CUDA_ARCH__)
+            m = atomicAdd(c.miss_count, 1);
+#else
+            m = (*c.miss_count)++;
+#endif
+            c.miss_idx[m] = leaf;
+        }
+        m = cg.bcast(m, 0);
+        int8_t *ps = c.packed_state + (size_t)m * c.S;
+        for (int i = cg.lane; i < c.S; i += cg.width()) ps[i] = st[i];
+    }
+    if (cg.lane == 0) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(c.stats, 1ULL);
+        if (same) atomicAdd(c.stats + 1, 1ULL);
+#else
+        c.stats[0]++;
+        if (same) c.stats[1]++;
+#endif
+    }
+}
+// packed miss m: results back to its leaf, and into the table (one writer per slot and pass: the first to claim it)
+template <class CG> GAZ_HD void cache_fill_miss(const CG &cg, const View &v, const CacheView &c, int m) {
+    const int leaf = c.miss_idx[m];
+    const float *pp = c.packed_pol + (size_t)m * c.P;
+    float *po = v.policy + (size_t)leaf * c.P;
+    for (int i = cg.lane; i < c.P; i += cg.width()) po[i] = pp[i];
+    if (cg.lane == 0) v.value[leaf] = c.packed_val[m];
+    const unsigned long long h = cache_hash(cg, v, c, leaf);
+    const long long slot = (long long)(h % (unsigned long long)c.entries);
+    int mine = 0;
+    if (cg.lane == 0) {
+#if defined(__CUDA_ARCH__)
+        mine = atomicExch(c.claim + slot, c.epoch) != c.epoch;
+#else
+        mine = c.claim[slot] != c.epoch;
+        c.claim[slot] = c.epoch;
+#endif
+    }
+    mine = cg.bcast(mine, 0);
+    if (!mine) return;
+    const int8_t *st = v.leaf_state + (size_t)leaf * c.S;
+    int8_t *cs = c.state + (size_t)slot * c.S;
+    float *cp = c.pol + (size_t)slot * c.P;
+    for (int i = cg.lane; i < c.S; i += cg.width()) cs[i] = st[i];
+    for (int i = cg.lane; i < c.P; i += cg.width()) cp[i] = pp[i];
+    cg.sync();
+    if (cg.lane == 0) { c.val[slot] = c.packed_val[m]; c.tag[slot] = h; }
+}
+static CacheView cache_view(const gaz_eval_cache *c) {
+    CacheView cv;
+    cv.entries = c->entries; cv.scope = c->scope; cv.S = c->S; cv.P = c->P; cv.state = c->state; cv.tag = c->tag; cv.pol = c->pol;
+    cv.val = c->val; cv.claim = c->claim; cv.miss_idx = c->miss_idx; cv.miss_count = c->miss_count; cv.packed_state = c->packed_state;
+    cv.packed_pol = c->packed_pol; cv.packed_val = c->packed_val; cv.stats = c->stats; cv.epoch = c->epoch;
+    return cv;
 }
 
 // Start of run(): budget rules MCTS.py:542-546 / MCTS_Gumbel.py:570-599
@@ -214,11 +319,24 @@ __global__ void __launch_bounds__(THREADS) k_expand(View v) {
     WARP_PROLOGUE(*v.leaf_count)
     expand_finish(cg, v, widx, sc);
 }
-__global__ void __launch_bounds__(THREADS) k_hash_eval(View v, uint64_t salt, int logits) {
+__global__ void __launch_bounds__(THREADS) k_hash_eval(View v, uint64_t salt, int logits, const int32_t *count, const int8_t *states,
+                                                       float *policy, float *value) {
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= *count) return;
+    Coop cg;
+    hash_eval_leaf(cg, v, widx, salt, logits, states, policy, value);
+}
+__global__ void __launch_bounds__(THREADS) k_cache_lookup(View v, CacheView c) {
     const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (widx >= *v.leaf_count) return;
     Coop cg;
-    hash_eval_leaf(cg, v, widx, salt, logits);
+    cache_lookup_leaf(cg, v, c, widx);
+}
+__global__ void __launch_bounds__(THREADS) k_cache_fill(View v, CacheView c) {
+    const int widx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (widx >= *c.miss_count) return;
+    Coop cg;
+    cache_fill_miss(cg, v, c, widx);
 }
 __global__ void __launch_bounds__(THREADS) k_new_roots(View v, const uint8_t *mask) {
     WARP_PROLOGUE(v.n_trees)
@@ -341,13 +459,44 @@ static int launch_expand(gaz_engine *e) {
 #endif
     return 0;
 }
-static int launch_hash(gaz_engine *e, uint64_t salt, int logits) {
+int gaz_internal_cache_lookup(gaz_engine *e) {
+    gaz_eval_cache *c = e->cache;
+    if (dev_zero(c->miss_count, sizeof(int32_t), e->stream) != 0) return -1;
+    const CacheView cv = cache_view(c);
 #ifdef GAZ_EMUL
-    for (int l = 0; l < *e->v.leaf_count; l++) { Coop cg; hash_eval_leaf(cg, e->v, l, salt, logits); }
+    for (int l = 0; l < *e->v.leaf_count; l++) { Coop cg; cache_lookup_leaf(cg, e->v, cv, l); }
 #else
-    k_hash_eval<<<grid_warps(e->v.n_trees), THREADS, 0, e->stream>>>(e->v, salt, logits);
+    k_cache_lookup<<<grid_warps(e->v.n_trees), THREADS, 0, e->stream>>>(e->v, cv);
     CK(cudaGetLastError());
 #endif
+    return 0;
+}
+int gaz_internal_cache_fill(gaz_engine *e) {
+    gaz_eval_cache *c = e->cache;
+    c->epoch++;
+    const CacheView cv = cache_view(c);
+#ifdef GAZ_EMUL
+    for (int m = 0; m < *c->miss_count; m++) { Coop cg; cache_fill_miss(cg, e->v, cv, m); }
+#else
+    k_cache_fill<<<grid_warps(e->v.n_trees), THREADS, 0, e->stream>>>(e->v, cv);
+    CK(cudaGetLastError());
+#endif
+    return 0;
+}
+static int launch_hash(gaz_engine *e, uint64_t salt, int logits) {
+    const View &v = e->v;
+    gaz_eval_cache *c = e->cache;
+    if (c && gaz_internal_cache_lookup(e) != 0) return -1;
+    const int32_t *count = c ? c->miss_count : v.leaf_count;
+    const int8_t *states = c ? c->packed_state : v.leaf_state;
+    float *pol = c ? c->packed_pol : v.policy, *val = c ? c->packed_val : v.value;
+#ifdef GAZ_EMUL
+    for (int l = 0; l < *count; l++) { Coop cg; hash_eval_leaf(cg, v, l, salt, logits, states, pol, val); }
+#else
+    k_hash_eval<<<grid_warps(v.n_trees), THREADS, 0, e->stream>>>(v, salt, logits, count, states, pol, val);
+    CK(cudaGetLastError());
+#endif
+    if (c && gaz_internal_cache_fill(e) != 0) return -1;
     return 0;
 }
 int gaz_internal_launch_select(gaz_engine *e) { return launch_select(e); }
@@ -382,6 +531,7 @@ int gaz_create(const gaz_config *cfg, gaz_engine **out) {
     e->cfg = *cfg;
     e->bytes = 0;
     e->net = nullptr;
+    e->cache = nullptr;
     e->leaf_bound = 0;
     e->round_graph = nullptr; e->round_graph_net = nullptr; e->round_graph_chunks = 0; e->round_graph_warm = 0;
     e->view_epoch = 0; e->round_graph_epoch = 0;
@@ -475,6 +625,7 @@ void gaz_destroy(gaz_engine *e) {
     if (e->round_graph) cudaGraphExecDestroy((cudaGraphExec_t)e->round_graph);
 #endif
     for (void *p : e->allocs) dev_free(p);
+    delete e->cache;
 #ifndef GAZ_EMUL
     if (e->ev0) { cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); }
     cudaStreamDestroy(e->stream);
@@ -1015,6 +1166,43 @@ int gaz_augment(int device, const int8_t *states, const float *policies, int64_t
     if (rc) return done(fail("gaz_augment: %s", cudaGetErrorString(cudaGetLastError())));
     return done(0);
 #endif
+}
+
+int gaz_eval_cache_enable(gaz_engine *e, int64_t entries, int shared_scope) {
+    if (!e) return fail("null engine");
+    if (e->cache) return fail("the evaluation cache is already enabled");
+    if (entries < 1024) return fail("evaluation cache: at least 1024 entries");
+    const View &v = e->v;
+    gaz_eval_cache *c = new gaz_eval_cache();
+    memset(c, 0, sizeof *c);
+    c->entries = entries; c->scope = shared_scope ? 1 : 0; c->S = v.ncell * v.C; c->P = v.P; c->epoch = 0;
+    const size_t NT = (size_t)v.n_trees, E = (size_t)entries;
+    int rc = 0;
+    rc |= ealloc(e, &c->state, E * c->S);
+    rc |= ealloc(e, &c->tag, E);
+    rc |= ealloc(e, &c->pol, E * c->P);
+    rc |= ealloc(e, &c->val, E);
+    rc |= ealloc(e, &c->claim, E);
+    rc |= ealloc(e, &c->miss_idx, NT);
+    rc |= ealloc(e, &c->miss_count, 4);
+    rc |= ealloc(e, &c->packed_state, NT * c->S);
+    rc |= ealloc(e, &c->packed_pol, NT * c->P);
+    rc |= ealloc(e, &c->packed_val, NT);
+    rc |= ealloc(e, &c->stats, 2);
+    if (rc != 0) { delete c; return g_err.empty() ? fail("evaluation cache: allocation failed") : -1; }
+    e->cache = c;
+    e->view_epoch++;   // the captured round graph does not contain the cache passes
+    return 0;
+}
+
+int gaz_eval_cache_stats(gaz_engine *e, int64_t *out) {
+    if (!e || !out) return fail("null argument");
+    out[0] = out[1] = out[2] = 0;
+    if (!e->cache) return 0;
+    unsigned long long st[2] = {0, 0};
+    if (d2h(st, e->cache->stats, sizeof st, e->stream) != 0) return -1;
+    out[0] = (int64_t)st[0]; out[1] = (int64_t)st[1]; out[2] = e->cache->entries;
+    return 0;
 }
 
 int gaz_pool_info(gaz_engine *e, int64_t *out) {

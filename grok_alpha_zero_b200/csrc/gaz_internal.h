@@ -54,6 +54,7 @@ struct gaz_engine {
     int64_t bytes;
     std::vector<void *> allocs;
     struct gaz_net *net; // attached evaluator (gaz_net.cu) or null
+    struct gaz_eval_cache *cache; // evaluation cache or null
     int leaf_bound;      // host-side upper bound of outstanding leaf requests (0 = n_trees)
     // CUDA graph of one search round (select -> network -> expand), built by gaz_net.cu on first use
     void *round_graph;   // cudaGraphExec_t
@@ -83,6 +84,30 @@ struct gaz_engine {
 #endif
 };
 
+
+// Evaluation cache (Session_Cache.Cache_Wrapper on the device, gaz_eval_cache_enable): direct-mapped table of evaluated
+// positions.  A round's leaf requests are looked up first; the hits get their outputs at once, the misses are packed into a
+// dense list that the evaluator serves, and a fill pass scatters the results back and stores them.
+struct gaz_eval_cache {
+    int64_t entries;
+    int scope;                 // 0 = per game (the key includes the game's stream key / tree's game), 1 = shared by all games
+    int S, P;
+    int8_t *state;             // [entries][S]
+    unsigned long long *tag;   // [entries]: 0 = empty, else hash | 1<<63
+    float *pol;                // [entries][P]
+    float *val;                // [entries]
+    int32_t *claim;            // [entries]: fill epoch of the last writer (one writer per slot and pass)
+    int32_t *miss_idx;         // [n_trees]: leaf index of packed miss m
+    int32_t *miss_count;       // device counter
+    int8_t *packed_state;      // [n_trees][S]
+    float *packed_pol;         // [n_trees][P]
+    float *packed_val;         // [n_trees]
+    unsigned long long *stats; // [2]: look-ups, hits
+    int epoch;
+};
+// look-up pass over the current leaf list / fill pass after the evaluator served the packed misses (stream-ordered)
+int gaz_internal_cache_lookup(gaz_engine *e);
+int gaz_internal_cache_fill(gaz_engine *e);
 
 int gaz_internal_launch_select(gaz_engine *e);
 int gaz_internal_launch_expand(gaz_engine *e);

@@ -1101,12 +1101,18 @@ static int engine_forward(gaz_engine *e) {
     int chunks = (bound + n->max_batch - 1) / n->max_batch;
     if (chunks > 16) return gaz_fail("leaf bound %d needs more than 16 chunks of %d", bound, n->max_batch);
     const size_t ss = (size_t)v.ncell * v.C;
-    for (int c = 0; c < chunks; c++) {
-        const int off = c * n->max_batch;
-        chunk_count_kernel<<<1, 1, 0, e->stream>>>(v.leaf_count, off, n->max_batch, n->d_chunk_count + c);
-        if (net_forward(n, v.leaf_state + (size_t)off * ss, n->d_chunk_count + c, v.policy + (size_t)off * v.P,
-                        v.value + off, e->stream) != 0) return -1;
+    // with the evaluation cache on, the network sees the packed misses of the look-up pass instead of the leaf list
+    gaz_eval_cache *c = e->cache;
+    if (c && gaz_internal_cache_lookup(e) != 0) return -1;
+    const int32_t *total = c ? c->miss_count : v.leaf_count;
+    const int8_t *states = c ? c->packed_state : v.leaf_state;
+    float *pol = c ? c->packed_pol : v.policy, *val = c ? c->packed_val : v.value;
+    for (int ck = 0; ck < chunks; ck++) {
+        const int off = ck * n->max_batch;
+        chunk_count_kernel<<<1, 1, 0, e->stream>>>(total, off, n->max_batch, n->d_chunk_count + ck);
+        if (net_forward(n, states + (size_t)off * ss, n->d_chunk_count + ck, pol + (size_t)off * v.P, val + off, e->stream) != 0) return -1;
     }
+    if (c && gaz_internal_cache_fill(e) != 0) return -1;
     return 0;
 }
 

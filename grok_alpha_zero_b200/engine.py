@@ -241,6 +241,15 @@ class Engine:
         self._ck(self.lib.gaz_tree_sizes(self._h, _p(out)))
         return out
 
+    def enable_eval_cache(self, entries, shared=False):
+        """device-side evaluation cache (Session_Cache.Cache_Wrapper's role): identical positions are evaluated once"""
+        self._ck(self.lib.gaz_eval_cache_enable(self._h, int(entries), int(bool(shared))))
+
+    def eval_cache_stats(self):
+        out = np.zeros(3, dtype=np.int64)
+        self._ck(self.lib.gaz_eval_cache_stats(self._h, _p(out)))
+        return dict(lookups=int(out[0]), hits=int(out[1]), entries=int(out[2]))
+
     def pool_info(self):
         """slot page pool: dict(pages, free, page_slots, max_pages_per_tree)"""
         out = np.zeros(4, dtype=np.int64)

@@ -149,6 +149,17 @@ int gaz_status(gaz_engine *e); /* sticky error bits: 1 node overflow, 2 slot ove
  * gaz_config.node_cap / slot_cap.  The reference's trees are unbounded Python objects (MCTS.py:20-72); a host driver
  * uses this after gaz_prune to give a tree that could not hold one more move's search a fresh root instead. */
 int gaz_tree_sizes(gaz_engine *e, int32_t *out);
+/* Session_Cache.Cache_Wrapper (Session_Cache.py:4-26: evaluator outputs cached by the raw input bytes) on the device: a
+ * direct-mapped table of `entries` evaluated positions in HBM.  Every round the leaf requests are looked up first (the FULL
+ * input state is compared, so a hit returns exactly what the evaluator returned for that position); only the misses reach
+ * the evaluator, packed into a dense batch; their outputs are stored afterwards.  Identical outputs => the searches are
+ * bit-identical with and without the cache (tests/test_eval_cache.py holds the reference goldens with it on).
+ * shared_scope 0: a game's entries are private to it (the key includes the game id); 1: all games share the table, like the
+ * reference's one diskcache directory per generation.  Unlike Cache_Wrapper there is no depth limit and look-ups do not
+ * stop at the first miss - both only bound the disk store's size and latency there.  Call before the first search round. */
+int gaz_eval_cache_enable(gaz_engine *e, int64_t entries, int shared_scope);
+/* out[0] look-ups, out[1] hits (evaluator calls saved), out[2] entries; zeros when the cache is off */
+int gaz_eval_cache_stats(gaz_engine *e, int64_t *out);
 /* the slot page pool: out[0] pages in the pool, out[1] pages free now, out[2] slots per page, out[3] page-table entries per tree */
 int gaz_pool_info(gaz_engine *e, int64_t *out);
 int64_t gaz_bytes_allocated(gaz_engine *e);
