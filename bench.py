@@ -404,10 +404,11 @@ def run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games):
     if world > 1:
         dist.all_reduce(mst, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    line = None
     if rank == 0:
         sims, evals, moves, alive = (float(x) for x in tot.tolist())
         t = float(mst.item()) * 1e-3
-        print(json.dumps(dict(
+        line = (dict(
             metric="MCTS simulations/sec", value=sims / t, unit="sims/s", n_gpus=world, steps=rounds, warmup=cfg["limit"],
             ms_per_step=t * 1e3 / rounds, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
             data="synthetic",
@@ -417,10 +418,9 @@ def run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games):
                         noise="on" if sb.noise else "off"),
             positions_per_s=moves / t, moves_timed=int(moves), games_still_running=int(alive),
             nn_evals_per_s=evals / t, sims_per_eval=sims / max(1.0, evals), gpu_launches=int(sb.launches - l0),
-            clocks=clocks, hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()))), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            clocks=clocks, hbm_bytes=dict(engine=sb.eng.bytes_allocated(), net=sb.net.bytes_allocated()),
+            eval_cache=(dict(sb.eng.eval_cache_stats(), scope="per game") if args.eval_cache > 0 else None)))
+    return line
 
 
 def main():
@@ -464,6 +464,11 @@ def main():
     peaks = load_peaks()
     line = measure(args, cfg, world, rank, local, peaks, want_cpu=(world == 1 and not args.no_cpu_baseline), full=True)
     if args.moves > 0:
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     if args.config == "gomoku" and not args.no_extras:
         if world == 1:      # the other BASELINE configurations, short runs, same measurement (driver-visible in the one JSON line)
@@ -478,15 +483,20 @@ def main():
                                   net_frac_of_sustained_peak=sub["net_tflops"] / peaks["sustained"],
                                   roofline=dict((k, sub["roofline"][k]) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel")) if sub["roofline"] else None,
                                   clocks=sub["clocks"], gpu_launches=sub["gpu_launches"])
-            # the parity-safe evaluation cache (Session_Cache's role, per-game scope) on Connect4, where transpositions are
-            # common; the headline and the sub-records above run without it
-            a3 = argparse.Namespace(**vars(args))
-            a3.steps, a3.warmup, a3.games, a3.presearch, a3.config, a3.eval_cache = 200, 3, 0, 600, "connect4", 1 << 23
-            sub = measure(a3, dict(CONFIGS["connect4"]), world, rank, local, peaks, want_cpu=False, full=False)
-            subs["connect4_eval_cache"] = dict(workload=sub["config"]["workload"] + ", evaluation cache of 2^23 entries (per game)",
-                                               value=sub["value"], ms_per_step=sub["ms_per_step"], steps=sub["steps"],
-                                               presearch_rounds=600, sims_per_eval=sub["sims_per_eval"], nn_evals_per_s=sub["nn_evals_per_s"],
-                                               eval_cache=sub["eval_cache"], positions_per_s=sub["positions_per_s"])
+            # The parity-safe evaluation cache (Session_Cache's role, per-game scope) pays over WHOLE moves - the idle tree of a
+            # game re-meets what the other tree evaluated, re-rooted trees re-expand known positions - so it is shown on 8
+            # consecutive whole Connect4 moves of every game, with and without it (the headline runs without it).
+            pair = {}
+            for tag, entries in (("off", 0), ("on", 1 << 23)):
+                a3 = argparse.Namespace(**vars(args))
+                a3.games, a3.config, a3.eval_cache, a3.moves = 0, "connect4", entries, 8
+                sub = measure(a3, dict(CONFIGS["connect4"]), world, rank, local, peaks, want_cpu=False, full=False)
+                pair[tag] = dict(value=sub["value"], positions_per_s=sub["positions_per_s"], sims_per_eval=sub["sims_per_eval"],
+                                 nn_evals_per_s=sub["nn_evals_per_s"], ms_per_step=sub["ms_per_step"], moves_timed=sub["moves_timed"],
+                                 eval_cache=sub["eval_cache"])
+            subs["connect4_whole_moves_eval_cache"] = dict(
+                workload=CONFIGS["connect4"]["label"] + "; 8 whole moves of every game after one warm-up move; evaluation cache of 2^23 "
+                "entries, per-game scope", **pair)
             if rank == 0:
                 line["configs"] = subs
         else:               # multi-GPU: a short REAL generation with the NCCL trajectory gather and the writer inside the wall clock
@@ -605,8 +615,12 @@ def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
         return sb.eng.timer_end(), rounds
 
     if args.moves > 0:
-        run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games)
-        return None
+        line = run_moves(args, cfg, sb, timed_moves, barrier, world, rank, local, n_games)
+        sb.eng.close()
+        sb.net.close()
+        del sb
+        torch.cuda.empty_cache()
+        return line
 
     # ---- warm-up + timed region -------------------------------------------------------------------
     timed_rounds(args.warmup)
@@ -631,24 +645,27 @@ def measure(args, cfg, world, rank, local, peaks, want_cpu, full):
 
     # ---- one WHOLE move of every game, timed: fresh start position, the full run (forced root expansions included), root
     # statistics, the tau = 0 move, do_action / check_win, prune_tree of both trees, the next run's begin
-    sb.alive[:] = True
-    sb.next_player[:] = -1
-    sb.start()
-    m0 = sb.moves
-    barrier()
-    wm_ms, wm_rounds = timed_moves(1)
-    barrier()
-    wm = torch.tensor([float(sb.moves - m0)], dtype=torch.float64, device="cuda")
-    wmt = torch.tensor([wm_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(wm, op=dist.ReduceOp.SUM)
-        dist.all_reduce(wmt, op=dist.ReduceOp.MAX)
-    whole_move = dict(moves=int(wm.item()), ms=float(wmt.item()), rounds=int(wm_rounds),
-                      what="one whole move of every game from the start position: search run + root statistics + move choice "
-                           "+ do_action/check_win + prune_tree (both trees) + next run begin; device events, max over ranks")
-    positions_per_s = float(wm.item()) / (float(wmt.item()) * 1e-3)
-    if sb.eng.status() != 0:
-        raise SystemExit("engine status %d after the whole-move measurement" % sb.eng.status())
+    # (skipped with the evaluation cache on: replaying the first move would hit what the timed rounds just stored)
+    whole_move, positions_per_s = None, None
+    if args.eval_cache == 0:
+        sb.alive[:] = True
+        sb.next_player[:] = -1
+        sb.start()
+        m0 = sb.moves
+        barrier()
+        wm_ms, wm_rounds = timed_moves(1)
+        barrier()
+        wm = torch.tensor([float(sb.moves - m0)], dtype=torch.float64, device="cuda")
+        wmt = torch.tensor([wm_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(wm, op=dist.ReduceOp.SUM)
+            dist.all_reduce(wmt, op=dist.ReduceOp.MAX)
+        whole_move = dict(moves=int(wm.item()), ms=float(wmt.item()), rounds=int(wm_rounds),
+                          what="one whole move of every game from the start position: search run + root statistics + move choice "
+                               "+ do_action/check_win + prune_tree (both trees) + next run begin; device events, max over ranks")
+        positions_per_s = float(wm.item()) / (float(wmt.item()) * 1e-3)
+        if sb.eng.status() != 0:
+            raise SystemExit("engine status %d after the whole-move measurement" % sb.eng.status())
 
     # ---- e2e: host boards in, root statistics out ---------------------------------------------------------
     H, Wd = sb.eng.H, sb.eng.W

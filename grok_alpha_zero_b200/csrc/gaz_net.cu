@@ -608,11 +608,13 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 const size_t sm = gaz_small::head_wide_smem(d.cin, d.ksize, n->P_pad, n->Wp, a.G);
                 static size_t attr_sm = 0;
                 if (sm > attr_sm) {
-                    CKN(cudaFuncSetAttribute(gaz_small::headconv_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    CKN(cudaFuncSetAttribute(gaz_small::headconv_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    CKN(cudaFuncSetAttribute(gaz_small::headconv_wide_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                     attr_sm = sm;
                 }
                 const int groups = (n->max_batch + a.G - 1) / a.G;
-                gaz_small::headconv_wide_kernel<<<groups < n->n_sm ? groups : n->n_sm, 512, sm, s>>>(a);
+                if (d.ksize == 3) gaz_small::headconv_wide_kernel<3><<<groups < n->n_sm ? groups : n->n_sm, 512, sm, s>>>(a);
+                else gaz_small::headconv_wide_kernel<1><<<groups < n->n_sm ? groups : n->n_sm, 512, sm, s>>>(a);
                 break;
             }
             HeadConvArgs a;

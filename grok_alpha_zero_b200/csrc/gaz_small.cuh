@@ -207,9 +207,10 @@ static inline size_t head_wide_smem(int Cin, int K, int P_pad, int Wp, int G) {
     return (size_t)K * K * (Cin >> 4) * 2 * 32 * 16 + (size_t)2 * rows * Cin * 2 + 16;
 }
 
-__global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
+template <int K> __global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int taps = p.K * p.K, kh = p.K >> 1, KS = p.Cin >> 4, CH = p.Cin >> 3;
+    constexpr int taps = K * K, kh = K >> 1;
+    const int KS = p.Cin >> 4, CH = p.Cin >> 3;
     const int halo = kh * (p.Wp + 1), srows = p.G * p.P_pad + 2 * halo;
     uint4 *s_frag = reinterpret_cast<uint4 *>(smem);
     uint8_t *s_hi = smem + (size_t)taps * KS * 2 * 32 * 16, *s_lo = s_hi + (size_t)srows * p.Cin * 2;
@@ -239,13 +240,15 @@ __global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
                 const int i = i0 + u * (int)blockDim.x;
                 const int pc = i / srows, sr = i - pc * srows;       // consecutive threads: consecutive rows of one 8-channel piece
                 pcs[u] = pc; srs[u] = sr;
-                const long long r = row0 + sr;
-                ok[u] = i < srows * CH && r >= 0 && r < p.in_rows;
-                if (ok[u]) {
-                    const int b = (int)(r / p.P_pad), pos = (int)(r - (long long)b * p.P_pad);
-                    ok[u] = b < cnt && pos / p.Wp != 0 && pos / p.Wp <= p.H && pos % p.Wp != p.Wp - 1;
-                }
-                if (ok[u]) gaz_conv::ldg256(p.in + f32_blk_index(r, pc * 8, p.Cin), v[u]);
+                // board and position of the staged row in 32-bit arithmetic (halo < P_pad: at most one board before / after)
+                const int rel = sr - halo;
+                int b = grp * p.G, pos = rel;
+                if (rel < 0) { b -= 1; pos = rel + p.P_pad; }
+                else if (rel >= p.G * p.P_pad) { b += p.G; pos = rel - p.G * p.P_pad; }
+                else { const int q = rel / p.P_pad; b += q; pos = rel - q * p.P_pad; }
+                const int yy = pos / p.Wp;
+                ok[u] = i < srows * CH && b >= 0 && b < cnt && yy != 0 && yy <= p.H && pos - yy * p.Wp != p.Wp - 1;
+                if (ok[u]) gaz_conv::ldg256(p.in + f32_blk_index(row0 + sr, pc * 8, p.Cin), v[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(512) headconv_wide_kernel(HeadWideArgs p) {
 #pragma unroll
                 for (int e = 0; e < 4; e++) { ahh[hd][e] = 0.0f; alh[hd][e] = 0.0f; ahl[hd][e] = 0.0f; }
             for (int tp = 0; tp < taps; tp++) {
-                const int sr = halo + mt * 16 + a_row + (tp / p.K - kh) * p.Wp + (tp % p.K - kh);
+                const int sr = halo + mt * 16 + a_row + (tp / K - kh) * p.Wp + (tp % K - kh);
                 const uint32_t rowoff = (uint32_t)(sr * row_bytes);
                 const uint4 *fr = s_frag + (size_t)tp * KS * 64 + lane;
 #pragma unroll 4

@@ -92,7 +92,10 @@ def run_sample(game, spec, weights, n_workers, sims_per_step, steps, warmup, c_p
         t = orc.OracleTree(game, False, evaluator=ev, c_puct_init=c_puct_init)
         trees.append((g, t))
 
-    def parallel(fn):
+    # Free-running workers, as the reference's worker PROCESSES are (Self_Play.py:346-363): every worker thread runs its own
+    # simulations back to back and only meets the others inside the inference server's batch; threads are started once per
+    # phase and joined once at its end (no per-step barrier).
+    def phase(fn):
         server.active = n_workers
         th = [threading.Thread(target=fn, args=(i,)) for i in range(n_workers)]
         for x in th:
@@ -100,15 +103,14 @@ def run_sample(game, spec, weights, n_workers, sims_per_step, steps, warmup, c_p
         for x in th:
             x.join()
 
-    parallel(lambda i: trees[i][1].new_root(trees[i][0]))
-    for _ in range(warmup):
-        parallel(lambda i: trees[i][1].iterate(sims_per_step))
+    phase(lambda i: trees[i][1].new_root(trees[i][0]))
+    if warmup > 0:
+        phase(lambda i: trees[i][1].iterate(sims_per_step * warmup))
     s0 = sum(t.n_sims for _, t in trees)
     e0 = sum(t.n_evals for _, t in trees)
     b0, r0 = server.batches, server.requests
     t0 = time.perf_counter()
-    for _ in range(steps):
-        parallel(lambda i: trees[i][1].iterate(sims_per_step))
+    phase(lambda i: trees[i][1].iterate(sims_per_step * steps))
     dt = time.perf_counter() - t0
     sims = sum(t.n_sims for _, t in trees) - s0
     evals = sum(t.n_evals for _, t in trees) - e0
