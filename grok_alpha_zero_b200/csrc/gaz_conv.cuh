@@ -64,7 +64,8 @@ struct BoardConvArgs {
     int max_count;
     int P_pad, Wp, H;         // rows per board (a divisor of 256 or (H+1)*Wp), row pitch W+1, board height: rows of a board beyond
                               // (H+1)*Wp are dead like the padding row / column
-    int taps, kpt;            // filter taps (1 or 9), 64-channel K-blocks per tap
+    int taps, kpt;            // filter taps (1 or 9; 3 in dx-merged mode), 64-channel K-blocks per tap
+    int dxm;                  // dx-merged 3x3 convolution (BN = 96 instance only, see the kernel): taps = 3 row shifts dy * Wp
     int base_offset_mode;     // debug bits: 4 = skip the output stores (timing experiment)
     // per-channel parameters travel in the kernel-argument (constant) bank: bias | scale_a | shift_a | scale_b |
     // shift_b, 128 floats each.  The epilogue reads them with uniform LDC, which keeps them off the shared-memory
@@ -92,13 +93,13 @@ constexpr int SLAB_BOX_ROWS = SLAB_ROWS / 2;
 
 template <int BN, bool PAIR> struct BoardCfg {
     static constexpr int NSLAB = PAIR ? 4 : 3;
-    static constexpr int NB = BN <= 32 ? 16 : (BN <= 64 ? 8 : 4);  // weight-tile ring: small tiles are consumed in ~100 cycles each,
-                                                                   // the ring has to span the L2 latency
-    static constexpr int NSTAGE = PAIR ? 2 : 1; // 32-row x 32-channel bf16 staging tiles per epilogue warp (TMA store source)
+    static constexpr int NB = BN <= 32 ? 16 : (BN <= 64 ? 8 : (BN == 96 ? 6 : 4)); // weight-tile ring: small tiles are consumed in
+                                                                   // ~100 cycles each, the ring has to span the L2 latency
+    static constexpr int NSTAGE = (PAIR && BN != 96) ? 2 : 1; // 32-row x 32-channel bf16 staging tiles per epilogue warp (TMA store source)
     static constexpr int STAGE_BYTES = 8 * NSTAGE * 2048;
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN; // weight rows (output channels) this CTA stages per tile
     static constexpr int B_BYTES = B_ROWS * 128;
-    static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;
+    static constexpr int TMEM_COLS = BN == 96 ? 512 : (4 * BN < 32 ? 32 : 4 * BN);   // a power of two
     static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [8 warps][BN], mean, hidden, gate
     static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ +
                                 SE_FLOATS * 4;
@@ -222,7 +223,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int tap = 0; tap < p.taps; tap++) {
                         mbar_wait(&b_full[rb.idx], rb.phase);
                         tc_fence_after();
-                        const int shift = p.taps == 9 ? dy * p.Wp + dx : 0;
+                        const int shift = BN == 96 ? (tap - 1) * p.Wp : (p.taps == 9 ? dy * p.Wp + dx : 0);
                         const uint32_t b_lo = umma_desc_lo(smem_u32(sB + rb.idx * Cfg::B_BYTES));
                         const uint32_t a_lo = slab_lo + (uint32_t)(shift * 8); // 128 B per row = 8 descriptor units
                         const uint32_t accf = (uint32_t)((kc | tap) != 0); // the first MMA into each accumulator overwrites
@@ -267,6 +268,67 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int pos = (int)(row % p.P_pad);
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
             const bool live = row < valid_rows && (p.dense || (yy != 0 && yy <= p.H && xx != p.Wp - 1));
+            if constexpr (BN == 96) {
+                // ---- dx-merged 3x3 convolution with 32 outputs (the C128 -> C32 head convolutions).  The weight tile of row
+                // shift dy holds the filters of its three taps side by side (N = 96: column dx' * 32 + c, dx' = dx + 1), so
+                // an MMA computes E_dx[r][c] = sum_dy sum_k A[r + dy * Wp][k] * W[dy][dx][k][c] for all three dx from ONE
+                // read of A (a N = 32 MMA reads the same 4 KB of A for a third of the work and is bound by the shared-
+                // memory port), and the output is out[r] = E_-1[r - 1] + E_0[r] + E_+1[r + 1]: the two neighbour terms come
+                // from the adjacent TMEM lanes by warp shuffle.  Wp divides 32 and a tile starts with a board, so the
+                // lanes 0 / 31 of a warp are cells of column 0 / the padding column: the term a lane 0 would need from the
+                // previous warp belongs to a padding cell (its A rows are zero: E = 0 exactly), lane 31's output is dead.
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + sub) * BN);
+                uint8_t *st = sStage + (warp - 4) * Cfg::NSTAGE * 2048;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; hf++) {
+                    uint32_t em[16], e0[16], ep[16];
+                    tmem_ld_32x16(t_acc + (uint32_t)(hf * 16), em);
+                    tmem_ld_32x16(t_acc + (uint32_t)(32 + hf * 16), e0);
+                    tmem_ld_32x16(t_acc + (uint32_t)(64 + hf * 16), ep);
+                    tmem_ld_wait();
+                    if (hf == 1) { // the accumulator is in registers: hand it back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+                    } else {       // the previous tile's store must have drained the staging tile
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                    }
+                    const float *pb = p.par + hf * 16, *sc = p.par + 128 + hf * 16, *sh = p.par + 256 + hf * 16;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            float o2[2];
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                const int c = 8 * j + 2 * i + u;
+                                float a = __shfl_up_sync(0xffffffffu, __uint_as_float(em[c]), 1);
+                                float b = __shfl_down_sync(0xffffffffu, __uint_as_float(ep[c]), 1);
+                                if (lane == 0) a = 0.0f;
+                                if (lane == 31) b = 0.0f;
+                                const float v = ((a + __uint_as_float(e0[c])) + b) + pb[c];
+                                o2[u] = live ? fmaxf(fmaf(sc[c], v, sh[c]), 0.0f) : 0.0f;
+                            }
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(o2[0], o2[1]);
+                            w[i] = *reinterpret_cast<uint32_t *>(&hh);
+                        }
+                        const int piece = hf * 2 + j;
+                        *reinterpret_cast<uint4 *>(st + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmOa, st, 0, (int)(row - lane));
+                    tma_store_commit();
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             float rnext[32]; // residual of the first output chunk: issued before the accumulator is even ready
             const bool use_res = p.res && !(dbg & 8);
             if (use_res) {

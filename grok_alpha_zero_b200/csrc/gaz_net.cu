@@ -380,6 +380,7 @@ struct NetOp {
     int skip;             // SE op folded into the previous conv
     int block_fused;      // this conv1 runs the whole residual block (gaz_block.cuh) together with the next conv (+SE)
     int in_block;         // this conv2 is executed by the previous op's fused block kernel
+    int dxm;              // 3x3 C -> 32 convolution run dx-merged (conv_board_kernel<96>): d_wt = filters repacked [dx*32+c][dy*Cin+k]
     int dual_partner;     // HEADCONV: index of a later head convolution on the same fp32 input that this op's launch computes
     int dual_skip;        // as well (gaz_small::headconv_wide_kernel, N = 16); dual_skip marks that later op
     int head_wide;        // HEADCONV on the fp32 stream through headconv_wide_kernel: d_frag / d_hbias are set
@@ -395,6 +396,7 @@ struct NetOp {
     __nv_bfloat16 *d_act; // [rows_dense][In]: written by the producing head convolution
     __nv_bfloat16 *d_wt;  // [Out][In]
     int stem_tc;          // stem on the tensor cores (gaz_stem.cuh): d_stem_w / d_stem_par / tmOa (out_a) / tmOb (out_q) are set
+    int stem_proj;        // ... and it also runs the next op, the 1x1 projection of the first block's shortcut (stem_proj_kernel)
     uint16_t *d_stem_w;   // [256][64] bf16 hi | lo split filters
     float *d_stem_par;    // stem_tc: [4][256] BN scale | shift + scale * bias | scale_a | shift_a; mma stem: [5][Cout] conv bias |
                           // BN scale | BN shift | scale_a | shift_a
@@ -510,6 +512,20 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
         switch (d.type) {
         case GAZ_OP_STEM: {
+            if (op.stem_proj) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    CKN(cudaFuncSetAttribute(gaz_stem::stem_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_stem::ProjCfg::SMEM));
+                    attr_set = true;
+                }
+                const gaz_net_op &pj = n->ops[oi + 1].d;
+                gaz_stem::StemProjArgs t;
+                t.count = count; t.max_count = n->max_batch; t.states = states; t.H = n->H; t.W = n->W; t.Wp = n->Wp;
+                t.relu = d.act == GAZ_ACT_RELU; t.wpack = op.d_stem_w; t.par = op.d_stem_par;
+                t.wproj = n->wh + pj.w; t.pbias = n->wf + pj.bias; t.out_res = (float *)buf(pj.out_raw);
+                gaz_stem::stem_proj_kernel<<<n->n_sm, 512, gaz_stem::ProjCfg::SMEM, s>>>(op.tmOa, t);
+                break;
+            }
             if (op.stem_tc) {
                 static bool attr_set = false;
                 if (!attr_set) {
@@ -564,6 +580,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 memset(&a, 0, sizeof a);
                 a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp; a.H = n->H;
                 a.taps = d.ksize * d.ksize; a.kpt = d.cin / 64; a.base_offset_mode = n->dbg;
+                if (op.dxm) { a.taps = 3; a.dxm = 1; }
                 const gaz_net_op &o = op.fused_se ? op.se : d; // outputs / residual of the fused SE op
                 memcpy(a.par, op.par, sizeof a.par);
                 a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
@@ -573,7 +590,8 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                     a.se_w1 = wfp(n, op.se.w2); a.se_b1 = wfp(n, op.se.bias2); a.se_w2 = wfp(n, op.se.w3); a.se_b2 = wfp(n, op.se.bias3);
                     a.se_b1 = op.d_se_b1; // conv bias folded into the dense1 bias (b1 + W1^T bias)
                 }
-                rc = d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
+                rc = op.dxm ? launch_conv_board<96>(n, op, a, s)
+                     : d.cout == 128 ? launch_conv_board<128>(n, op, a, s) : d.cout == 64 ? launch_conv_board<64>(n, op, a, s)
                      : d.cout == 32 ? launch_conv_board<32>(n, op, a, s) : gaz_fail("conv_tc cout %d unsupported", d.cout);
             }
             if (rc != 0) return rc;
@@ -785,10 +803,12 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.skip = 0;
         op.block_fused = 0;
         op.in_block = 0;
+        op.dxm = 0;
         op.dual_partner = -1;
         op.dual_skip = 0;
         op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0;
         op.stem_tc = 0;
+        op.stem_proj = 0;
         op.d_stem_w = nullptr;
         op.d_stem_par = nullptr;
         op.d_se_b1 = nullptr;
@@ -810,6 +830,25 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
                 gaz_net_destroy(n);
                 return -1;
             }
+            // 3x3 convolutions with 32 outputs and one bf16 output (the C128 -> C32 head convolutions): dx-merged form, the
+            // three taps of a filter row side by side as N = 96 (gaz_conv.cuh).  Needs whole boards per tile and a row pitch
+            // that divides the 32 rows of an epilogue warp.
+#ifndef GAZ_NO_DXM         // A/B builds only
+            if (d.cout == 32 && d.ksize == 3 && gaz_conv::TILE_ROWS % n->P_pad == 0 && 32 % n->Wp == 0 && d.out_a >= 0 && d.out_b < 0 &&
+                d.out_raw < 0 && d.res_buf < 0 && (n->n_sm & ~1) >= 2) {
+                const size_t ld = (size_t)3 * d.cin;
+                std::vector<uint16_t> wt((size_t)96 * ld);
+                for (int dy = 0; dy < 3; dy++)
+                    for (int dx = 0; dx < 3; dx++)
+                        for (int c = 0; c < 32; c++)
+                            memcpy(&wt[(size_t)(dx * 32 + c) * ld + (size_t)dy * d.cin], desc->wh + d.w + (size_t)c * 9 * d.cin + (size_t)(dy * 3 + dx) * d.cin,
+                                   (size_t)d.cin * 2);
+                if (alloc((void **)&op.d_wt, wt.size() * 2) != 0) { gaz_net_destroy(n); return -1; }
+                CKN(cudaMemcpy(op.d_wt, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+                if (make_map(enc, &op.tmB2, op.d_wt, (uint64_t)ld, 96, 48) != 0) { gaz_net_destroy(n); return -1; }
+                op.dxm = 1;
+            }
+#endif
         }
         if (d.type == GAZ_OP_POLICY_OUT) n->logits_buf = d.in_buf;
         // fold an SE op into the epilogue of the convolution that feeds it (tile == board geometries only)
@@ -1019,6 +1058,23 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         }
         op.stem_tc = ok ? 1 : 0;
     }
+    // stem followed by the 1x1 projection of the first block's shortcut (C256 -> C128, fp32 out, nothing else reads the stem's
+    // raw output): one kernel, the raw stem output never goes to HBM
+#ifndef GAZ_NO_STEM_PROJ   // A/B builds only (tools/build_variant.sh)
+    for (size_t oi = 0; oi + 1 < n->ops.size(); oi++) {
+        NetOp &st = n->ops[oi], &pj = n->ops[oi + 1];
+        if (st.d.type != GAZ_OP_STEM || !st.stem_tc || st.d.out_a < 0 || st.d.out_b < 0) continue;
+        const gaz_net_op &d = pj.d;
+        if (d.type != GAZ_OP_CONV_TC || d.ksize != 1 || d.cin != 256 || d.cout != 128 || d.in_buf != st.d.out_b || d.out_raw < 0 ||
+            d.out_a >= 0 || d.out_b >= 0 || d.res_buf >= 0 || d.bias < 0 || pj.fused_se) continue;
+        bool other = false;
+        for (size_t k = 0; k < n->ops.size(); k++)
+            if (k != oi + 1 && (n->ops[k].d.in_buf == st.d.out_b || n->ops[k].d.res_buf == st.d.out_b)) other = true;
+        if (other) continue;
+        st.stem_proj = 1;
+        pj.in_block = 1;
+    }
+#endif
     for (auto &op : n->ops) {   // every other stem: B fragments (hi | lo) + parameters of gaz_small::stem_mma_kernel
         const gaz_net_op &d = op.d;
         if (d.type != GAZ_OP_STEM || op.stem_tc) continue;

@@ -214,4 +214,264 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmOq, const __grid_constant__
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// ---- stem + the 1x1 projection of the first residual block's shortcut in one kernel ------------------------------------------
+// Net/ResNet/ResNet_Block.py:29-31: when the stem has more filters than the trunk (Gomoku: 256 -> 128) the first block's
+// shortcut is a 1x1 convolution of the stem output.  As two kernels the stem writes that output as a second bf16 operand
+// (128 KB per board) only for the projection to read it back; here it stays in shared memory: per 128-row half of a board
+//   im2col (K = 48) --MMA N=256--> TMEM --epilogue 1: BN (+ReLU)--> x0 as bf16 K-major SWIZZLE_128B tiles in shared memory
+//                                        + relu(BN1(x0)) --staging tiles, TMA store--> out_a (operand of the block's conv1)
+//   x0 tiles --MMA N=128, K=256 (projection filters resident in shared memory)--> TMEM --epilogue 2: + bias--> fp32 stream
+// HBM traffic per board: 128 KB (out_a) + 128 KB (fp32 shortcut) instead of 512 KB.  Same operand values and the same
+// accumulation order as stem_tc_kernel followed by conv_board_kernel<128> (1x1), so the results are bit-identical.
+// 512 threads: warp w works on TMEM lane quarter w & 3 and column part w >> 2 (epilogue 1: 64 of the 256 stem filters =
+// one 64-channel K-block of the projection's A operand; epilogue 2: 32 of the 128 outputs).
+struct StemProjArgs {
+    const int32_t *count;
+    int max_count;
+    const int8_t *states;
+    int H, W, Wp, relu;
+    const uint16_t *wpack;  // as StemTcArgs
+    const float *par;       // as StemTcArgs
+    const uint16_t *wproj;  // [128 outputs][256 k] bf16, K-major (the 1x1 convolution's tensor-core weights)
+    const float *pbias;     // [128]
+    float *out_res;         // blocked fp32 rows x 128 (gaz_conv::f32_blk_index)
+};
+
+struct ProjCfg {
+    static constexpr int A1_BYTES = 128 * 128, B1_BYTES = 256 * 128, A2_BYTES = 4 * 128 * 128, B2_BYTES = 4 * 128 * 128;
+    static constexpr int STAGE_BYTES = 16 * 2048, PAR_BYTES = 4 * 256 * 4 + 128 * 4;
+    static constexpr int IN_BYTES = 18 * 18 * 2 + 28;
+    static constexpr int SMEM = 1024 + A1_BYTES + B1_BYTES + A2_BYTES + B2_BYTES + STAGE_BYTES + PAR_BYTES + 2 * IN_BYTES + 64;
+};
+
+__global__ void __launch_bounds__(512, 1)
+stem_proj_kernel(const __grid_constant__ CUtensorMap tmOa, const StemProjArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA1 = base, *sB1 = sA1 + ProjCfg::A1_BYTES, *sA2 = sB1 + ProjCfg::B1_BYTES, *sB2 = sA2 + ProjCfg::A2_BYTES;
+    uint8_t *sStage = sB2 + ProjCfg::B2_BYTES;
+    float *s_par = (float *)(sStage + ProjCfg::STAGE_BYTES);   // [4][256] | projection bias [128]
+    int8_t *s_in = (int8_t *)(s_par + 4 * 256 + 128);          // two zero-bordered boards (double buffer)
+    uint64_t *bars = (uint64_t *)(((uintptr_t)(s_in + 2 * ProjCfg::IN_BYTES) + 7) & ~(uintptr_t)7);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+
+    for (int i = threadIdx.x; i < 256 * 8; i += 512) {       // stem filters, swizzled like a SWIZZLE_128B TMA write
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4 *>(sB1 + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4 *>(p.wpack + (size_t)r * 64 + c * 8);
+    }
+    for (int i = threadIdx.x; i < 128 * 32; i += 512) {      // projection filters: four 64-channel K-blocks of [128][64]
+        const int r = i >> 5, cc = i & 31, kb = cc >> 3, c = cc & 7;
+        *reinterpret_cast<uint4 *>(sB2 + kb * 16384 + r * 128 + ((c ^ (r & 7)) << 4)) =
+            *reinterpret_cast<const uint4 *>(p.wproj + (size_t)r * 256 + cc * 8);
+    }
+    for (int i = threadIdx.x; i < 4 * 256; i += 512) s_par[i] = p.par[i];
+    if (threadIdx.x < 128) s_par[4 * 256 + threadIdx.x] = p.pbias[threadIdx.x];
+    for (int i = threadIdx.x; i < 2 * ProjCfg::IN_BYTES; i += 512) s_in[i] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmOa);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int q = warp & 3, part = warp >> 2;
+    const int rsub = q * 32 + lane;                          // row of the 128-row half owned by this thread in both epilogues
+    const int pitch = (p.W + 2) * 2;
+    const int ncell = p.H * p.W;
+    const uint32_t par_addr = smem_u32(s_par), stage_addr = smem_u32(sStage + warp * 2048);
+    const uint32_t a1_lo = umma_desc_lo(smem_u32(sA1)), b1_lo = umma_desc_lo(smem_u32(sB1));
+    const uint32_t a2_lo = umma_desc_lo(smem_u32(sA2)), b2_lo = umma_desc_lo(smem_u32(sB2));
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, 256), idesc2 = umma_idesc_bf16(128, 128);
+    const uint32_t a2_row = smem_u32(sA2) + (uint32_t)(part * 16384 + rsub * 128);
+    const uint32_t sw7 = (uint32_t)(rsub & 7), sw3 = (uint32_t)((lane >> 1) & 3);
+
+    // The work list of this CTA: halves i = 0 .. T-1, half i = 128-row half i & 1 of board blockIdx.x + (i >> 1) * gridDim.x.
+    // Software pipeline over the halves (one __syncthreads per half):
+    //   iteration i:  wait stem(i) | TMEM -> registers | wait projection(i-1) | epilogue 1 of i (x0 tiles, out_a) |
+    //                 epilogue 2 of i-1 (fp32 shortcut) | warps 12..15: im2col of i+1 | sync | issue stem(i+1), projection(i)
+    // so both MMAs and the im2col run in the shadow of the two epilogues.
+    const int n_my = cnt > (int)blockIdx.x ? (cnt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int T = 2 * n_my;
+    auto board_of = [&](int i) { return (int)blockIdx.x + (i >> 1) * (int)gridDim.x; };
+    bool live_sub[2];
+    for (int h = 0; h < 2; h++) {
+        const int pos = h * 128 + rsub;
+        const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
+        live_sub[h] = yy >= 0 && yy < p.H && xx < p.W;
+    }
+    auto live_of = [&](int i) { return (i & 1) ? live_sub[1] : live_sub[0]; };
+    auto load_states = [&](int k) {     // board k of this CTA's list -> zero-bordered int8 tile k & 1
+        if ((int)threadIdx.x < ncell) {
+            const int y = threadIdx.x / p.W, x = threadIdx.x - y * p.W;
+            *reinterpret_cast<uint16_t *>(s_in + (k & 1) * ProjCfg::IN_BYTES + (y + 1) * pitch + (x + 1) * 2) =
+                *reinterpret_cast<const uint16_t *>(p.states + ((size_t)board_of(2 * k) * ncell + threadIdx.x) * 2);
+        }
+    };
+    auto im2col = [&](int i) {          // warps 12..15: the 128 rows of half i, as in stem_tc_kernel; dead rows are written as zeros
+        if (threadIdx.x < 384) return;
+        const int row = (int)threadIdx.x - 384;
+        const int pos = (i & 1) * 128 + row;
+        const int yy = pos / p.Wp - 1, xx = pos % p.Wp;
+        const bool lv = yy >= 0 && yy < p.H && xx < p.W;
+        const int8_t *tile = s_in + ((i >> 1) & 1) * ProjCfg::IN_BYTES;
+        uint32_t w[10];
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            uint32_t v = 0u;
+            if (lv) {
+                const uint16_t two = *reinterpret_cast<const uint16_t *>(tile + (yy + t / 3) * pitch + (xx + t % 3) * 2);
+                const int v0 = (int)(int8_t)(two & 0xff), v1 = (int)(int8_t)(two >> 8);
+                // -1 / 0 / +1 -> bf16 bits 0xBF80 / 0 / 0x3F80
+                const uint32_t h0 = v0 == 0 ? 0u : (v0 > 0 ? 0x3F80u : 0xBF80u), h1 = v1 == 0 ? 0u : (v1 > 0 ? 0x3F80u : 0xBF80u);
+                v = h0 | (h1 << 16);
+            }
+            w[t] = v;
+        }
+        w[9] = 0u;
+        const uint32_t a_row = smem_u32(sA1) + (uint32_t)(row * 128), sw = (uint32_t)(row & 7);
+        // words 0..8 = k 0..17, words 9..17 = k 18..35 (same entries, they meet the lo parts of the filters), k 36..47 = 0
+        sts128(a_row + ((0u ^ sw) << 4), w[0], w[1], w[2], w[3]);
+        sts128(a_row + ((1u ^ sw) << 4), w[4], w[5], w[6], w[7]);
+        sts128(a_row + ((2u ^ sw) << 4), w[8], w[0], w[1], w[2]);
+        sts128(a_row + ((3u ^ sw) << 4), w[3], w[4], w[5], w[6]);
+        sts128(a_row + ((4u ^ sw) << 4), w[7], w[8], w[9], w[9]);
+        sts128(a_row + ((5u ^ sw) << 4), 0u, 0u, 0u, 0u);
+    };
+    auto issue_stem = [&]() {           // D1[128 rows][256 filters] (TMEM columns 0..255) = A1[128][48] x B1[256][48]^T
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            umma_bf16_elect<false>(tmem_base, a1_lo + (uint32_t)(k * 2), b1_lo + (uint32_t)(k * 2), idesc1, k > 0 ? 1u : 0u);
+        umma_commit_elect<false>(&bars[0]);
+    };
+    auto epilogue2 = [&](int i) {       // outputs part*32 .. +31 of this thread's row of half i -> blocked fp32 stream (dead rows as zeros)
+        const bool live = live_of(i);
+        const int row0 = board_of(i) * 256 + (i & 1) * 128 + q * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(part * 32), r);
+        tmem_ld_wait_dep(r);
+        float *outp = p.out_res + ((((size_t)(row0 >> 5)) * 4 + (size_t)part) << 10) + (size_t)(lane * 8);
+        const uint32_t pb = par_addr + 4096 + (uint32_t)(part * 128);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float4 b0 = lds128f(pb + j * 32), b1 = lds128f(pb + j * 32 + 16);
+            float t[8];
+            t[0] = __uint_as_float(r[8 * j]) + b0.x;     t[1] = __uint_as_float(r[8 * j + 1]) + b0.y;
+            t[2] = __uint_as_float(r[8 * j + 2]) + b0.z; t[3] = __uint_as_float(r[8 * j + 3]) + b0.w;
+            t[4] = __uint_as_float(r[8 * j + 4]) + b1.x; t[5] = __uint_as_float(r[8 * j + 5]) + b1.y;
+            t[6] = __uint_as_float(r[8 * j + 6]) + b1.z; t[7] = __uint_as_float(r[8 * j + 7]) + b1.w;
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = live ? t[u] : 0.0f;
+            gaz_conv::stg256(outp + j * 256, t);
+        }
+    };
+
+    if (T > 0) {
+        load_states(0);
+        __syncthreads();
+        im2col(0);
+        if (n_my > 1) load_states(1);
+        fence_proxy_async();
+        __syncthreads();
+        if (warp == 0) { tc_fence_after(); issue_stem(); }
+    }
+#pragma unroll 1
+    for (int i = 0; i < T; i++) {
+        const bool live = live_of(i);
+        const uint32_t mask = live ? 0xffffffffu : 0u;
+        const int row0 = board_of(i) * 256 + (i & 1) * 128 + q * 32;
+        // board k + 1 arrives during half 2k (its tile was last read by the im2col of board k - 1, two syncs ago); the global
+        // load's latency hides behind the wait for the stem MMA
+        if ((i & 1) == 0 && i > 0 && (i >> 1) + 1 < n_my) load_states((i >> 1) + 1);
+        mbar_wait(&bars[0], (uint32_t)(i & 1));
+        tc_fence_after();
+        // ---- epilogue 1: filters part*64 .. +63 of this thread's row
+        {
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64);
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(t_acc, ra);
+            tmem_ld_32x32(t_acc + 32u, rb);
+            tmem_ld_wait_dep(ra);
+            tmem_ld_wait_dep(rb);
+            if (i > 0) {        // the projection of the previous half has read the x0 tiles (and its accumulator is complete)
+                mbar_wait(&bars[1], (uint32_t)((i - 1) & 1));
+                tc_fence_after();
+            }
+            auto piece = [&](const uint32_t (&r)[32], int c) {
+                if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the staging tile
+                __syncwarp();
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const uint32_t o = (uint32_t)((part * 64 + c * 32 + ch * 8) * 4);
+                    const float4 s0 = lds128f(par_addr + o), s1 = lds128f(par_addr + o + 16);
+                    const float4 h0 = lds128f(par_addr + 1024 + o), h1 = lds128f(par_addr + 1024 + o + 16);
+                    float v[8];
+                    const int j = ch * 8;
+                    v[0] = fmaf(s0.x, __uint_as_float(r[j]), h0.x);     v[1] = fmaf(s0.y, __uint_as_float(r[j + 1]), h0.y);
+                    v[2] = fmaf(s0.z, __uint_as_float(r[j + 2]), h0.z); v[3] = fmaf(s0.w, __uint_as_float(r[j + 3]), h0.w);
+                    v[4] = fmaf(s1.x, __uint_as_float(r[j + 4]), h1.x); v[5] = fmaf(s1.y, __uint_as_float(r[j + 5]), h1.y);
+                    v[6] = fmaf(s1.z, __uint_as_float(r[j + 6]), h1.z); v[7] = fmaf(s1.w, __uint_as_float(r[j + 7]), h1.w);
+                    if (p.relu) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) v[u] = fmaxf(v[u], 0.0f);
+                    }
+                    // x0 -> 16-byte chunk c*4 + ch of this row in K-block `part` of the projection's A operand
+                    sts128(a2_row + ((((uint32_t)(c * 4 + ch)) ^ sw7) << 4), pack_bf16x2(v[0], v[1]) & mask, pack_bf16x2(v[2], v[3]) & mask,
+                           pack_bf16x2(v[4], v[5]) & mask, pack_bf16x2(v[6], v[7]) & mask);
+                    const float4 a0 = lds128f(par_addr + 2048 + o), a1 = lds128f(par_addr + 2048 + o + 16);
+                    const float4 t0 = lds128f(par_addr + 3072 + o), t1 = lds128f(par_addr + 3072 + o + 16);
+                    sts128(stage_addr + (uint32_t)(lane * 64) + (((uint32_t)ch ^ sw3) << 4),
+                           pack_relu_bf16x2(fmaf(a0.x, v[0], t0.x), fmaf(a0.y, v[1], t0.y)) & mask,
+                           pack_relu_bf16x2(fmaf(a0.z, v[2], t0.z), fmaf(a0.w, v[3], t0.w)) & mask,
+                           pack_relu_bf16x2(fmaf(a1.x, v[4], t1.x), fmaf(a1.y, v[5], t1.y)) & mask,
+                           pack_relu_bf16x2(fmaf(a1.z, v[6], t1.z), fmaf(a1.w, v[7], t1.w)) & mask);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d_addr(&tmOa, stage_addr, part * 64 + c * 32, row0);
+                    tma_store_commit();
+                }
+            };
+            piece(ra, 0);
+            piece(rb, 1);
+        }
+        if (i > 0) epilogue2(i - 1);
+        if (i + 1 < T) im2col(i + 1);
+        fence_proxy_async();       // x0 tiles / im2col rows: generic-proxy writes that the MMAs read through the async proxy
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            tc_fence_after();
+            if (i + 1 < T) issue_stem();
+            // projection: D2[128 rows][128] (TMEM columns 256..383) = x0[128][256] x Wp[128][256]^T
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    umma_bf16_elect<false>(tmem_base + 256u, a2_lo + (uint32_t)(kb * 1024 + k * 2), b2_lo + (uint32_t)(kb * 1024 + k * 2),
+                                           idesc2, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_elect<false>(&bars[1]);
+        }
+    }
+    if (T > 0) {
+        mbar_wait(&bars[1], (uint32_t)((T - 1) & 1));
+        tc_fence_after();
+        epilogue2(T - 1);
+    }
+    if (lane == 0) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 } // namespace gaz_stem
