@@ -284,19 +284,27 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
     passes = cnt / max(1, n_tc_ops)
     hw = sb.spec["H"] * sb.spec["W"]
 
+    def n_blocks(tag):      # "block+se*5": one launch runs 5 consecutive residual blocks (trunk launch, gaz_block.cuh)
+        return int(tag.split("*")[1]) if "*" in tag else 1
+
     def label(cin, cout, k, tag):
         if tag.startswith("block"):
+            nb = n_blocks(tag)
+            tail = "+SE+skip" if "se" in tag else "+skip"
             if cin != cout:
-                return "residual block 3x3 C%d->C%d, 3x3 C%d->C%d%s" % (cin, cout, cout, cout, "+SE+skip" if "se" in tag else "+skip")
-            return "residual block 2x(3x3 C%d->C%d)%s" % (cin, cout, "+SE+skip" if "se" in tag else "+skip")
+                first = "residual block 3x3 C%d->C%d, 3x3 C%d->C%d%s" % (cin, cout, cout, cout, tail)
+                return first if nb == 1 else "%s followed by %d x residual block 2x(3x3 C%d->C%d)%s, one launch" % (first, nb - 1, cout, cout, tail)
+            return "%sresidual block 2x(3x3 C%d->C%d)%s" % ("%d x " % nb if nb > 1 else "", cin, cout, tail + (", one launch" if nb > 1 else ""))
         return "%dx%d C%d->C%d%s" % (k, k, cin, cout, "+SE" if tag == "se" else "")
 
     def work(cin, cout, k, tag):
         """algorithmic (FLOPs, HBM bytes over live cells) of one launch"""
         cells = leaves_per_launch * hw
         conv = 2.0 * cells * k * k * cin * cout
-        if tag.startswith("block"):   # two convolutions; in: bf16 operand + fp32 residual, out: fp32 residual + bf16 operand
-            return conv + 2.0 * cells * k * k * cout * cout, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
+        if tag.startswith("block"):   # per block two convolutions; in: bf16 operand + fp32 residual, out: fp32 residual + bf16 operand
+            nb = n_blocks(tag)
+            inner = 2.0 * cells * k * k * cout * cout
+            return (conv + inner) + (nb - 1) * 2.0 * inner, cells * ((cin * 2 + cout * 4 + cout * 4 + cout * 2) + (nb - 1) * (cout * 2 + cout * 4 + cout * 4 + cout * 2))
         if tag == "se":
             return conv, cells * (cin * 2 + cout * 4 + cout * 4 + cout * 2)
         return conv, cells * (cin * 2 + cout * 2)
@@ -320,14 +328,15 @@ def dominant_kernel_stats(sb, leaves_per_launch, peaks):
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tp):
         try:
-            tkey = "block_3x3_C%d_C%d" % (cin, cout) if tag.startswith("block") else "%dx%d_C%d_C%d%s" % (k, k, cin, cout, "_se" if tag else "")
+            tkey = "block_3x3_C%d_C%d_x%d" % (cin, cout, n_blocks(tag)) if tag.startswith("block") else "%dx%d_C%d_C%d%s" % (k, k, cin, cout, "_se" if tag else "")
             t = json.load(open(tp)).get(tkey)
             if t and t.get("leaves") == int(round(leaves_per_launch)) and t.get("kernel_sha16") == kernel_sha16():
                 traffic = t.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     if tag.startswith("block"):
-        name = "gaz_block::res_block_kernel (conv1 -> SMEM -> conv2 + SE + skip, tcgen05 cta_group::2 implicit GEMMs)"
+        name = ("gaz_block::res_trunk_kernel, %d residual block(s) per launch (per block: conv1 -> SMEM -> conv2 + SE + skip, tcgen05 "
+                "cta_group::2 implicit GEMMs)" % n_blocks(tag))
     else:
         name = ("gaz_conv::conv_board_kernel<%d, pair> %dx%d C%d->C%d%s (tcgen05 cta_group::2 implicit GEMM)"
                 % (cout, k, k, cin, cout, " + fused SE/skip epilogue" if tag else ""))

@@ -33,6 +33,7 @@ SYMBOLS = {
     "gaz_rounds_net_async": (C.c_int, [_P, C.c_int]),
     "gaz_net_bytes": (C.c_int64, [_P]),
     "gaz_net_launches_per_forward": (C.c_int, [_P]),
+    "gaz_net_op_blocks": (C.c_int, [_P, C.c_int]),
     "gaz_net_profile": (C.c_int, [_P, C.c_int]),
     "gaz_net_profile_read": (C.c_int, [_P, _P, _P, _P]),
     "gaz_net_time_forward": (C.c_int, [_P, C.c_int, C.c_int, _P]),

@@ -21,6 +21,14 @@
 // Both epilogues are software-pipelined (the TMEM load / residual load of the next piece is in flight while the current
 // one is converted) and keep their per-channel parameters out of registers (shared-memory broadcast loads, indexed
 // constant bank).  Cycle accounting per role: build with -DGAZ_BLOCK_CLK, run with debug bit 1024.
+//
+// TRUNK LAUNCHES.  A launch runs up to MAX_LAYERS consecutive residual blocks: every CTA walks its tiles once per layer
+// (layer-major), so tile t of layer l + 1 is processed by the CTA that produced it in layer l, n_my items earlier.  Boards
+// depend only on themselves, so the only cross-layer ordering is inside a CTA: the slab producer waits until the epilogue-2
+// warps have seen their TMA stores of (l, t) complete (per-warp progress counters in shared memory) before it loads (l + 1, t);
+// the fp32 residual is written and re-read by the same thread.  The pipeline (weight ring, slab prefetch, accumulator
+// ping-pong) never drains between layers: the ~25 us of fill / drain and launch gap that every separate block launch pays
+// (a fifth of a 4096-leaf Connect4 block) is paid once per launch.
 #pragma once
 #include "gaz_conv.cuh"
 
@@ -50,18 +58,27 @@ using gaz_conv::SLAB_BYTES;
 using gaz_conv::stg256;
 using gaz_conv::TILE_ROWS;
 
-struct BlockArgs {
-    const int32_t *count;
-    int max_count;
-    int Wp, H, P_pad, n_cells, dbg;   // P_pad divides 256: a tile is 256 / P_pad whole boards (Gomoku 1, Connect4 4, TicTacToe 16)
-    int nkc1;                 // 64-channel K-blocks of conv1's input (2: C_in = 128, 4: C_in = 256)
+constexpr int MAX_LAYERS = 6;   // kernel parameters: 6 x 4.8 KB < 32 KB
+
+struct TrunkLayer {           // one residual block
+    CUtensorMap tmA, tmW1, tmW2, tmOa, tmOb;   // input operand | conv1 / conv2 filters | bf16 outputs
     float par1[3 * 128];      // conv1 bias | BN2 scale | BN2 shift          (constant bank, uniform loads)
     float par2[5 * 128];      // conv2 bias | scale_a | shift_a | scale_b | shift_b
     const float *res;         // blocked fp32 residual stream in
     float *out_raw;           // blocked fp32 residual stream out
     __nv_bfloat16 *out_a, *out_b;
+    int nkc1;                 // 64-channel K-blocks of conv1's input (2: C_in = 128, 4: C_in = 256)
+    int dep;                  // the input operand / residual of this layer are outputs of the previous layer of this launch
     int se, se_r;
     const float *se_w1, *se_b1, *se_w2, *se_b2; // se_b1 has the conv2 bias folded in (b1 + W1^T bias2)
+};
+
+struct TrunkArgs {
+    const int32_t *count;
+    int max_count;
+    int Wp, H, P_pad, n_cells, dbg;   // P_pad divides 256: a tile is 256 / P_pad whole boards (Gomoku 1, Connect4 4, TicTacToe 16)
+    int n_layers;
+    TrunkLayer L[MAX_LAYERS];
 };
 
 struct Cfg {
@@ -69,7 +86,7 @@ struct Cfg {
     static constexpr int W_BYTES = 64 * 128;
     static constexpr int STAGE_BYTES = 8 * 2 * 2048; // epilogue-2 warps: one 32 x 32-channel bf16 tile per output
     static constexpr int SE_FLOATS = 8 * 128 + 128 + 256 + 64 + 128 + 128;
-    static constexpr int SMEM = 2 * SLAB_BYTES + NW * W_BYTES + STAGE_BYTES + 1024 + 512 + SE_FLOATS * 4 + 2 * 128 * 4;
+    static constexpr int SMEM = 2 * SLAB_BYTES + NW * W_BYTES + STAGE_BYTES + 1024 + 512 + SE_FLOATS * 4 + 2 * 128 * 4 + 64;
 };
 
 // per-channel sums of 32 accumulator columns over the 32 rows of a warp: halving butterfly (31 shuffles), lane l ends
@@ -103,9 +120,9 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) { // {h
 // epilogue 2, one 16-column chunk of one row: gate * (conv2 + bias) + residual -> fp32 stream, relu(BN(.)) -> bf16
 // operand(s) of the next layer through the warp's 32 x 32-channel SWIZZLE_64B staging tile (one TMA store per 2 chunks)
 template <int ODD>
-__device__ __forceinline__ void e2_chunk(const uint32_t (&acc)[16], const float (&res)[16], bool use_res, int ck, const BlockArgs &p,
+__device__ __forceinline__ void e2_chunk(const uint32_t (&acc)[16], const float (&res)[16], bool use_res, int ck, const TrunkLayer &p,
                                          float *outp, uint32_t gate_addr, uint32_t bg_addr, uint32_t stage_addr, uint32_t mask,
-                                         int lane, int row0, const CUtensorMap &tmOa, const CUtensorMap &tmOb, int dbg) {
+                                         int lane, int row0, int dbg) {
     const int c0 = ck * 16;
     float v[16];
 #pragma unroll
@@ -149,7 +166,7 @@ __device__ __forceinline__ void e2_chunk(const uint32_t (&acc)[16], const float 
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d_addr(o == 0 ? &tmOa : &tmOb, st, c0 - 16, row0);
+                tma_store_2d_addr(o == 0 ? &p.tmOa : &p.tmOb, st, c0 - 16, row0);
                 tma_store_commit();
             }
         }
@@ -224,9 +241,7 @@ __device__ __forceinline__ void issue_tile(uint32_t d0, uint32_t slab_lo, uint32
 }
 
 __global__ void __launch_bounds__(512, 1)
-res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOa,
-                 const __grid_constant__ CUtensorMap tmOb, const __grid_constant__ BlockArgs p) {
+res_trunk_kernel(const __grid_constant__ TrunkArgs p) {
     constexpr int BN = 128, NW = Cfg::NW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -241,6 +256,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t *tmem_slot = (uint32_t *)(acc1_full + 8);
     float *s_se = (float *)(bars + 64);
     float *s_e1par = s_se + Cfg::SE_FLOATS;   // epilogue 1: BN2 scale[128] | BN2 shift + scale * conv1 bias [128]
+    volatile int *s_done = (volatile int *)(s_e1par + 2 * 128);   // [8]: items whose bf16 stores epilogue-2 warp w has seen complete
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
@@ -250,24 +266,24 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_tiles = (int)(((long long)cnt * p.P_pad + TILE_ROWS - 1) / TILE_ROWS);   // a tile = 256 / P_pad whole boards
     const int bpt = TILE_ROWS / p.P_pad;
     const int n_loop = (n_tiles + 1) / 2;
+    const int n_my = n_loop > pair0 ? (n_loop - pair0 + pair_step - 1) / pair_step : 0;   // items of this CTA per layer
     const int dbg = p.dbg;
+    const int NL = p.n_layers;
 
-    if (threadIdx.x < 128) {
-        const float sc = p.par1[128 + threadIdx.x];
-        s_e1par[threadIdx.x] = sc;
-        s_e1par[128 + threadIdx.x] = fmaf(sc, p.par1[threadIdx.x], p.par1[256 + threadIdx.x]);
-    }
+    if (threadIdx.x < 8) s_done[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
         for (int s = 0; s < NW; s++) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int h = 0; h < 2; h++) { mbar_init(&acc1_full[h], 1); mbar_init(&e1_done[h], 8); } // 4 epilogue-1 warps of each CTA
         for (int a = 0; a < 2; a++) { mbar_init(&acc2_full[a], 1); mbar_init(&acc2_empty[a], 16); } // 8 epilogue-2 warps of each CTA
         fence_barrier_init();
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmW1);
-        tma_prefetch_desc(&tmW2);
-        if (p.out_a) tma_prefetch_desc(&tmOa);
-        if (p.out_b) tma_prefetch_desc(&tmOb);
+        for (int l = 0; l < NL; l++) {
+            tma_prefetch_desc(&p.L[l].tmA);
+            tma_prefetch_desc(&p.L[l].tmW1);
+            tma_prefetch_desc(&p.L[l].tmW2);
+            if (p.L[l].out_a) tma_prefetch_desc(&p.L[l].tmOa);
+            if (p.L[l].out_b) tma_prefetch_desc(&p.L[l].tmOb);
+        }
     }
     if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
@@ -287,42 +303,54 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the first visit and rewinds its ring position for the second, so the producer's order and the 36 tiles per board
     // are unchanged, and so is the order in which every accumulator row sees its (K-block, tap) terms.
     // C_in = 256 (K-blocks 2, 3 overwrite 0, 1): conv1 is issued whole, conv2 as above.
-    const bool defer = p.nkc1 == 2;
     const uint32_t sH_addr = smem_u32(sH), par_addr = smem_u32(s_e1par);
     const bool e1_off = (dbg & 512) != 0;
 
     if (warp == 0) { // ---------------- slab TMA producer (one lane)
-        const int half = p.nkc1 >> 1;
-        int it = 0;
-        if (lane == 0)
-            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) { // K-block kc of the input goes to slab kc & 1
-                const int t = 2 * lt + rank;
-                const int row0 = t * TILE_ROWS - HALO;
-                for (int kc = 0; kc < p.nkc1; kc++) {
-                    const int sl = kc & 1;
-                    const uint32_t use = (uint32_t)(it * half + (kc >> 1));   // how often slab sl has been filled before
-                    mbar_wait(&x_empty[sl], (use & 1) ^ 1);
-                    if (rank == 0) mbar_expect_tx(&x_full[sl], 2 * SLAB_BYTES);
-                    uint8_t *dst = sX + sl * SLAB_BYTES;
-                    tma_load_2d_pair(dst, &tmA, &x_full[sl], kc * 64, row0);
-                    tma_load_2d_pair(dst + SLAB_BYTES / 2, &tmA, &x_full[sl], kc * 64, row0 + SLAB_BOX_ROWS);
+        if (lane == 0) {
+            uint32_t fills[2] = {0u, 0u};     // how often each slab has been filled
+            int it = 0;
+            for (int l = 0; l < NL; l++) {
+                const TrunkLayer &L = p.L[l];
+                for (int lt = pair0; lt < n_loop; lt += pair_step, it++) { // K-block kc of the input goes to slab kc & 1
+                    const int t = 2 * lt + rank;
+                    const int row0 = t * TILE_ROWS - HALO;
+                    if (L.dep) {   // the previous layer's outputs for this tile (item it - n_my) have reached global memory
+                        const int need = it - n_my + 1;
+                        for (int w = 0; w < 8; w++)
+                            while (s_done[w] < need) { }
+                        __threadfence();
+                    }
+                    for (int kc = 0; kc < L.nkc1; kc++) {
+                        const int sl = kc & 1;
+                        mbar_wait(&x_empty[sl], (fills[sl] & 1) ^ 1);
+                        fills[sl]++;
+                        if (rank == 0) mbar_expect_tx(&x_full[sl], 2 * SLAB_BYTES);
+                        uint8_t *dst = sX + sl * SLAB_BYTES;
+                        tma_load_2d_pair(dst, &L.tmA, &x_full[sl], kc * 64, row0);
+                        tma_load_2d_pair(dst + SLAB_BYTES / 2, &L.tmA, &x_full[sl], kc * 64, row0 + SLAB_BOX_ROWS);
+                    }
                 }
             }
+        }
     } else if (warp == 1) { // ---------------- weight-tile TMA producer (one lane), tiles in the issuer's order
         if (lane == 0) {
             Ring r;
-            auto load = [&](int cv, int kc, int tap, int cin) {
+            auto load = [&](const CUtensorMap *tm, int kc, int tap, int cin) {
                 mbar_wait(&w_empty[r.idx], r.phase ^ 1);
                 if (rank == 0) mbar_expect_tx(&w_full[r.idx], 2 * Cfg::W_BYTES);
-                tma_load_2d_pair(sW + r.idx * Cfg::W_BYTES, cv == 0 ? &tmW1 : &tmW2, &w_full[r.idx], tap * cin + kc * 64, rank * 64);
+                tma_load_2d_pair(sW + r.idx * Cfg::W_BYTES, tm, &w_full[r.idx], tap * cin + kc * 64, rank * 64);
                 r.advance(NW);
             };
-            for (int lt = pair0; lt < n_loop; lt += pair_step) {
-                const int cin1 = p.nkc1 * 64;
-                for (int kc = 0; kc < p.nkc1; kc++)
-                    for (int tap = 0; tap < 9; tap++) load(0, kc, tap, cin1);
-                for (int kc = 0; kc < 2; kc++)
-                    for (int tap = 0; tap < 9; tap++) load(1, kc, tap, 128);
+            for (int l = 0; l < NL; l++) {
+                const TrunkLayer &L = p.L[l];
+                const int cin1 = L.nkc1 * 64;
+                for (int lt = pair0; lt < n_loop; lt += pair_step) {
+                    for (int kc = 0; kc < L.nkc1; kc++)
+                        for (int tap = 0; tap < 9; tap++) load(&L.tmW1, kc, tap, cin1);
+                    for (int kc = 0; kc < 2; kc++)
+                        for (int tap = 0; tap < 9; tap++) load(&L.tmW2, kc, tap, 128);
+                }
             }
         }
     } else if (warp == 2) {
@@ -330,6 +358,7 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
             Ring rw;
             uint32_t ph = 0;
+            uint32_t got[2] = {0u, 0u};       // how often each slab has been consumed as a conv1 input
             int it = 0;
             [[maybe_unused]] long long tk_e2 = 0, tk_e1 = 0, tk_w = 0, tk_x = 0, tk0 = 0, tq = 0;
             TK_START(tk0);
@@ -345,58 +374,63 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (RELEASE_) umma_commit_elect<true>(&w_empty[rw.idx]);                                                       \
         rw.advance(NW);                                                                                                \
     } while (0)
-            for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1, it++) {
-                // Accumulator set `as` (256 TMEM columns) serves BOTH convolutions of this board: conv1 fills it, epilogue 1
-                // drains it into slab H, conv2 refills it, epilogue 2 reads it - while the next board already runs both of
-                // its convolutions in the other set.
-                const int as = it & 1;
-                const uint32_t sph = (uint32_t)((it >> 1) & 1);
-                const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * BN);
-                // ---- conv1
-                TK_BEGIN();
-                mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
-                TK_END(tk_e2);
-                tc_fence_after();
-                Ring hold;
-                for (int kc = 0; kc < p.nkc1; kc++) {
-                    const int sl = kc & 1;
+            for (int l = 0; l < NL; l++) {
+                const int nkc1 = p.L[l].nkc1;
+                const bool defer = nkc1 == 2;
+                for (int lt = pair0; lt < n_loop; lt += pair_step, ph ^= 1, it++) {
+                    // Accumulator set `as` (256 TMEM columns) serves BOTH convolutions of this board: conv1 fills it, epilogue 1
+                    // drains it into slab H, conv2 refills it, epilogue 2 reads it - while the next board already runs both of
+                    // its convolutions in the other set.
+                    const int as = it & 1;
+                    const uint32_t sph = (uint32_t)((it >> 1) & 1);
+                    const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * BN);
+                    // ---- conv1
                     TK_BEGIN();
-                    mbar_wait(&x_full[sl], (uint32_t)(it * (p.nkc1 >> 1) + (kc >> 1)) & 1u);
-                    TK_END(tk_x);
+                    mbar_wait(&acc2_empty[as], sph ^ 1);  // epilogue 2 of board it-2 has drained this set
+                    TK_END(tk_e2);
                     tc_fence_after();
-                    for (int tap = 0; tap < 4; tap++) TILE(3, sl, kc, tap, true);
-                    if (defer && kc == 1) {
-                        hold = rw;
-                        for (int tap = 4; tap < 9; tap++) TILE(1, sl, kc, tap, false);   // tiles stay for phase C
-                    } else {
-                        for (int tap = 4; tap < 9; tap++) TILE(3, sl, kc, tap, true);
+                    Ring hold;
+                    for (int kc = 0; kc < nkc1; kc++) {
+                        const int sl = kc & 1;
+                        TK_BEGIN();
+                        mbar_wait(&x_full[sl], got[sl] & 1u);
+                        got[sl]++;
+                        TK_END(tk_x);
+                        tc_fence_after();
+                        for (int tap = 0; tap < 4; tap++) TILE(3, sl, kc, tap, true);
+                        if (defer && kc == 1) {
+                            hold = rw;
+                            for (int tap = 4; tap < 9; tap++) TILE(1, sl, kc, tap, false);   // tiles stay for phase C
+                        } else {
+                            for (int tap = 4; tap < 9; tap++) TILE(3, sl, kc, tap, true);
+                        }
+                        if (kc + 2 < nkc1) umma_commit_elect<true>(&x_empty[sl]);   // C_in = 256: the slab takes K-block kc + 2 next
                     }
-                    if (kc + 2 < p.nkc1) umma_commit_elect<true>(&x_empty[sl]);   // C_in = 256: the slab takes K-block kc + 2 next
-                }
-                umma_commit_elect<true>(&acc1_full[0]);
-                if (defer) {
+                    umma_commit_elect<true>(&acc1_full[0]);
+                    if (defer) {
+                        rw = hold;
+                        for (int tap = 4; tap < 9; tap++) TILE(2, 1, 1, tap, true);          // phase C
+                    }
+                    umma_commit_elect<true>(&acc1_full[1]);
+                    // ---- conv2 (input: slab H = the two slabs, rewritten in place by epilogue 1)
+                    TK_BEGIN();
+                    mbar_wait(&e1_done[0], ph);            // half 0 of the set drained, rows 0..127 of H written (both CTAs)
+                    TK_END(tk_e1);
+                    tc_fence_after();
+                    hold = rw;
+                    for (int tap = 0; tap < 6; tap++) TILE(1, 0, 0, tap, false);             // phase D, tiles stay for E
+                    TK_BEGIN();
+                    mbar_wait(&e1_done[1], ph);            // half 1 drained, rows 128..255 written
+                    TK_END(tk_e1);
+                    tc_fence_after();
                     rw = hold;
-                    for (int tap = 4; tap < 9; tap++) TILE(2, 1, 1, tap, true);          // phase C
+                    for (int tap = 0; tap < 6; tap++) TILE(2, 0, 0, tap, true);              // phase E
+                    for (int tap = 6; tap < 9; tap++) TILE(3, 0, 0, tap, true);
+                    umma_commit_elect<true>(&x_empty[0]);  // conv2 has read K-block 0 of H: the slab is free for the next board
+                    for (int tap = 0; tap < 9; tap++) TILE(3, 1, 1, tap, true);
+                    umma_commit_elect<true>(&x_empty[1]);
+                    umma_commit_elect<true>(&acc2_full[as]);
                 }
-                umma_commit_elect<true>(&acc1_full[1]);
-                // ---- conv2 (input: slab H = the two slabs, rewritten in place by epilogue 1)
-                TK_BEGIN();
-                mbar_wait(&e1_done[0], ph);            // half 0 of the set drained, rows 0..127 of H written (both CTAs)
-                TK_END(tk_e1);
-                tc_fence_after();
-                hold = rw;
-                for (int tap = 0; tap < 6; tap++) TILE(1, 0, 0, tap, false);             // phase D, tiles stay for E
-                TK_BEGIN();
-                mbar_wait(&e1_done[1], ph);            // half 1 drained, rows 128..255 written
-                TK_END(tk_e1);
-                tc_fence_after();
-                rw = hold;
-                for (int tap = 0; tap < 6; tap++) TILE(2, 0, 0, tap, true);              // phase E
-                for (int tap = 6; tap < 9; tap++) TILE(3, 0, 0, tap, true);
-                umma_commit_elect<true>(&x_empty[0]);  // conv2 has read K-block 0 of H: the slab is free for the next board
-                for (int tap = 0; tap < 9; tap++) TILE(3, 1, 1, tap, true);
-                umma_commit_elect<true>(&x_empty[1]);
-                umma_commit_elect<true>(&acc2_full[as]);
             }
 #undef TILE
             if ((dbg & 1024) && blockIdx.x == 0 && lane == 0)
@@ -408,20 +442,30 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= 4 && warp < 8) { // ---------------- epilogue 1 (acc1 -> relu(BN2(conv1 + b1)) -> slab, bf16, swizzled), half 0 then half 1
         const int e1_q = warp & 3;
+        const int e1t = threadIdx.x - 128;   // 0..127
         int it = 0;
         [[maybe_unused]] long long tk_work = 0, tq = 0;
-        for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
-            const bool work = (2 * lt + rank) < n_tiles && !e1_off;
-            TK_BEGIN();
-#pragma unroll 1
-            for (int h = 0; h < 2; h++) {
-                const int pos = h * 128 + e1_q * 32 + lane;
-                const int bp = pos % p.P_pad, yy = bp / p.Wp;
-                const bool live = yy != 0 && yy <= p.H && (bp % p.Wp) != p.Wp - 1 && (2 * lt + rank) * bpt + pos / p.P_pad < cnt;
-                const uint32_t t_sub = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)((it & 1) * 2 * BN + h * BN);
-                e1_half(&acc1_full[h], &e1_done[h], (uint32_t)(it & 1), work, t_sub, par_addr, sH_addr, HALO + pos, live, lane);
+        for (int l = 0; l < NL; l++) {
+            {   // this layer's BN2 scale and bias-folded shift (the four epilogue-1 warps own the table)
+                named_bar_sync(2, 128);
+                const float sc = p.L[l].par1[128 + e1t];
+                s_e1par[e1t] = sc;
+                s_e1par[128 + e1t] = fmaf(sc, p.L[l].par1[e1t], p.L[l].par1[256 + e1t]);
+                named_bar_sync(2, 128);
             }
-            TK_END(tk_work);
+            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
+                const bool work = (2 * lt + rank) < n_tiles && !e1_off;
+                TK_BEGIN();
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    const int pos = h * 128 + e1_q * 32 + lane;
+                    const int bp = pos % p.P_pad, yy = bp / p.Wp;
+                    const bool live = yy != 0 && yy <= p.H && (bp % p.Wp) != p.Wp - 1 && (2 * lt + rank) * bpt + pos / p.P_pad < cnt;
+                    const uint32_t t_sub = tmem_base + ((uint32_t)(e1_q * 32) << 16) + (uint32_t)((it & 1) * 2 * BN + h * BN);
+                    e1_half(&acc1_full[h], &e1_done[h], (uint32_t)(it & 1), work, t_sub, par_addr, sH_addr, HALO + pos, live, lane);
+                }
+                TK_END(tk_work);
+            }
         }
         if ((dbg & 1024) && blockIdx.x == 0 && warp == 4 && lane == 0) TK_PRINT("epilogue1: wait + work %lld\n", tk_work);
     } else if (warp >= 8) { // ---------------- epilogue 2: SE + skip add + outputs (acc2)
@@ -436,147 +480,161 @@ res_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int pos = sub * 128 + q * 32 + lane;          // row of the tile: the same for every tile of this thread
         const int bp = pos % p.P_pad;
         const bool live_pos = (bp / p.Wp) != 0 && (bp / p.Wp) <= p.H && (bp % p.Wp) != p.Wp - 1;
-        const bool use_res = p.res && !(dbg & 8);
-        const bool do_se = p.se && !(dbg & 64);
-        if (!do_se) { // no gate: out = conv2 + bias (+ residual)
-            if (et < BN) { s_gate[et] = 1.0f; s_bg[et] = p.par2[et]; }
-            named_bar_sync(1, 256);
-        }
         const uint32_t gate_addr = smem_u32(s_gate), bg_addr = smem_u32(s_bg);
         const uint32_t stage_addr = smem_u32(sStage + ew * 2 * 2048);
         int it = 0;
         [[maybe_unused]] long long tk_wait = 0, tk_se = 0, tk_out = 0, tq = 0;
-        for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
-            const int t = 2 * lt + rank;
-            const int as = it & 1;
-            const uint32_t sph = (uint32_t)((it >> 1) & 1);
-            if (t >= n_tiles) { // dummy half of the last pair
+        for (int l = 0; l < NL; l++) {
+            const TrunkLayer &L = p.L[l];
+            const bool use_res = L.res && !(dbg & 8);
+            const bool do_se = L.se && !(dbg & 64);
+            if (!do_se) { // no gate: out = conv2 + bias (+ residual); the table is rewritten once every warp has left the previous layer
+                named_bar_sync(1, 256);
+                if (et < BN) { s_gate[et] = 1.0f; s_bg[et] = L.par2[et]; }
+                named_bar_sync(1, 256);
+            }
+            for (int lt = pair0; lt < n_loop; lt += pair_step, it++) {
+                const int t = 2 * lt + rank;
+                const int as = it & 1;
+                const uint32_t sph = (uint32_t)((it >> 1) & 1);
+                if (t >= n_tiles) { // dummy half of the last pair
+                    mbar_wait(&acc2_full[as], sph);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive_leader(&acc2_empty[as]); s_done[ew] = it + 1; }
+                    continue;
+                }
+                // blocked fp32 layout (f32_blk_index): the 32 rows x 128 channels of this warp are 16 KB contiguous; 8-channel
+                // piece k of this thread's row sits at + k * 256 floats
+                const size_t rbase = ((size_t)(t * 8 + sub * 4 + q) << 12) + (size_t)(lane * 8);
+                const float *resp = L.res + rbase;
+                float *outp = L.out_raw + rbase;
+                const int row0 = t * TILE_ROWS + sub * 128 + q * 32;   // first row of this warp (TMA store coordinate)
+                const bool live = live_pos && t * bpt + pos / p.P_pad < cnt;     // boards past the last one of the batch stay zero
+                const uint32_t mask = live ? 0xffffffffu : 0u;
+                float resA[16], resB[16];
+                if (use_res) {
+#pragma unroll 1
+                    for (int k = 4; k < 16; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(resp + k * 256));
+                    ldg256(resp, *reinterpret_cast<float(*)[8]>(&resA[0]));
+                    ldg256(resp + 256, *reinterpret_cast<float(*)[8]>(&resA[8]));
+                }
+                TK_BEGIN();
                 mbar_wait(&acc2_full[as], sph);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&acc2_empty[as]);
-                continue;
-            }
-            // blocked fp32 layout (f32_blk_index): the 32 rows x 128 channels of this warp are 16 KB contiguous; 8-channel
-            // piece k of this thread's row sits at + k * 256 floats
-            const size_t rbase = ((size_t)(t * 8 + sub * 4 + q) << 12) + (size_t)(lane * 8);
-            const float *resp = p.res + rbase;
-            float *outp = p.out_raw + rbase;
-            const int row0 = t * TILE_ROWS + sub * 128 + q * 32;   // first row of this warp (TMA store coordinate)
-            const bool live = live_pos && t * bpt + pos / p.P_pad < cnt;     // boards past the last one of the batch stay zero
-            const uint32_t mask = live ? 0xffffffffu : 0u;
-            float resA[16], resB[16];
-            if (use_res) {
+                TK_END(tk_wait);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + sub * BN);
+                TK_BEGIN();
+                if (do_se) {
+                    // ---- pass 1: per-channel sums over the live cells of this warp's 32 rows (32-column pieces, the TMEM load
+                    // of the next piece in flight while this one is folded)
+                    {
+                        uint32_t ra[32], rb[32];
+                        float *dst = s_part + ew * BN;
+                        tmem_ld_32x32(t_acc, ra);
 #pragma unroll 1
-                for (int k = 4; k < 16; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(resp + k * 256));
-                ldg256(resp, *reinterpret_cast<float(*)[8]>(&resA[0]));
-                ldg256(resp + 256, *reinterpret_cast<float(*)[8]>(&resA[8]));
-            }
-            TK_BEGIN();
-            mbar_wait(&acc2_full[as], sph);
-            TK_END(tk_wait);
-            tc_fence_after();
-            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + sub * BN);
-            TK_BEGIN();
-            if (do_se) {
-                // ---- pass 1: per-channel sums over the live cells of this warp's 32 rows (32-column pieces, the TMEM load
-                // of the next piece in flight while this one is folded)
-                {
-                    uint32_t ra[32], rb[32];
-                    float *dst = s_part + ew * BN;
-                    tmem_ld_32x32(t_acc, ra);
-#pragma unroll 1
-                    for (int h = 0; h < 2; h++) {
-                        tmem_ld_wait_dep(ra);
-                        tmem_ld_32x32(t_acc + (uint32_t)(h * 64 + 32), rb);
-                        colsum32(ra, mask, lane, dst + h * 64);
-                        tmem_ld_wait_dep(rb);
-                        if (h == 0) tmem_ld_32x32(t_acc + 64u, ra);
-                        colsum32(rb, mask, lane, dst + h * 64 + 32);
-                    }
-                }
-                named_bar_sync(1, 256);
-                if (et < BN) { // board mean per channel
-                    float sum = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) sum += s_part[k * BN + et];
-                    s_mean[et] = sum * inv_cells;
-                }
-                named_bar_sync(1, 256);
-                {   // dense1 (C -> R): output j, quarter `part` of the inputs
-                    const int j = et & 63, part = et >> 6;
-                    if (j < p.se_r) {
-                        const float *w1 = p.se_w1 + (size_t)(part * 32) * p.se_r + j;
-                        const float4 *m4 = reinterpret_cast<const float4 *>(s_mean + part * 32);
-                        float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float4 m = m4[i];
-                            h0 = fmaf(m.x, __ldg(w1 + (size_t)(4 * i) * p.se_r), h0);
-                            h1 = fmaf(m.y, __ldg(w1 + (size_t)(4 * i + 1) * p.se_r), h1);
-                            h2 = fmaf(m.z, __ldg(w1 + (size_t)(4 * i + 2) * p.se_r), h2);
-                            h3 = fmaf(m.w, __ldg(w1 + (size_t)(4 * i + 3) * p.se_r), h3);
+                        for (int h = 0; h < 2; h++) {
+                            tmem_ld_wait_dep(ra);
+                            tmem_ld_32x32(t_acc + (uint32_t)(h * 64 + 32), rb);
+                            colsum32(ra, mask, lane, dst + h * 64);
+                            tmem_ld_wait_dep(rb);
+                            if (h == 0) tmem_ld_32x32(t_acc + 64u, ra);
+                            colsum32(rb, mask, lane, dst + h * 64 + 32);
                         }
-                        s_hp[part * 64 + j] = (h0 + h1) + (h2 + h3);
                     }
-                }
-                named_bar_sync(1, 256);
-                if (et < p.se_r) s_h[et] = fmaxf(((s_hp[et] + s_hp[64 + et]) + (s_hp[128 + et] + s_hp[192 + et])) + __ldg(p.se_b1 + et), 0.0f);
-                named_bar_sync(1, 256);
-                {   // dense2 (R -> C): output channel cc, half `part` of the hidden units
-                    const int cc = et & 127, part = et >> 7;
-                    const int r2 = p.se_r >> 1;
-                    const float *w2 = p.se_w2 + (size_t)(part * r2) * BN + cc;
-                    const float *hh = s_h + part * r2;
-                    float g0 = 0.0f, g1 = 0.0f;
+                    named_bar_sync(1, 256);
+                    if (et < BN) { // board mean per channel
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) sum += s_part[k * BN + et];
+                        s_mean[et] = sum * inv_cells;
+                    }
+                    named_bar_sync(1, 256);
+                    {   // dense1 (C -> R): output j, quarter `part` of the inputs
+                        const int j = et & 63, part = et >> 6;
+                        if (j < L.se_r) {
+                            const float *w1 = L.se_w1 + (size_t)(part * 32) * L.se_r + j;
+                            const float4 *m4 = reinterpret_cast<const float4 *>(s_mean + part * 32);
+                            float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const float4 m = m4[i];
+                                h0 = fmaf(m.x, __ldg(w1 + (size_t)(4 * i) * L.se_r), h0);
+                                h1 = fmaf(m.y, __ldg(w1 + (size_t)(4 * i + 1) * L.se_r), h1);
+                                h2 = fmaf(m.z, __ldg(w1 + (size_t)(4 * i + 2) * L.se_r), h2);
+                                h3 = fmaf(m.w, __ldg(w1 + (size_t)(4 * i + 3) * L.se_r), h3);
+                            }
+                            s_hp[part * 64 + j] = (h0 + h1) + (h2 + h3);
+                        }
+                    }
+                    named_bar_sync(1, 256);
+                    if (et < L.se_r) s_h[et] = fmaxf(((s_hp[et] + s_hp[64 + et]) + (s_hp[128 + et] + s_hp[192 + et])) + __ldg(L.se_b1 + et), 0.0f);
+                    named_bar_sync(1, 256);
+                    {   // dense2 (R -> C): output channel cc, half `part` of the hidden units
+                        const int cc = et & 127, part = et >> 7;
+                        const int r2 = L.se_r >> 1;
+                        const float *w2 = L.se_w2 + (size_t)(part * r2) * BN + cc;
+                        const float *hh = s_h + part * r2;
+                        float g0 = 0.0f, g1 = 0.0f;
 #pragma unroll 8
-                    for (int i = 0; i < r2; i += 2) {
-                        g0 = fmaf(hh[i], __ldg(w2 + (size_t)(i) * BN), g0);
-                        g1 = fmaf(hh[i + 1], __ldg(w2 + (size_t)(i + 1) * BN), g1);
-                    }
-                    s_gp[part * BN + cc] = g0 + g1;
-                }
-                named_bar_sync(1, 256);
-                if (et < BN) {
-                    const float g = 1.0f / (1.0f + expf(-((s_gp[et] + s_gp[BN + et]) + p.se_b2[et])));
-                    s_gate[et] = g;
-                    s_bg[et] = g * p.par2[et];   // gate * (conv2 + bias) = fma(conv2, gate, gate * bias)
-                }
-                named_bar_sync(1, 256);
-            }
-            TK_END(tk_se);
-            TK_BEGIN();
-            // ---- output pass: 16-column chunks in pairs (A, B); TMEM load and residual load of the next chunk are in
-            // flight while the current one is written
-            {
-                uint32_t accA[16], accB[16];
-                tmem_ld_32x16(t_acc, accA);
-#pragma unroll 1
-                for (int cp = 0; cp < 4; cp++) {
-                    const int ck = 2 * cp;
-                    tmem_ld_wait_dep(accA);
-                    tmem_ld_32x16(t_acc + (uint32_t)(ck * 16 + 16), accB);
-                    if (use_res) {
-                        ldg256(resp + (2 * ck + 2) * 256, *reinterpret_cast<float(*)[8]>(&resB[0]));
-                        ldg256(resp + (2 * ck + 3) * 256, *reinterpret_cast<float(*)[8]>(&resB[8]));
-                    }
-                    e2_chunk<0>(accA, resA, use_res, ck, p, outp, gate_addr, bg_addr, stage_addr, mask, lane, row0, tmOa, tmOb, dbg);
-                    tmem_ld_wait_dep(accB);
-                    if (cp < 3) {
-                        tmem_ld_32x16(t_acc + (uint32_t)(ck * 16 + 32), accA);
-                        if (use_res) {
-                            ldg256(resp + (2 * ck + 4) * 256, *reinterpret_cast<float(*)[8]>(&resA[0]));
-                            ldg256(resp + (2 * ck + 5) * 256, *reinterpret_cast<float(*)[8]>(&resA[8]));
+                        for (int i = 0; i < r2; i += 2) {
+                            g0 = fmaf(hh[i], __ldg(w2 + (size_t)(i) * BN), g0);
+                            g1 = fmaf(hh[i + 1], __ldg(w2 + (size_t)(i + 1) * BN), g1);
                         }
-                    } else { // the accumulator set is in registers: hand it back to the MMA issuer before the last stores
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_leader(&acc2_empty[as]);
+                        s_gp[part * BN + cc] = g0 + g1;
                     }
-                    e2_chunk<1>(accB, resB, use_res, ck + 1, p, outp, gate_addr, bg_addr, stage_addr, mask, lane, row0, tmOa, tmOb, dbg);
+                    named_bar_sync(1, 256);
+                    if (et < BN) {
+                        const float g = 1.0f / (1.0f + expf(-((s_gp[et] + s_gp[BN + et]) + L.se_b2[et])));
+                        s_gate[et] = g;
+                        s_bg[et] = g * L.par2[et];   // gate * (conv2 + bias) = fma(conv2, gate, gate * bias)
+                    }
+                    named_bar_sync(1, 256);
                 }
+                TK_END(tk_se);
+                TK_BEGIN();
+                // ---- output pass: 16-column chunks in pairs (A, B); TMEM load and residual load of the next chunk are in
+                // flight while the current one is written
+                {
+                    uint32_t accA[16], accB[16];
+                    tmem_ld_32x16(t_acc, accA);
+#pragma unroll 1
+                    for (int cp = 0; cp < 4; cp++) {
+                        const int ck = 2 * cp;
+                        tmem_ld_wait_dep(accA);
+                        tmem_ld_32x16(t_acc + (uint32_t)(ck * 16 + 16), accB);
+                        if (use_res) {
+                            ldg256(resp + (2 * ck + 2) * 256, *reinterpret_cast<float(*)[8]>(&resB[0]));
+                            ldg256(resp + (2 * ck + 3) * 256, *reinterpret_cast<float(*)[8]>(&resB[8]));
+                        }
+                        e2_chunk<0>(accA, resA, use_res, ck, L, outp, gate_addr, bg_addr, stage_addr, mask, lane, row0, dbg);
+                        tmem_ld_wait_dep(accB);
+                        if (cp < 3) {
+                            tmem_ld_32x16(t_acc + (uint32_t)(ck * 16 + 32), accA);
+                            if (use_res) {
+                                ldg256(resp + (2 * ck + 4) * 256, *reinterpret_cast<float(*)[8]>(&resA[0]));
+                                ldg256(resp + (2 * ck + 5) * 256, *reinterpret_cast<float(*)[8]>(&resA[8]));
+                            }
+                        } else { // the accumulator set is in registers: hand it back to the MMA issuer before the last stores
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_leader(&acc2_empty[as]);
+                        }
+                        e2_chunk<1>(accB, resB, use_res, ck + 1, L, outp, gate_addr, bg_addr, stage_addr, mask, lane, row0, dbg);
+                    }
+                }
+                // a following layer of this launch reads this tile's bf16 operand back through TMA: publish once the stores of
+                // this warp have completed (the fp32 stream is re-read by the very thread that wrote it)
+                if (l + 1 < NL) {
+                    if (lane == 0) {
+                        tma_store_wait_all();
+                        __threadfence();
+                        s_done[ew] = it + 1;
+                    }
+                    __syncwarp();
+                }
+                TK_END(tk_out);
             }
-            TK_END(tk_out);
         }
         if ((dbg & 1024) && blockIdx.x == 0 && (warp == 8 || warp == 15) && lane == 0)
             TK_PRINT("epilogue2 warp %d: wait_acc %lld se %lld out %lld\n", warp, tk_wait, tk_se, tk_out);

@@ -380,6 +380,8 @@ struct NetOp {
     int skip;             // SE op folded into the previous conv
     int block_fused;      // this conv1 runs the whole residual block (gaz_block.cuh) together with the next conv (+SE)
     int in_block;         // this conv2 is executed by the previous op's fused block kernel
+    int trunk_len;        // block_fused conv1 that starts a launch: number of consecutive residual blocks the launch runs (1..MAX_LAYERS)
+    int in_trunk;         // block_fused conv1 whose block runs inside an earlier op's trunk launch
     int dxm;              // 3x3 C -> 32 convolution run dx-merged (conv_board_kernel<96>): d_wt = filters repacked [dx*32+c][dy*Cin+k]
     int dual_partner;     // HEADCONV: index of a later head convolution on the same fp32 input that this op's launch computes
     int dual_skip;        // as well (gaz_small::headconv_wide_kernel, N = 16); dual_skip marks that later op
@@ -389,6 +391,8 @@ struct NetOp {
     int head_G;           // boards per CTA iteration of the wide head convolution / the mma stem
     int chain_len;        // DENSE: this op starts a chain of chain_len dense layers run by ONE mlp_chain_kernel launch
     int chain_skip;       // DENSE executed by an earlier op's chain launch
+    int chain_partner;    // DENSE chain start: index of a later chain whose input is already complete; it runs in this launch (grid.y = 2)
+    int chain_joined;     // DENSE chain start executed by an earlier chain's launch
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
     float *d_se_b1;       // fused SE: dense1 bias with the conv bias folded in (b1 + W1^T bias)
     // dense layer on the tensor cores (DENSE op fed by a HEADCONV op): bf16 activated input + bf16 [Out][In] weights
@@ -467,25 +471,35 @@ template <int BN> static int launch_conv_board(gaz_net *n, NetOp &op, const gaz_
     return 0;
 }
 
-static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *count, cudaStream_t s) {
+// one launch = trunk_len consecutive residual blocks starting at op `first` (gaz_block.cuh)
+static int launch_res_trunk(gaz_net *n, size_t first, const int32_t *count, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        CKN(cudaFuncSetAttribute(gaz_block::res_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_block::Cfg::SMEM));
+        CKN(cudaFuncSetAttribute(gaz_block::res_trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gaz_block::Cfg::SMEM));
         attr_set = true;
     }
     auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
-    gaz_block::BlockArgs a;
+    static gaz_block::TrunkArgs a;   // 29 KB: kept off the stack; the launch copies it
     memset(&a, 0, sizeof a);
     a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.H = n->H; a.P_pad = n->P_pad; a.n_cells = n->H * n->W; a.dbg = n->dbg;
-    a.nkc1 = c1.d.cin / 64;
-    memcpy(a.par1, c1.par, sizeof a.par1);   // conv1 bias | BN2 scale | BN2 shift
-    memcpy(a.par2, c2.par, sizeof a.par2);
-    const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
-    a.res = (const float *)buf(o.res_buf); a.out_raw = (float *)buf(o.out_raw);
-    a.out_a = (__nv_bfloat16 *)buf(o.out_a); a.out_b = (__nv_bfloat16 *)buf(o.out_b);
-    if (c2.fused_se) {
-        a.se = 1; a.se_r = c2.se.cin;
-        a.se_w1 = n->wf + c2.se.w2; a.se_b1 = c2.d_se_b1; a.se_w2 = n->wf + c2.se.w3; a.se_b2 = n->wf + c2.se.bias3;
+    a.n_layers = n->ops[first].trunk_len;
+    size_t oi = first;
+    for (int l = 0; l < a.n_layers; l++) {
+        NetOp &c1 = n->ops[oi], &c2 = n->ops[oi + 1];
+        gaz_block::TrunkLayer &L = a.L[l];
+        L.tmA = c1.tmA2; L.tmW1 = c1.tmB2; L.tmW2 = c2.tmB2; L.tmOa = c2.tmOa; L.tmOb = c2.tmOb;
+        L.nkc1 = c1.d.cin / 64;
+        L.dep = l > 0;
+        memcpy(L.par1, c1.par, sizeof L.par1);   // conv1 bias | BN2 scale | BN2 shift
+        memcpy(L.par2, c2.par, sizeof L.par2);
+        const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
+        L.res = (const float *)buf(o.res_buf); L.out_raw = (float *)buf(o.out_raw);
+        L.out_a = (__nv_bfloat16 *)buf(o.out_a); L.out_b = (__nv_bfloat16 *)buf(o.out_b);
+        if (c2.fused_se) {
+            L.se = 1; L.se_r = c2.se.cin;
+            L.se_w1 = n->wf + c2.se.w2; L.se_b1 = c2.d_se_b1; L.se_w2 = n->wf + c2.se.w3; L.se_b2 = n->wf + c2.se.bias3;
+        }
+        oi += c2.fused_se ? 3 : 2;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -498,7 +512,7 @@ static int launch_res_block(gaz_net *n, NetOp &c1, NetOp &c2, const int32_t *cou
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CKN(cudaLaunchKernelEx(&cfg, gaz_block::res_block_kernel, c1.tmA2, c1.tmB2, c2.tmB2, c2.tmOa, c2.tmOb, a));
+    CKN(cudaLaunchKernelEx(&cfg, gaz_block::res_trunk_kernel, a));
     return 0;
 }
 
@@ -567,14 +581,14 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             break;
         }
         case GAZ_OP_CONV_TC: {
-            if (op.in_block) break; // executed by the previous op's block kernel
+            if (op.in_block || op.in_trunk) break; // executed by an earlier op's block / trunk kernel
             if (n->profile && n->ev_used + 2 <= n->ev.size()) {
                 n->ev_op.push_back((int)oi);
                 CKN(cudaEventRecord(n->ev[n->ev_used++], s));
             }
             int rc;
             if (op.block_fused) {
-                rc = launch_res_block(n, op, n->ops[oi + 1], count, s);
+                rc = launch_res_trunk(n, oi, count, s);
             } else {
                 gaz_conv::BoardConvArgs a;
                 memset(&a, 0, sizeof a);
@@ -661,25 +675,33 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             break;
         }
         case GAZ_OP_DENSE: {
-            if (op.chain_skip) break;
+            if (op.chain_skip || op.chain_joined) break;
             if (op.chain_len > 0) {   // the dense stack behind a head as one launch (gaz_small::mlp_chain_kernel)
-                gaz_small::MlpArgs a;
-                memset(&a, 0, sizeof a);
-                a.count = count; a.max_count = n->max_batch; a.n_layers = op.chain_len; a.in = (const float *)buf(d.in_buf);
-                for (int li = 0; li < op.chain_len; li++) {
-                    const gaz_net_op &dl = n->ops[oi + (size_t)li].d;
-                    gaz_small::MlpLayer &L = a.L[li];
-                    L.In = dl.cin; L.Out = dl.cout; L.pre_affine = dl.flags & 1; L.pre_relu = (dl.flags >> 1) & 1; L.act = dl.act;
-                    L.w = wfp(n, dl.w); L.bias = wfp(n, dl.bias); L.pre_scale = wfp(n, dl.scale_a); L.pre_shift = wfp(n, dl.shift_a);
-                    if (li + 1 == op.chain_len) a.out = (dl.flags & 4) ? value : (float *)buf(dl.out_raw);
+                gaz_small::MlpArgs a[2];
+                memset(a, 0, sizeof a);
+                size_t sm = 0;
+                const int nch = op.chain_partner >= 0 ? 2 : 1;
+                for (int c = 0; c < nch; c++) {
+                    const size_t o0 = c == 0 ? oi : (size_t)op.chain_partner;
+                    const NetOp &co = n->ops[o0];
+                    a[c].count = count; a[c].max_count = n->max_batch; a[c].n_layers = co.chain_len; a[c].in = (const float *)buf(co.d.in_buf);
+                    for (int li = 0; li < co.chain_len; li++) {
+                        const gaz_net_op &dl = n->ops[o0 + (size_t)li].d;
+                        gaz_small::MlpLayer &L = a[c].L[li];
+                        L.In = dl.cin; L.Out = dl.cout; L.pre_affine = dl.flags & 1; L.pre_relu = (dl.flags >> 1) & 1; L.act = dl.act;
+                        L.w = wfp(n, dl.w); L.bias = wfp(n, dl.bias); L.pre_scale = wfp(n, dl.scale_a); L.pre_shift = wfp(n, dl.shift_a);
+                        if (li + 1 == co.chain_len) a[c].out = (dl.flags & 4) ? value : (float *)buf(dl.out_raw);
+                    }
+                    const size_t smc = gaz_small::mlp_smem(a[c]);
+                    sm = smc > sm ? smc : sm;
                 }
-                const size_t sm = gaz_small::mlp_smem(a);
                 static size_t attr_sm = 48 * 1024;
                 if (sm > attr_sm) {
                     CKN(cudaFuncSetAttribute(gaz_small::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                     attr_sm = sm;
                 }
-                gaz_small::mlp_chain_kernel<<<(n->max_batch + gaz_small::MLP_TL - 1) / gaz_small::MLP_TL, 256, sm, s>>>(a);
+                dim3 grid((unsigned)((n->max_batch + gaz_small::MLP_TL - 1) / gaz_small::MLP_TL), (unsigned)nch);
+                gaz_small::mlp_chain_kernel<<<grid, 256, sm, s>>>(a[0], a[1]);
                 break;
             }
             if (op.dense_tc) { // [leaf][In] bf16 x [Out][In] bf16 on the board kernel: rows = leaves, 128 outputs per launch
@@ -803,10 +825,11 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.skip = 0;
         op.block_fused = 0;
         op.in_block = 0;
+        op.trunk_len = 0; op.in_trunk = 0;
         op.dxm = 0;
         op.dual_partner = -1;
         op.dual_skip = 0;
-        op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0;
+        op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0; op.chain_partner = -1; op.chain_joined = 0;
         op.stem_tc = 0;
         op.stem_proj = 0;
         op.d_stem_w = nullptr;
@@ -934,6 +957,26 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
             c1.block_fused = 1;
             c2.in_block = 1;
         }
+        // consecutive fused blocks, each reading the previous one's bf16 operand and fp32 stream, share a launch
+        for (size_t oi = 0; oi < n->ops.size(); oi++) {
+            if (!n->ops[oi].block_fused || n->ops[oi].in_trunk) continue;
+            n->ops[oi].trunk_len = 1;
+#ifndef GAZ_NO_TRUNK      // A/B builds only
+            size_t cur = oi;
+            while (n->ops[oi].trunk_len < gaz_block::MAX_LAYERS) {
+                const NetOp &c2 = n->ops[cur + 1];
+                const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
+                const size_t nx = cur + (c2.fused_se ? 3 : 2);
+                if (nx + 1 >= n->ops.size() || !n->ops[nx].block_fused) break;
+                const NetOp &n2 = n->ops[nx + 1];
+                const gaz_net_op &o2 = n2.fused_se ? n2.se : n2.d;
+                if (n->ops[nx].d.in_buf != o.out_a || o.out_a < 0 || o2.res_buf != o.out_raw || o.out_raw < 0) break;
+                n->ops[nx].in_trunk = 1;
+                n->ops[oi].trunk_len++;
+                cur = nx;
+            }
+#endif
+        }
     }
     // Head convolutions that read the fp32 trunk output (Connect4, TicTacToe) run on headconv_wide_kernel; a second head
     // convolution with the same input, taps and input channels joins the launch as columns 8..15 (N = 16).
@@ -1014,6 +1057,28 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         if (len < 2) continue;
         o1.chain_len = len;
         for (int k = 1; k < len; k++) n->ops[i + (size_t)k].chain_skip = 1;
+    }
+    // a later chain whose input is complete before this chain's launch (its producer comes earlier in the op list, or is the
+    // second head of an earlier dual head convolution) joins the launch
+    for (size_t i = 0; i < n->ops.size(); i++) {
+        NetOp &o1 = n->ops[i];
+        if (o1.d.type != GAZ_OP_DENSE || o1.chain_len == 0 || o1.chain_joined || o1.chain_partner >= 0) continue;
+        for (size_t j = i + (size_t)o1.chain_len; j < n->ops.size(); j++) {
+            NetOp &o2 = n->ops[j];
+            if (o2.d.type != GAZ_OP_DENSE || o2.chain_len == 0 || o2.chain_joined || o2.chain_partner >= 0) continue;
+            bool ready = false, clash = false;
+            for (size_t k = 0; k < n->ops.size(); k++) {
+                const NetOp &pk = n->ops[k];
+                if (pk.d.out_raw != o2.d.in_buf) continue;
+                size_t exec = k;                       // the op whose launch writes this buffer
+                if (pk.dual_skip) { exec = n->ops.size(); for (size_t q = 0; q < k; q++) if (n->ops[q].dual_partner == (int)k) exec = q; }
+                if (exec < i) ready = true; else clash = true;
+            }
+            if (!ready || clash) continue;
+            o1.chain_partner = (int)j;
+            o2.chain_joined = 1;
+            break;
+        }
     }
     // stem on the tensor cores: 3x3 on 2 planes -> 256 filters, tile == board, bf16 outputs only
     for (auto &op : n->ops) {
@@ -1241,8 +1306,13 @@ int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
 int gaz_net_launches_per_forward(gaz_net *n) { // kernels actually launched: ops folded into another op's kernel do not count
     if (!n) return 0;
     int k = 0;
-    for (auto &op : n->ops) k += (op.skip || op.in_block || op.dual_skip || op.chain_skip) ? 0 : 1;
+    for (auto &op : n->ops) k += (op.skip || op.in_block || op.in_trunk || op.dual_skip || op.chain_skip || op.chain_joined) ? 0 : 1;
     return k;
+}
+
+int gaz_net_op_blocks(gaz_net *n, int op) { // residual blocks run by the launch of op `op` (0: the op launches no block kernel)
+    if (!n || op < 0 || (size_t)op >= n->ops.size()) return 0;
+    return n->ops[(size_t)op].in_trunk ? 0 : n->ops[(size_t)op].trunk_len;
 }
 
 /* profile = number of conv launches to keep events for (0 disables).  While enabled every tcgen05 conv

@@ -385,8 +385,11 @@ __device__ __forceinline__ void mlp_tile(float (&acc)[8][4], const float *s_w, c
     }
 }
 
-__global__ void __launch_bounds__(256) mlp_chain_kernel(MlpArgs p) {
+// Two chains with independent inputs (the policy and the value stack of Connect4 / TicTacToe) share one launch: blockIdx.y
+// selects the chain, so the second stack runs in the shadow of the first instead of as another latency-bound launch.
+__global__ void __launch_bounds__(256) mlp_chain_kernel(const MlpArgs p0, const MlpArgs p1) {
     extern __shared__ __align__(16) float s_act[];
+    const MlpArgs &p = blockIdx.y ? p1 : p0;
     int cnt = *p.count;
     if (cnt > p.max_count) cnt = p.max_count;
     const int leaf0 = blockIdx.x * MLP_TL;

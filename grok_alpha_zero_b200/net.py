@@ -287,6 +287,14 @@ class Net:
             raise EngineError(self.lib.gaz_last_error().decode())
         self._h = h
         self.n_launches = int(self.lib.gaz_net_launches_per_forward(h))   # kernels per forward (fused ops launch nothing)
+        # consecutive fused blocks share a launch (trunk launches, gaz_block.cuh): "block+se*5" = this op's launch runs 5 blocks,
+        # "intrunk" = the block runs inside an earlier op's launch
+        shapes = [list(x) for x in self._op_shapes]
+        for i, x in enumerate(shapes):
+            if x[4].startswith("block"):
+                nb = int(self.lib.gaz_net_op_blocks(h, i))
+                x[4] = "intrunk" if nb == 0 else (x[4] + "*%d" % nb)
+        self._op_shapes = [tuple(x) for x in shapes]
 
     def _ck(self, rc):
         if rc < 0:

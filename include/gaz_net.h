@@ -81,6 +81,9 @@ int gaz_net_profile(gaz_net *net, int max_launches);
 int gaz_net_profile_read(gaz_net *net, float *total_ms, int *n_launches, float *per_op_ms);
 int64_t gaz_net_bytes(gaz_net *net);
 int gaz_net_launches_per_forward(gaz_net *net);
+/* residual blocks run by the launch of op `op`: consecutive fused blocks share one launch of up to 6 layers (gaz_block.cuh);
+ * 0 = the op launches no block kernel (not a block, or absorbed into an earlier op's launch) */
+int gaz_net_op_blocks(gaz_net *net, int op);
 /* times `iters` forward passes of `n` resident leaves with CUDA events on the net's stream;
  * ms_out[0] = average milliseconds per pass */
 int gaz_net_time_forward(gaz_net *net, int n, int iters, float *ms_out);
