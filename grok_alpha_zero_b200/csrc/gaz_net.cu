@@ -400,6 +400,7 @@ struct NetOp {
     __nv_bfloat16 *d_act; // [rows_dense][In]: written by the producing head convolution
     __nv_bfloat16 *d_wt;  // [Out][In]
     int stem_tc;          // stem on the tensor cores (gaz_stem.cuh): d_stem_w / d_stem_par / tmOa (out_a) / tmOb (out_q) are set
+    int stem_tile;        // stem with 128 filters on tiles of whole boards (gaz_stem::stem_tile_kernel): d_stem_w / d_stem_par / tmOa set
     int stem_proj;        // ... and it also runs the next op, the 1x1 projection of the first block's shortcut (stem_proj_kernel)
     uint16_t *d_stem_w;   // [256][64] bf16 hi | lo split filters
     float *d_stem_par;    // stem_tc: [4][256] BN scale | shift + scale * bias | scale_a | shift_a; mma stem: [5][Cout] conv bias |
@@ -551,6 +552,28 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                 t.relu = d.act == GAZ_ACT_RELU; t.wpack = op.d_stem_w; t.par = op.d_stem_par;
                 t.has_q = d.out_b >= 0; t.has_a = d.out_a >= 0;
                 gaz_stem::stem_tc_kernel<<<2 * n->n_sm, 256, gaz_stem::Cfg::SMEM, s>>>(op.tmOb, op.tmOa, t);
+                break;
+            }
+            if (op.stem_tile) {
+                gaz_stem::StemTileArgs t;
+                t.count = count; t.max_count = n->max_batch; t.states = states; t.H = n->H; t.W = n->W; t.Wp = n->Wp; t.P_pad = n->P_pad;
+                t.act = d.act; t.wpack = op.d_stem_w; t.par = op.d_stem_par; t.out_raw = (float *)buf(d.out_raw); t.has_a = d.out_a >= 0;
+                const int tiles = (int)(n->rows_alloc / 256);
+                const int grid = tiles < 2 * n->n_sm ? tiles : 2 * n->n_sm;
+#define STEM_TILE(K_, C_)                                                                                                       \
+    do {                                                                                                                        \
+        const int sm = gaz_stem::TileCfg<K_, C_>::smem(n->H, n->W, n->P_pad);                                                    \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            CKN(cudaFuncSetAttribute(gaz_stem::stem_tile_kernel<K_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));      \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        gaz_stem::stem_tile_kernel<K_, C_><<<grid, 256, sm, s>>>(op.tmOa, t);                                                    \
+    } while (0)
+                if (d.ksize == 3 && d.cin == 4) STEM_TILE(3, 4);
+                else if (d.ksize == 3 && d.cin == 2) STEM_TILE(3, 2);
+                else STEM_TILE(5, 2);
+#undef STEM_TILE
                 break;
             }
             {   // every other stem shape: implicit GEMM on mma.sync (gaz_small.cuh)
@@ -831,6 +854,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.dual_skip = 0;
         op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0; op.chain_partner = -1; op.chain_joined = 0;
         op.stem_tc = 0;
+        op.stem_tile = 0;
         op.stem_proj = 0;
         op.d_stem_w = nullptr;
         op.d_stem_par = nullptr;
@@ -1140,9 +1164,49 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         pj.in_block = 1;
     }
 #endif
-    for (auto &op : n->ops) {   // every other stem: B fragments (hi | lo) + parameters of gaz_small::stem_mma_kernel
+    // stems with 128 filters on tiles of whole boards (Connect4, TicTacToe): tcgen05 as well (gaz_stem::stem_tile_kernel)
+    for (auto &op : n->ops) {
         const gaz_net_op &d = op.d;
         if (d.type != GAZ_OP_STEM || op.stem_tc) continue;
+        const bool shape = (d.ksize == 3 && (d.cin == 2 || d.cin == 4)) || (d.ksize == 5 && d.cin == 2);
+        if (!shape || d.cout != 128 || gaz_conv::TILE_ROWS % n->P_pad != 0 || d.out_b >= 0 || (d.out_raw < 0 && d.out_a < 0)) continue;
+        if (d.act != GAZ_ACT_NONE && d.act != GAZ_ACT_RELU && d.act != GAZ_ACT_GELU) continue;
+        const int KK = d.ksize * d.ksize * d.cin;
+        std::vector<uint16_t> wp((size_t)128 * 2 * 64, 0);
+        auto bf16_bits = [](float f) -> uint16_t { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16); };
+        auto bf16_val = [](uint16_t b) -> float { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; };
+        for (int o = 0; o < 128; o++)
+            for (int k = 0; k < KK; k++) {
+                const float w = desc->wf[d.w + (int64_t)k * 128 + o];   // [tap][plane][filter]
+                const uint16_t hi = bf16_bits(w);
+                wp[((size_t)o * 2) * 64 + k] = hi;
+                wp[((size_t)o * 2 + 1) * 64 + k] = bf16_bits(w - bf16_val(hi));
+            }
+        std::vector<float> par((size_t)5 * 128);
+        for (int c = 0; c < 128; c++) {
+            par[c] = desc->wf[d.bias + c];
+            par[128 + c] = d.scale_b >= 0 ? desc->wf[d.scale_b + c] : 1.0f;
+            par[256 + c] = d.shift_b >= 0 ? desc->wf[d.shift_b + c] : 0.0f;
+            par[384 + c] = d.scale_a >= 0 ? desc->wf[d.scale_a + c] : 1.0f;
+            par[512 + c] = d.shift_a >= 0 ? desc->wf[d.shift_a + c] : 0.0f;
+        }
+        if (alloc((void **)&op.d_stem_w, wp.size() * 2) != 0 || alloc((void **)&op.d_stem_par, par.size() * 4) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(op.d_stem_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+        CKN(cudaMemcpy(op.d_stem_par, par.data(), par.size() * 4, cudaMemcpyHostToDevice));
+        memset(&op.tmOa, 0, sizeof op.tmOa);
+        if (d.out_a >= 0) {
+            const NetBuf &ob = n->bufs[(size_t)d.out_a];
+            if (ob.kind != GAZ_BUF_ROWS_BF16 || ob.width != 128) continue;
+            if (make_map_ex(enc, &op.tmOa, ob.ptr, 128, (uint64_t)n->rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) != 0) { gaz_net_destroy(n); return -1; }
+        }
+        if (d.out_raw >= 0 && (n->bufs[(size_t)d.out_raw].kind != GAZ_BUF_ROWS_F32 || n->bufs[(size_t)d.out_raw].width != 128)) continue;
+#ifndef GAZ_NO_STEM_TILE   // A/B builds only
+        op.stem_tile = 1;
+#endif
+    }
+    for (auto &op : n->ops) {   // every other stem: B fragments (hi | lo) + parameters of gaz_small::stem_mma_kernel
+        const gaz_net_op &d = op.d;
+        if (d.type != GAZ_OP_STEM || op.stem_tc || op.stem_tile) continue;
         if (d.cout % 8 != 0 || d.cout > 256 || !((d.ksize == 3 && (d.cin == 2 || d.cin == 4)) || (d.ksize == 5 && d.cin == 2))) {
             gaz_net_destroy(n);
             return gaz_fail("stem shape unsupported (k %d cin %d cout %d)", d.ksize, d.cin, d.cout);

@@ -12,6 +12,7 @@
 // so two CTAs share an SM and one CTA's epilogue overlaps the other's im2col + MMA without any pipeline inside a CTA.
 #pragma once
 #include "gaz_conv.cuh"
+#include "gaz_small.cuh"
 
 namespace gaz_stem {
 using namespace gaz_tc;
@@ -472,6 +473,209 @@ stem_proj_kernel(const __grid_constant__ CUtensorMap tmOa, const StemProjArgs p)
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- stems with up to 128 filters on tiles of whole boards (Connect4: 3x3 on 4 planes -> 128, gelu; TicTacToe-shaped
+// stems with 128 filters) ------------------------------------------------------------------------------------------------
+// A tile is 256 padded rows = 256 / P_pad whole boards.  K = taps x planes <= 64: the im2col tile is ONE 64-wide K-block
+// (entries -1 / 0 / +1); the filters are two K-blocks, bf16 hi parts and bf16 lo parts at the same k positions, and both are
+// multiplied with the same A tile (fp32 filter accuracy, 2 x ceil(K / 16) MMAs per 128-row half).  One CTA = one tile at a
+// time, thread = row, two CTAs per SM so that one's epilogue (BN, activation, fp32 stream + bf16 operand stores) overlaps
+// the other's im2col + MMAs.  The mma.sync stem this replaces was instruction-bound at 147 us per 4096 Connect4 leaves
+// (fragment loads and scattered 8-byte stores; HBM floor 31 us).
+struct StemTileArgs {
+    const int32_t *count;
+    int max_count;
+    const int8_t *states;   // [leaf][H*W*CIN] HWC, values -1/0/+1
+    int H, W, Wp, P_pad, act;   // act: 0 none, 1 relu, 2 gelu (exact-erf form)
+    const uint16_t *wpack;  // [128 filters][2][64 k] bf16: hi parts | lo parts, k = tap*CIN + plane, zeros beyond taps*CIN
+    const float *par;       // [5][128]: conv bias | BN scale | BN shift | scale_a | shift_a
+    float *out_raw;         // activation as the blocked fp32 stream (optional)
+    int has_a;              // out_a = relu(scale_a * activation + shift_a) as bf16 rows through tmOa
+};
+
+template <int KSZ, int CIN> struct TileCfg {
+    static constexpr int K = KSZ * KSZ * CIN, KS = (K + 15) / 16, kh = KSZ / 2;
+    static_assert(K <= 64, "one K-block");
+    static constexpr int A_BYTES = 256 * 128, B_BYTES = 2 * 128 * 128, STAGE_BYTES = 8 * 2048, PAR_BYTES = 5 * 128 * 4;
+    static int in_bytes(int H, int W, int P_pad) { return (256 / P_pad) * (H + 2 * kh) * (W + 2 * kh) * CIN + 16; }
+    static int smem(int H, int W, int P_pad) { return 1024 + A_BYTES + B_BYTES + STAGE_BYTES + PAR_BYTES + in_bytes(H, W, P_pad) + 64; }
+};
+
+template <int KSZ, int CIN>
+__global__ void __launch_bounds__(256, 2)
+stem_tile_kernel(const __grid_constant__ CUtensorMap tmOa, const StemTileArgs p) {
+    using Cfg = TileCfg<KSZ, CIN>;
+    constexpr int KS = Cfg::KS, kh = Cfg::kh;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base, *sB = sA + Cfg::A_BYTES, *sStage = sB + Cfg::B_BYTES;
+    float *s_par = (float *)(sStage + Cfg::STAGE_BYTES);
+    uint64_t *bar = (uint64_t *)(s_par + 5 * 128);
+    uint32_t *tmem_slot = (uint32_t *)(bar + 1);
+    int8_t *s_in = (int8_t *)(bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cnt = *p.count;
+    if (cnt > p.max_count) cnt = p.max_count;
+    const int bpt = 256 / p.P_pad;                       // boards per tile
+    const int n_tiles = (cnt + bpt - 1) / bpt;
+    const int WB = p.W + 2 * kh, cells_b = (p.H + 2 * kh) * WB;     // zero-bordered board: cells of CIN bytes
+    const int ncell = p.H * p.W;
+
+    for (int i = threadIdx.x; i < 2 * 128 * 8; i += 256) {   // filters: K-block 0 = hi parts, K-block 1 = lo parts; SWIZZLE_128B layout
+        const int kb = i >> 10, r = (i >> 3) & 127, c = i & 7;
+        *reinterpret_cast<uint4 *>(sB + kb * 16384 + r * 128 + ((c ^ (r & 7)) << 4)) =
+            *reinterpret_cast<const uint4 *>(p.wpack + ((size_t)r * 2 + kb) * 64 + c * 8);
+    }
+    for (int i = threadIdx.x; i < 256 * 8; i += 256) *reinterpret_cast<uint4 *>(sA + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 5 * 128; i += 256) s_par[i] = p.par[i];
+    for (int i = threadIdx.x; i < bpt * cells_b * CIN; i += 256) s_in[i] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        if (p.has_a) tma_prefetch_desc(&tmOa);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pos = threadIdx.x;                          // row of the tile owned by this thread (im2col + epilogue)
+    const int gb = pos / p.P_pad, bp = pos - gb * p.P_pad;
+    const int yy = bp / p.Wp - 1, xx = bp % p.Wp;
+    const bool live_pos = yy >= 0 && yy < p.H && xx < p.W;
+    const int q = warp & 3, sub = warp >> 2;              // TMEM lane quarter / 128-row half: rows sub*128 + q*32 + lane = pos
+    const uint32_t a_row = smem_u32(sA) + (uint32_t)(pos * 128), sw7 = (uint32_t)(pos & 7), sw3 = (uint32_t)((lane >> 1) & 3);
+    const uint32_t par_addr = smem_u32(s_par), stage_addr = smem_u32(sStage + warp * 2048);
+    const uint32_t a_lo = umma_desc_lo(smem_u32(sA)), b_lo = umma_desc_lo(smem_u32(sB));
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+    const int8_t *my_in = s_in + ((size_t)gb * cells_b + (size_t)(live_pos ? yy * WB + xx : 0)) * CIN;
+    uint32_t ph = 0;
+
+    for (int t = (int)blockIdx.x; t < n_tiles; t += (int)gridDim.x, ph ^= 1) {
+        // ---- the tile's boards -> zero-bordered int8 tiles (boards past the batch as zeros)
+        for (int i = threadIdx.x; i < bpt * ncell; i += 256) {
+            const int g = i / ncell, e = i - g * ncell, y = e / p.W, x = e - y * p.W;
+            const int b = t * bpt + g;
+            int8_t *dst = s_in + ((size_t)g * cells_b + (size_t)((y + kh) * WB + x + kh)) * CIN;
+            if (CIN == 4) *reinterpret_cast<uint32_t *>(dst) = b < cnt ? *reinterpret_cast<const uint32_t *>(p.states + ((size_t)b * ncell + e) * 4) : 0u;
+            else *reinterpret_cast<uint16_t *>(dst) = b < cnt ? *reinterpret_cast<const uint16_t *>(p.states + ((size_t)b * ncell + e) * 2) : (uint16_t)0;
+        }
+        __syncthreads();
+        const bool live = live_pos && t * bpt + gb < cnt;
+        // ---- im2col row: k = tap * CIN + plane, -1 / 0 / +1 -> bf16 bits 0xBF80 / 0 / 0x3F80
+        {
+            uint32_t w[8 * KS];                            // KS k-steps = 2 * KS chunks of 4 words
+#pragma unroll
+            for (int j = 0; j < 8 * KS; j++) w[j] = 0u;
+            if (live) {
+#pragma unroll
+                for (int tp = 0; tp < KSZ * KSZ; tp++) {
+                    const int8_t *src = my_in + ((tp / KSZ) * WB + (tp % KSZ)) * CIN;
+                    uint32_t cell;
+                    if (CIN == 4) cell = *reinterpret_cast<const uint32_t *>(src);
+                    else cell = *reinterpret_cast<const uint16_t *>(src);
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ci++) {
+                        const int v = (int)(int8_t)((cell >> (8 * ci)) & 0xffu);
+                        const uint32_t h = v == 0 ? 0u : (v > 0 ? 0x3F80u : 0xBF80u);
+                        const int k = tp * CIN + ci;
+                        w[k >> 1] |= h << (16 * (k & 1));
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2 * KS; c++)
+                sts128(a_row + ((((uint32_t)c) ^ sw7) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // ---- D[256 rows][128 filters] = A[256][K] x (B_hi + B_lo)[128][K]^T : 2 halves x 2 filter parts x KS k-steps
+        if (warp == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+                for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+                    for (int k = 0; k < KS; k++)
+                        umma_bf16_elect<false>(tmem_base + (uint32_t)(s * 128), a_lo + (uint32_t)(s * 1024 + k * 2),
+                                               b_lo + (uint32_t)(kb * 1024 + k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_elect<false>(bar);
+        }
+        mbar_wait(bar, ph);
+        tc_fence_after();
+        // ---- epilogue: this thread's row, 4 pieces of 32 filters
+        {
+            const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 128);
+            const int row0 = t * 256 + sub * 128 + q * 32;
+            const uint32_t mask = live ? 0xffffffffu : 0u;
+            float *outp = p.out_raw ? p.out_raw + ((((size_t)(row0 >> 5)) * 4) << 10) + (size_t)(lane * 8) : nullptr;
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32(t_acc, ra);
+            auto piece = [&](const uint32_t (&r)[32], int c32) {
+                if (p.has_a) {
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const uint32_t o = (uint32_t)((c32 * 32 + ch * 8) * 4);
+                    const float4 b0 = lds128f(par_addr + o), b1 = lds128f(par_addr + o + 16);
+                    const float4 s0 = lds128f(par_addr + 512 + o), s1 = lds128f(par_addr + 512 + o + 16);
+                    const float4 h0 = lds128f(par_addr + 1024 + o), h1 = lds128f(par_addr + 1024 + o + 16);
+                    const int j = ch * 8;
+                    float v[8];
+                    v[0] = fmaf(s0.x, __uint_as_float(r[j]) + b0.x, h0.x);     v[1] = fmaf(s0.y, __uint_as_float(r[j + 1]) + b0.y, h0.y);
+                    v[2] = fmaf(s0.z, __uint_as_float(r[j + 2]) + b0.z, h0.z); v[3] = fmaf(s0.w, __uint_as_float(r[j + 3]) + b0.w, h0.w);
+                    v[4] = fmaf(s1.x, __uint_as_float(r[j + 4]) + b1.x, h1.x); v[5] = fmaf(s1.y, __uint_as_float(r[j + 5]) + b1.y, h1.y);
+                    v[6] = fmaf(s1.z, __uint_as_float(r[j + 6]) + b1.z, h1.z); v[7] = fmaf(s1.w, __uint_as_float(r[j + 7]) + b1.w, h1.w);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (p.act == 1) v[u] = fmaxf(v[u], 0.0f);
+                        else if (p.act == 2) v[u] = gaz_small::gelu_erf(v[u]);
+                        v[u] = live ? v[u] : 0.0f;
+                    }
+                    if (outp) gaz_conv::stg256(outp + (size_t)c32 * 1024 + ch * 256, v);
+                    if (p.has_a) {
+                        const float4 a0 = lds128f(par_addr + 1536 + o), a1 = lds128f(par_addr + 1536 + o + 16);
+                        const float4 t0 = lds128f(par_addr + 2048 + o), t1 = lds128f(par_addr + 2048 + o + 16);
+                        sts128(stage_addr + (uint32_t)(lane * 64) + (((uint32_t)ch ^ sw3) << 4),
+                               pack_relu_bf16x2(fmaf(a0.x, v[0], t0.x), fmaf(a0.y, v[1], t0.y)) & mask,
+                               pack_relu_bf16x2(fmaf(a0.z, v[2], t0.z), fmaf(a0.w, v[3], t0.w)) & mask,
+                               pack_relu_bf16x2(fmaf(a1.x, v[4], t1.x), fmaf(a1.y, v[5], t1.y)) & mask,
+                               pack_relu_bf16x2(fmaf(a1.z, v[6], t1.z), fmaf(a1.w, v[7], t1.w)) & mask);
+                    }
+                }
+                if (p.has_a) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d_addr(&tmOa, stage_addr, c32 * 32, row0);
+                        tma_store_commit();
+                    }
+                }
+            };
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                tmem_ld_wait_dep(ra);
+                tmem_ld_32x32(t_acc + (uint32_t)(c * 64 + 32), rb);
+                piece(ra, 2 * c);
+                tmem_ld_wait_dep(rb);
+                if (c == 0) tmem_ld_32x32(t_acc + 64u, ra);
+                piece(rb, 2 * c + 1);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // TMEM, the A tile and the input tiles are free for the next tile
+    }
+    if (lane == 0) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 } // namespace gaz_stem

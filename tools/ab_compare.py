@@ -24,6 +24,18 @@ for path in (_lib.lib_path(), os.path.join("tests", "_emul", var)):
     net = Net(spec, W, max_batch=B, lib=lib)
     outs.append(net.forward(states, want_logits=True))
     net.close()
+if os.environ.get("AB_ORACLE"):      # both builds against the fp32 restatement (first 256 states)
+    sys.path.insert(0, "oracle")
+    from net_oracle import NetOracle
+    m = min(B, 256)
+    ref = NetOracle(spec, W).forward(states[:m])
+    for tag, o in zip(("this build", var), outs):
+        print("%-28s vs fp32 oracle: logits err %.4g value err %.4g" % (tag, np.abs(o[2][:m] - ref["logits"].numpy()).max(),
+                                                                          np.abs(o[1][:m] - ref["value"].numpy().reshape(-1)).max()))
 for name, a, b in zip(("policy", "value", "logits"), outs[0], outs[1]):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     print(name, "max|diff| %.3e" % np.abs(a - b).max(), "bit-identical" if np.array_equal(a, b) else "differs", "absmax %.3f" % np.abs(a).max())
+
+d = np.abs(np.asarray(outs[0][2], np.float64) - np.asarray(outs[1][2], np.float64)).max(axis=1)
+bad = np.nonzero(d > 0)[0]
+print("boards whose logits differ: %d of %d; first %s; per-board max diff of those: %s" % (len(bad), B, bad[:24].tolist(), np.round(d[bad[:12]], 5).tolist()))
