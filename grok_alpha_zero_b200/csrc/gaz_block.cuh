@@ -69,6 +69,8 @@ struct TrunkLayer {           // one residual block
     __nv_bfloat16 *out_a, *out_b;
     int nkc1;                 // 64-channel K-blocks of conv1's input (2: C_in = 128, 4: C_in = 256)
     int dep;                  // the input operand / residual of this layer are outputs of the previous layer of this launch
+    int plain_a;              // out_a = bf16(scale_a * v + shift_a) WITHOUT the ReLU (the bf16 copy of the trunk output that a
+                              // tensor-core head convolution reads, Connect4/Build_Model.py:27,48)
     int se, se_r;
     const float *se_w1, *se_b1, *se_w2, *se_b2; // se_b1 has the conv2 bias folded in (b1 + W1^T bias2)
 };
@@ -111,6 +113,11 @@ __device__ __forceinline__ void colsum32(const uint32_t (&r)[32], uint32_t mask,
     dst[col] = v[0];
 }
 
+__device__ __forceinline__ uint32_t pack_plain_bf16x2(float lo, float hi) { // {hi, lo} -> bf16x2
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) { // {hi, lo} -> max(., 0) -> bf16x2
     uint32_t d;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
@@ -157,7 +164,8 @@ __device__ __forceinline__ void e2_chunk(const uint32_t (&acc)[16], const float 
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int c = 8 * j + 2 * i;
-                w[i] = pack_relu_bf16x2(fmaf(sc[c], v[c], sh[c]), fmaf(sc[c + 1], v[c + 1], sh[c + 1])) & mask;
+                const float f0 = fmaf(sc[c], v[c], sh[c]), f1 = fmaf(sc[c + 1], v[c + 1], sh[c + 1]);
+                w[i] = ((o == 0 && p.plain_a) ? pack_plain_bf16x2(f0, f1) : pack_relu_bf16x2(f0, f1)) & mask;
             }
             const int piece = ODD * 2 + j; // 32-row x 32-channel SWIZZLE_64B tile: row = lane (64 B)
             sts128(st + (uint32_t)(lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4)), w[0], w[1], w[2], w[3]);

@@ -65,7 +65,10 @@ struct BoardConvArgs {
     int P_pad, Wp, H;         // rows per board (a divisor of 256 or (H+1)*Wp), row pitch W+1, board height: rows of a board beyond
                               // (H+1)*Wp are dead like the padding row / column
     int taps, kpt;            // filter taps (1 or 9; 3 in dx-merged mode), 64-channel K-blocks per tap
-    int dxm;                  // dx-merged 3x3 convolution (BN = 96 instance only, see the kernel): taps = 3 row shifts dy * Wp
+    int dxm;                  // dx-merged 3x3 convolution (BN = 96 / 48 instances only, see the kernel): taps = 3 row shifts dy * Wp
+    // BN = 48: two small head convolutions on one input (8 + 8 output channels per dx), flat fp32 outputs [leaf][H*W][c]
+    float *head_out[2];
+    int head_c[2], W;
     int base_offset_mode;     // debug bits: 4 = skip the output stores (timing experiment)
     // per-channel parameters travel in the kernel-argument (constant) bank: bias | scale_a | shift_a | scale_b |
     // shift_b, 128 floats each.  The epilogue reads them with uniform LDC, which keeps them off the shared-memory
@@ -93,13 +96,13 @@ constexpr int SLAB_BOX_ROWS = SLAB_ROWS / 2;
 
 template <int BN, bool PAIR> struct BoardCfg {
     static constexpr int NSLAB = PAIR ? 4 : 3;
-    static constexpr int NB = BN <= 32 ? 16 : (BN <= 64 ? 8 : (BN == 96 ? 6 : 4)); // weight-tile ring: small tiles are consumed in
+    static constexpr int NB = BN <= 48 ? 16 : (BN <= 64 ? 8 : (BN == 96 ? 6 : 4)); // weight-tile ring: small tiles are consumed in
                                                                    // ~100 cycles each, the ring has to span the L2 latency
-    static constexpr int NSTAGE = (PAIR && BN != 96) ? 2 : 1; // 32-row x 32-channel bf16 staging tiles per epilogue warp (TMA store source)
+    static constexpr int NSTAGE = (PAIR && BN != 96 && BN != 48) ? 2 : 1; // 32-row x 32-channel bf16 staging tiles per epilogue warp (TMA store source)
     static constexpr int STAGE_BYTES = 8 * NSTAGE * 2048;
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN; // weight rows (output channels) this CTA stages per tile
     static constexpr int B_BYTES = B_ROWS * 128;
-    static constexpr int TMEM_COLS = BN == 96 ? 512 : (4 * BN < 32 ? 32 : 4 * BN);   // a power of two
+    static constexpr int TMEM_COLS = BN == 96 ? 512 : (BN == 48 ? 256 : (4 * BN < 32 ? 32 : 4 * BN));   // a power of two
     static constexpr int SE_FLOATS = 8 * BN + BN + BN + BN; // partial sums [8 warps][BN], mean, hidden, gate
     static constexpr int SMEM = NSLAB * SLAB_BYTES + NB * B_BYTES + STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ +
                                 SE_FLOATS * 4;
@@ -223,7 +226,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int tap = 0; tap < p.taps; tap++) {
                         mbar_wait(&b_full[rb.idx], rb.phase);
                         tc_fence_after();
-                        const int shift = BN == 96 ? (tap - 1) * p.Wp : (p.taps == 9 ? dy * p.Wp + dx : 0);
+                        const int shift = (BN == 96 || BN == 48) ? (tap - 1) * p.Wp : (p.taps == 9 ? dy * p.Wp + dx : 0);
                         const uint32_t b_lo = umma_desc_lo(smem_u32(sB + rb.idx * Cfg::B_BYTES));
                         const uint32_t a_lo = slab_lo + (uint32_t)(shift * 8); // 128 B per row = 8 descriptor units
                         const uint32_t accf = (uint32_t)((kc | tap) != 0); // the first MMA into each accumulator overwrites
@@ -268,6 +271,46 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int pos = (int)(row % p.P_pad);
             const int yy = pos / p.Wp, xx = pos - yy * p.Wp;
             const bool live = row < valid_rows && (p.dense || (yy != 0 && yy <= p.H && xx != p.Wp - 1));
+            if constexpr (BN == 48) {
+                // ---- dx-merged pair of small head convolutions (Connect4: policy and value head, 3x3 C128 -> C8 each, on the
+                // bf16 copy of the trunk output): as BN = 96 below with 16 columns per dx (head 0: columns 0..7, head 1: 8..15);
+                // the sums go out as flat fp32 [leaf][cell][c] rows, the layout the dense stack behind a head reads.
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * 2 + sub) * BN);
+                uint32_t em[16], e0[16], ep[16];
+                tmem_ld_32x16(t_acc, em);
+                tmem_ld_32x16(t_acc + 16u, e0);
+                tmem_ld_32x16(t_acc + 32u, ep);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
+                float v[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    float a = __shfl_up_sync(0xffffffffu, __uint_as_float(em[c]), 1);
+                    float b = __shfl_down_sync(0xffffffffu, __uint_as_float(ep[c]), 1);
+                    if (lane == 0) a = 0.0f;
+                    if (lane == 31) b = 0.0f;
+                    v[c] = ((a + __uint_as_float(e0[c])) + b) + p.par[c];
+                }
+                if (live) {
+                    const int board = (int)(row / p.P_pad), cell = (yy - 1) * p.W + xx;
+#pragma unroll
+                    for (int hd = 0; hd < 2; hd++) {
+                        if (!p.head_out[hd]) continue;
+                        float *o = p.head_out[hd] + ((size_t)board * (size_t)(p.H * p.W) + (size_t)cell) * (size_t)p.head_c[hd];
+                        if (p.head_c[hd] == 8) stg256(o, *reinterpret_cast<const float(*)[8]>(&v[8 * hd]));
+                        else
+#pragma unroll
+                            for (int c = 0; c < 8; c++)
+                                if (c < p.head_c[hd]) o[c] = v[8 * hd + c];
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             if constexpr (BN == 96) {
                 // ---- dx-merged 3x3 convolution with 32 outputs (the C128 -> C32 head convolutions).  The weight tile of row
                 // shift dy holds the filters of its three taps side by side (N = 96: column dx' * 32 + c, dx' = dx + 1), so

@@ -386,6 +386,9 @@ struct NetOp {
     int dual_partner;     // HEADCONV: index of a later head convolution on the same fp32 input that this op's launch computes
     int dual_skip;        // as well (gaz_small::headconv_wide_kernel, N = 16); dual_skip marks that later op
     int head_wide;        // HEADCONV on the fp32 stream through headconv_wide_kernel: d_frag / d_hbias are set
+    int head_tc;          // HEADCONV (3x3, <= 8 + 8 outputs) on tcgen05 (conv_board_kernel<48>, dx-merged) reading the bf16 copy of the
+                          // trunk output that the last residual block writes: tmA2 / tmB2 / d_wt / par[0..15] (biases) are set
+    __nv_bfloat16 *d_xbf; // conv2 op of the last block: plain bf16 copy of its fp32 output (tmOa stores into it, no ReLU)
     uint4 *d_frag;        // mma.sync B fragments (stem_mma_kernel / headconv_wide_kernel)
     float *d_hbias;       // [16] biases of the (up to) two heads of a wide head convolution
     int head_G;           // boards per CTA iteration of the wide head convolution / the mma stem
@@ -496,6 +499,7 @@ static int launch_res_trunk(gaz_net *n, size_t first, const int32_t *count, cuda
         const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
         L.res = (const float *)buf(o.res_buf); L.out_raw = (float *)buf(o.out_raw);
         L.out_a = (__nv_bfloat16 *)buf(o.out_a); L.out_b = (__nv_bfloat16 *)buf(o.out_b);
+        if (c2.d_xbf) { L.out_a = c2.d_xbf; L.plain_a = 1; }   // bf16(x) for a tensor-core head convolution (scale 1, shift 0, no ReLU)
         if (c2.fused_se) {
             L.se = 1; L.se_r = c2.se.cin;
             L.se_w1 = n->wf + c2.se.w2; L.se_b1 = c2.d_se_b1; L.se_w2 = n->wf + c2.se.w3; L.se_b2 = n->wf + c2.se.bias3;
@@ -650,6 +654,20 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
         }
         case GAZ_OP_HEADCONV: {
             if (op.dual_skip) break;
+            if (op.head_tc) {     // bf16 copy of the trunk output -> both heads' 3x3 convolutions as one dx-merged tcgen05 pass
+                gaz_conv::BoardConvArgs a;
+                memset(&a, 0, sizeof a);
+                a.count = count; a.max_count = n->max_batch; a.P_pad = n->P_pad; a.Wp = n->Wp; a.H = n->H; a.W = n->W;
+                a.taps = 3; a.kpt = d.cin / 64; a.dxm = 1; a.base_offset_mode = 0;
+                memcpy(a.par, op.par, sizeof a.par);
+                a.head_out[0] = (float *)buf(d.out_raw); a.head_c[0] = d.cout;
+                if (op.dual_partner >= 0) {
+                    const NetOp &o2 = n->ops[(size_t)op.dual_partner];
+                    a.head_out[1] = (float *)buf(o2.d.out_raw); a.head_c[1] = o2.d.cout;
+                }
+                if (launch_conv_board<48>(n, op, a, s) != 0) return -1;
+                break;
+            }
             if (op.head_wide) {   // fp32 trunk output -> both heads' small convolutions in one mma.sync pass (gaz_small.cuh)
                 gaz_small::HeadWideArgs a;
                 a.count = count; a.max_count = n->max_batch; a.H = n->H; a.W = n->W; a.Cin = d.cin; a.K = d.ksize;
@@ -852,6 +870,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.dxm = 0;
         op.dual_partner = -1;
         op.dual_skip = 0;
+        op.head_tc = 0; op.d_xbf = nullptr;
         op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0; op.chain_partner = -1; op.chain_joined = 0;
         op.stem_tc = 0;
         op.stem_tile = 0;
@@ -1060,6 +1079,52 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         }
         // stems the tcgen05 kernel does not cover: fragments + parameters of stem_mma_kernel (set below once stem_tc is known)
     }
+    // A (dual) 3x3 head convolution on the fp32 output of a fused residual block moves to the tensor cores: the block's last
+    // epilogue also writes bf16(x) (its free out_a slot, no ReLU) and conv_board_kernel<48> convolves that copy with the bf16
+    // filters of both heads, dx-merged (N = 3 x 16).  Same operand precision as every trunk convolution.
+#ifndef GAZ_NO_HEAD_TC     // A/B builds only
+    for (size_t i = 0; i < n->ops.size(); i++) {
+        NetOp &o1 = n->ops[i];
+        const gaz_net_op &d1 = o1.d;
+        if (d1.type != GAZ_OP_HEADCONV || !o1.head_wide || d1.ksize != 3 || d1.cin != 128 || d1.cout > 8) continue;
+        if (gaz_conv::TILE_ROWS % n->P_pad != 0 || 32 % n->Wp != 0 || (n->n_sm & ~1) < 2) continue;
+        const gaz_net_op *d2p = o1.dual_partner >= 0 ? &n->ops[(size_t)o1.dual_partner].d : nullptr;
+        NetOp *src = nullptr;      // the conv2 op whose (fused SE) epilogue writes the head input
+        for (auto &c2 : n->ops) {
+            if (c2.d.type != GAZ_OP_CONV_TC || !c2.in_block) continue;
+            const gaz_net_op &o = c2.fused_se ? c2.se : c2.d;
+            if (o.out_raw == d1.in_buf && o.out_a < 0 && !c2.d_xbf) src = &c2;
+        }
+        if (!src) continue;
+        if (alloc((void **)&src->d_xbf, (size_t)n->rows_alloc * 128 * 2) != 0) { gaz_net_destroy(n); return -1; }
+        const size_t ld = (size_t)3 * d1.cin;
+        std::vector<uint16_t> wt((size_t)48 * ld, 0);
+        auto bf16_bits = [](float f) -> uint16_t { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16); };
+        for (int hd = 0; hd < 2; hd++) {
+            const gaz_net_op *dd = hd == 0 ? &d1 : d2p;
+            if (!dd) continue;
+            for (int dy = 0; dy < 3; dy++)
+                for (int dx = 0; dx < 3; dx++)
+                    for (int k = 0; k < dd->cin; k++)
+                        for (int c = 0; c < dd->cout; c++)      // [tap][Cin][Cout] fp32 filters of the head
+                            wt[(size_t)(dx * 16 + hd * 8 + c) * ld + (size_t)dy * dd->cin + k] =
+                                bf16_bits(desc->wf[dd->w + ((int64_t)(dy * 3 + dx) * dd->cin + k) * dd->cout + c]);
+        }
+        if (alloc((void **)&o1.d_wt, wt.size() * 2) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(o1.d_wt, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        if (make_map(enc, &o1.tmA2, src->d_xbf, 128, (uint64_t)n->rows_alloc, gaz_conv::SLAB_BOX_ROWS) != 0 ||
+            make_map(enc, &o1.tmB2, o1.d_wt, (uint64_t)ld, 48, 24) != 0 ||
+            make_map_ex(enc, &src->tmOa, src->d_xbf, 128, (uint64_t)n->rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B) != 0) { gaz_net_destroy(n); return -1; }
+        memset(&o1.tmOa, 0, sizeof o1.tmOa);
+        memset(&o1.tmOb, 0, sizeof o1.tmOb);
+        for (int c = 0; c < 640; c++) o1.par[c] = 0.0f;
+        for (int c = 0; c < 16; c++) {
+            const gaz_net_op *dd = c < 8 ? &d1 : d2p;
+            o1.par[c] = (dd && (c & 7) < dd->cout) ? desc->wf[dd->bias + (c & 7)] : 0.0f;
+        }
+        o1.head_tc = 1;
+    }
+#endif
     // dense chains: consecutive DENSE ops, each reading the previous one's output, that fit a CTA's shared memory
     for (size_t i = 0; i < n->ops.size(); i++) {
         NetOp &o1 = n->ops[i];
@@ -1245,7 +1310,7 @@ void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); if (op.d_frag) cudaFree(op.d_frag); if (op.d_hbias) cudaFree(op.d_hbias); }
+    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); if (op.d_frag) cudaFree(op.d_frag); if (op.d_hbias) cudaFree(op.d_hbias); if (op.d_xbf) cudaFree(op.d_xbf); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
