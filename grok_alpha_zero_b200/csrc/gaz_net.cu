@@ -733,16 +733,21 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                         L.w = wfp(n, dl.w); L.bias = wfp(n, dl.bias); L.pre_scale = wfp(n, dl.scale_a); L.pre_shift = wfp(n, dl.shift_a);
                         if (li + 1 == co.chain_len) a[c].out = (dl.flags & 4) ? value : (float *)buf(dl.out_raw);
                     }
-                    const size_t smc = gaz_small::mlp_smem(a[c]);
+                    const size_t smc = gaz_small::mlp_smem(a[c], 32);
                     sm = smc > sm ? smc : sm;
                 }
+                // 32 leaves per CTA once that still leaves about three CTAs per SM, else 16
+                const bool wide = (long long)((n->max_batch + 31) / 32) * nch >= 3LL * n->n_sm / 2;
                 static size_t attr_sm = 48 * 1024;
                 if (sm > attr_sm) {
-                    CKN(cudaFuncSetAttribute(gaz_small::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    CKN(cudaFuncSetAttribute(gaz_small::mlp_chain_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    CKN(cudaFuncSetAttribute(gaz_small::mlp_chain_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                     attr_sm = sm;
                 }
-                dim3 grid((unsigned)((n->max_batch + gaz_small::MLP_TL - 1) / gaz_small::MLP_TL), (unsigned)nch);
-                gaz_small::mlp_chain_kernel<<<grid, 256, sm, s>>>(a[0], a[1]);
+                const int tl = wide ? 32 : 16;
+                dim3 grid((unsigned)((n->max_batch + tl - 1) / tl), (unsigned)nch);
+                if (wide) gaz_small::mlp_chain_kernel<32><<<grid, 256, sm, s>>>(a[0], a[1]);
+                else gaz_small::mlp_chain_kernel<16><<<grid, 256, sm, s>>>(a[0], a[1]);
                 break;
             }
             if (op.dense_tc) { // [leaf][In] bf16 x [Out][In] bf16 on the board kernel: rows = leaves, 128 outputs per launch

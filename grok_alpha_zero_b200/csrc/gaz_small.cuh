@@ -340,9 +340,10 @@ struct MlpArgs {
     const float *in;      // [leaf][L[0].In]
     float *out;           // [leaf][L[n-1].Out]
 };
-constexpr int MLP_TL = 16;       // leaves per CTA
+// leaves per CTA: template parameter TL of the kernel (16: small batches, more CTAs; 32: twice the register tile per shared-memory
+// load once there are enough CTAs to fill the SMs - 117 -> 81 us for the two Connect4 stacks at 4096 leaves)
 constexpr int MLP_KT = 16;       // weight rows per shared-memory tile
-static inline size_t mlp_smem(const MlpArgs &a) {
+static inline size_t mlp_smem(const MlpArgs &a, int MLP_TL) {
     int mx = 0, mo = 0;
     for (int i = 0; i < a.n_layers; i++) {
         mx = a.L[i].In > mx ? a.L[i].In : mx; mx = a.L[i].Out > mx ? a.L[i].Out : mx;
@@ -355,7 +356,7 @@ static inline size_t mlp_smem(const MlpArgs &a) {
 // weights of a layer stream through a [MLP_KT][Out] shared-memory tile (the tile is a contiguous piece of the [In][Out]
 // matrix: coalesced loads, the next tile is fetched into registers while the current one is multiplied); a thread owns 4
 // consecutive outputs x `lpg` leaves.  Terms are accumulated in k order.  Requires Out <= 128 (8 prefetch registers).
-template <int LPG>
+template <int LPG, int MLP_TL>
 __device__ __forceinline__ void mlp_tile(float (&acc)[8][4], const float *s_w, const float *ap0, int kn, int Out, int o0, bool vec) {
     for (int kk = 0; kk < kn; kk++) {
         float w4[4];
@@ -387,7 +388,7 @@ __device__ __forceinline__ void mlp_tile(float (&acc)[8][4], const float *s_w, c
 
 // Two chains with independent inputs (the policy and the value stack of Connect4 / TicTacToe) share one launch: blockIdx.y
 // selects the chain, so the second stack runs in the shadow of the first instead of as another latency-bound launch.
-__global__ void __launch_bounds__(256) mlp_chain_kernel(const MlpArgs p0, const MlpArgs p1) {
+template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(const MlpArgs p0, const MlpArgs p1) {
     extern __shared__ __align__(16) float s_act[];
     const MlpArgs &p = blockIdx.y ? p1 : p0;
     int cnt = *p.count;
@@ -461,10 +462,10 @@ __global__ void __launch_bounds__(256) mlp_chain_kernel(const MlpArgs p0, const 
                 const int kn = min(MLP_KT, l.In - k0);
                 const float *ap0 = bufA + k0 * MLP_TL + lf0;
                 switch (lpg) {     // static trip counts: the generic predicated form spent 6x the useful instructions
-                case 1: mlp_tile<1>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
-                case 2: mlp_tile<2>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
-                case 4: mlp_tile<4>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
-                default: mlp_tile<8>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                case 1: mlp_tile<1, MLP_TL>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                case 2: mlp_tile<2, MLP_TL>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                case 4: mlp_tile<4, MLP_TL>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
+                default: mlp_tile<8, MLP_TL>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
                 }
             }
             __syncthreads();
