@@ -1440,7 +1440,10 @@ int64_t gaz_net_bytes(gaz_net *n) { return n ? n->bytes : 0; }
 int gaz_net_launches_per_forward(gaz_net *n) { // kernels actually launched: ops folded into another op's kernel do not count
     if (!n) return 0;
     int k = 0;
-    for (auto &op : n->ops) k += (op.skip || op.in_block || op.in_trunk || op.dual_skip || op.chain_skip || op.chain_joined) ? 0 : 1;
+    for (auto &op : n->ops) {
+        if (op.skip || op.in_block || op.in_trunk || op.dual_skip || op.chain_skip || op.chain_joined) continue;
+        k += op.dense_tc ? (op.d.cout + 127) / 128 : 1;   // a tensor-core dense layer launches one kernel per 128 outputs
+    }
     return k;
 }
 

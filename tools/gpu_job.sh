@@ -1,14 +1,3 @@
-# scratch driver of one gpurun call (rewritten per call; see tools/README.md)
 set -x
 mkdir -p gpurun_out
-t0=$(date +%s)
-timeout 1500 python bench.py > gpurun_out/r02_bench_default_v8.json 2> gpurun_out/bench_d8.err; echo bench rc=$?
-echo "default bench wall seconds: $(( $(date +%s) - t0 ))"
-tail -n 5 gpurun_out/bench_d8.err
-python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/r02_bench_default_v8.json') if l.startswith('{')][-1])
-print('default', d['value'], d['ms_per_step'], d['e2e']['value'], d['positions_per_s'], d['roofline']['frac'], d['roofline']['traffic'], d['clocks'], d['gpu_launches'])
-for k,v in d.get('configs',{}).items(): print(k, json.dumps(v)[:420])
-print('cpu', d.get('cpu_baseline'))
-"
+timeout 900 python -m pytest tests/test_net_fusion_gpu.py -m gpu -q -x 2>&1 | tail -15
