@@ -190,10 +190,16 @@ __device__ __forceinline__ void e1_piece(const uint32_t (&r)[32], uint32_t par_a
     const int sw = srow & 7, j0 = (c32 & 1) * 4;
     const uint32_t mask = live ? 0xffffffffu : 0u;   // padding rows / columns of the board stay zero
     const uint32_t sc_addr = par_addr + (uint32_t)(c32 * 128), sh_addr = sc_addr + 512;
+    // the parameters of chunk ch + 1 are loaded before chunk ch is converted (the volatile loads / stores keep their program
+    // order, so without this the 30-cycle shared-memory latency is exposed once per chunk)
+    float4 s0 = lds128f(sc_addr), s1 = lds128f(sc_addr + 16), h0 = lds128f(sh_addr), h1 = lds128f(sh_addr + 16);
 #pragma unroll
     for (int ch = 0; ch < 4; ch++) {
-        const float4 s0 = lds128f(sc_addr + ch * 32), s1 = lds128f(sc_addr + ch * 32 + 16);
-        const float4 h0 = lds128f(sh_addr + ch * 32), h1 = lds128f(sh_addr + ch * 32 + 16);
+        float4 ns0 = s0, ns1 = s1, nh0 = h0, nh1 = h1;
+        if (ch < 3) {
+            ns0 = lds128f(sc_addr + (ch + 1) * 32); ns1 = lds128f(sc_addr + (ch + 1) * 32 + 16);
+            nh0 = lds128f(sh_addr + (ch + 1) * 32); nh1 = lds128f(sh_addr + (ch + 1) * 32 + 16);
+        }
         const int j = ch * 8;
         uint32_t w[4];
         w[0] = pack_relu_bf16x2(fmaf(s0.x, __uint_as_float(r[j]), h0.x), fmaf(s0.y, __uint_as_float(r[j + 1]), h0.y)) & mask;
@@ -201,6 +207,7 @@ __device__ __forceinline__ void e1_piece(const uint32_t (&r)[32], uint32_t par_a
         w[2] = pack_relu_bf16x2(fmaf(s1.x, __uint_as_float(r[j + 4]), h1.x), fmaf(s1.y, __uint_as_float(r[j + 5]), h1.y)) & mask;
         w[3] = pack_relu_bf16x2(fmaf(s1.z, __uint_as_float(r[j + 6]), h1.z), fmaf(s1.w, __uint_as_float(r[j + 7]), h1.w)) & mask;
         sts128(rowp + (uint32_t)(((j0 + ch) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+        s0 = ns0; s1 = ns1; h0 = nh0; h1 = nh1;
     }
 }
 

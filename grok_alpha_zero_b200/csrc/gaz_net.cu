@@ -422,6 +422,9 @@ struct gaz_net {
     int64_t bytes;
     int n_sm;
     cudaStream_t stream;
+    cudaStream_t stream2;          // side stream of the second head (fork / join inside net_forward)
+    cudaEvent_t ev_fork, ev_join;
+    int head1_begin, head2_begin;  // op indices: first op of the first / second head; head2_begin = 0: the heads are not separable
     // own I/O buffers for the host path
     int8_t *d_states;
     int32_t *d_count;
@@ -523,9 +526,18 @@ static int launch_res_trunk(gaz_net *n, size_t first, const int32_t *count, cuda
 
 static const float *wfp(gaz_net *n, int64_t off) { return off < 0 ? nullptr : n->wf + off; }
 
-static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, float *policy, float *value, cudaStream_t s) {
+static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, float *policy, float *value, cudaStream_t s_main) {
     n->ev_used = n->profile ? n->ev_used : 0;
+    // Two heads that share nothing but the trunk output run as two branches: the second head's ops go to the network's side
+    // stream between a fork (event recorded where the first head starts) and a join at the end.  Inside a stream capture the
+    // side stream joins the capture through the event wait, so the round graph gets two parallel branches.
+    const bool two = n->head2_begin > 0;
     for (size_t oi = 0; oi < n->ops.size(); oi++) {
+        if (two && (int)oi == n->head1_begin) {
+            CKN(cudaEventRecord(n->ev_fork, s_main));
+            CKN(cudaStreamWaitEvent(n->stream2, n->ev_fork, 0));
+        }
+        cudaStream_t s = (two && (int)oi >= n->head2_begin) ? n->stream2 : s_main;
         NetOp &op = n->ops[oi];
         const gaz_net_op &d = op.d;
         auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
@@ -787,6 +799,10 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             return gaz_fail("unknown op type %d", d.type);
         }
     }
+    if (two) {
+        CKN(cudaEventRecord(n->ev_join, n->stream2));
+        CKN(cudaStreamWaitEvent(s_main, n->ev_join, 0));
+    }
     CKN(cudaGetLastError());
     return 0;
 }
@@ -834,6 +850,10 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     CKN(cudaGetDeviceProperties(&prop, desc->device));
     n->n_sm = prop.multiProcessorCount;
     CKN(cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking));
+    CKN(cudaStreamCreateWithFlags(&n->stream2, cudaStreamNonBlocking));
+    CKN(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+    CKN(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
+    n->head1_begin = 0; n->head2_begin = 0;
     auto alloc = [&](void **p, size_t bytes) -> int {
         CKN(cudaMalloc(p, bytes ? bytes : 16));
         CKN(cudaMemset(*p, 0, bytes ? bytes : 16));
@@ -1306,6 +1326,29 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         while ((G + g0) * n->P_pad <= 512) G += g0;    // ~32 m-tiles per iteration: 4 per warp, enough groups to balance the SMs
         op.head_G = G;
     }
+#ifndef GAZ_NO_HEAD_STREAMS   // A/B builds only
+    {   // separable heads: [head1_begin, head2_begin) ends with POLICY_OUT, [head2_begin, end) reads nothing the first head writes
+        int last_block = -1, pout = -1;
+        for (size_t i = 0; i < n->ops.size(); i++) {
+            const NetOp &o = n->ops[i];
+            if (o.block_fused || o.in_block || o.in_trunk || o.skip) last_block = (int)i;
+            if (o.d.type == GAZ_OP_POLICY_OUT) pout = (int)i;
+        }
+        const int h1 = last_block + 1, h2 = pout + 1;
+        bool ok = last_block >= 0 && pout > h1 && h2 < (int)n->ops.size();
+        for (int i = h2; ok && i < (int)n->ops.size(); i++) {
+            const gaz_net_op &d = n->ops[(size_t)i].d;
+            for (int j = h1; j < h2; j++) {
+                const NetOp &w = n->ops[(size_t)j];
+                const int outs[3] = {w.d.out_raw, w.d.out_a, w.d.out_b};
+                for (int k = 0; k < 3; k++)
+                    if (outs[k] >= 0 && (outs[k] == d.in_buf || outs[k] == d.res_buf || outs[k] == d.out_raw || outs[k] == d.out_a || outs[k] == d.out_b)) ok = false;
+                if (w.dual_partner >= i || w.chain_partner >= i) ok = false;   // a launch of the first head that also runs ops of the second
+            }
+        }
+        if (ok) { n->head1_begin = h1; n->head2_begin = h2; }
+    }
+#endif
     CKN(cudaDeviceSynchronize());
     *out = n;
     return 0;
@@ -1314,11 +1357,14 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
 void gaz_net_destroy(gaz_net *n) {
     if (!n) return;
     cudaStreamSynchronize(n->stream);
+    cudaStreamSynchronize(n->stream2);
     for (auto &b : n->bufs) cudaFree(b.ptr);
     for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); if (op.d_frag) cudaFree(op.d_frag); if (op.d_hbias) cudaFree(op.d_hbias); if (op.d_xbf) cudaFree(op.d_xbf); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
+    cudaStreamDestroy(n->stream2);
+    cudaEventDestroy(n->ev_fork); cudaEventDestroy(n->ev_join);
     delete n;
 }
 
