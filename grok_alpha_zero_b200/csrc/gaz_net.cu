@@ -394,6 +394,7 @@ struct NetOp {
     int head_G;           // boards per CTA iteration of the wide head convolution / the mma stem
     int chain_len;        // DENSE: this op starts a chain of chain_len dense layers run by ONE mlp_chain_kernel launch
     int chain_skip;       // DENSE executed by an earlier op's chain launch
+    uint4 *d_frag0;       // DENSE chain start: layer 0's weights as mma.sync B fragments (hi | lo), or null (CUDA-core layer 0)
     int chain_partner;    // DENSE chain start: index of a later chain whose input is already complete; it runs in this launch (grid.y = 2)
     int chain_joined;     // DENSE chain start executed by an earlier chain's launch
     float par[5 * 128];   // host copy of bias | scale_a | shift_a | scale_b | shift_b for the kernel-argument bank
@@ -424,6 +425,7 @@ struct gaz_net {
     cudaStream_t stream;
     cudaStream_t stream2;          // side stream of the second head (fork / join inside net_forward)
     cudaEvent_t ev_fork, ev_join;
+    gaz_block::TrunkArgs *trunk_args;   // host staging of a trunk launch's arguments
     int head1_begin, head2_begin;  // op indices: first op of the first / second head; head2_begin = 0: the heads are not separable
     // own I/O buffers for the host path
     int8_t *d_states;
@@ -486,7 +488,7 @@ static int launch_res_trunk(gaz_net *n, size_t first, const int32_t *count, cuda
         attr_set = true;
     }
     auto buf = [&](int id) -> void * { return id < 0 ? nullptr : n->bufs[(size_t)id].ptr; };
-    static gaz_block::TrunkArgs a;   // 29 KB: kept off the stack; the launch copies it
+    gaz_block::TrunkArgs &a = *n->trunk_args;   // 29 KB: kept off the stack (one per network); the launch copies it
     memset(&a, 0, sizeof a);
     a.count = count; a.max_count = n->max_batch; a.Wp = n->Wp; a.H = n->H; a.P_pad = n->P_pad; a.n_cells = n->H * n->W; a.dbg = n->dbg;
     a.n_layers = n->ops[first].trunk_len;
@@ -738,6 +740,7 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
                     const size_t o0 = c == 0 ? oi : (size_t)op.chain_partner;
                     const NetOp &co = n->ops[o0];
                     a[c].count = count; a[c].max_count = n->max_batch; a[c].n_layers = co.chain_len; a[c].in = (const float *)buf(co.d.in_buf);
+                    a[c].frag0 = co.d_frag0;
                     for (int li = 0; li < co.chain_len; li++) {
                         const gaz_net_op &dl = n->ops[o0 + (size_t)li].d;
                         gaz_small::MlpLayer &L = a[c].L[li];
@@ -854,6 +857,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
     CKN(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
     CKN(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
     n->head1_begin = 0; n->head2_begin = 0;
+    n->trunk_args = new gaz_block::TrunkArgs();
     auto alloc = [&](void **p, size_t bytes) -> int {
         CKN(cudaMalloc(p, bytes ? bytes : 16));
         CKN(cudaMemset(*p, 0, bytes ? bytes : 16));
@@ -896,7 +900,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         op.dual_partner = -1;
         op.dual_skip = 0;
         op.head_tc = 0; op.d_xbf = nullptr;
-        op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0; op.chain_partner = -1; op.chain_joined = 0;
+        op.head_wide = 0; op.d_frag = nullptr; op.d_hbias = nullptr; op.head_G = 1; op.chain_len = 0; op.chain_skip = 0; op.chain_partner = -1; op.chain_joined = 0; op.d_frag0 = nullptr;
         op.stem_tc = 0;
         op.stem_tile = 0;
         op.stem_proj = 0;
@@ -1172,6 +1176,23 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         o1.chain_len = len;
         for (int k = 1; k < len; k++) n->ops[i + (size_t)k].chain_skip = 1;
     }
+    // layer 0 of a chain on mma.sync when its shape allows (In a multiple of 16, 64 or 128 outputs, enough work to matter)
+#ifndef GAZ_NO_MLP_MMA     // A/B builds only
+    for (auto &o1 : n->ops) {
+        const gaz_net_op &d = o1.d;
+        if (d.type != GAZ_OP_DENSE || o1.chain_len == 0 || d.cin % 16 != 0 || d.cin < 128 || (d.cout != 64 && d.cout != 128)) continue;
+        const int KS = d.cin / 16, NT = d.cout / 8;
+        std::vector<gaz_small::Frag> fr((size_t)KS * NT * 32);
+        for (int ks = 0; ks < KS; ks++)
+            for (int nt = 0; nt < NT; nt++)
+                for (int lane = 0; lane < 32; lane++) {
+                    auto wfun = [&](int k, int nn) -> float { return desc->wf[d.w + (int64_t)k * d.cout + nn]; };   // [In][Out]
+                    fr[((size_t)ks * NT + nt) * 32 + lane] = gaz_small::host_frag(lane, wfun, ks * 16, nt * 8);
+                }
+        if (alloc((void **)&o1.d_frag0, fr.size() * sizeof(gaz_small::Frag)) != 0) { gaz_net_destroy(n); return -1; }
+        CKN(cudaMemcpy(o1.d_frag0, fr.data(), fr.size() * sizeof(gaz_small::Frag), cudaMemcpyHostToDevice));
+    }
+#endif
     // a later chain whose input is complete before this chain's launch (its producer comes earlier in the op list, or is the
     // second head of an earlier dual head convolution) joins the launch
     for (size_t i = 0; i < n->ops.size(); i++) {
@@ -1359,12 +1380,13 @@ void gaz_net_destroy(gaz_net *n) {
     cudaStreamSynchronize(n->stream);
     cudaStreamSynchronize(n->stream2);
     for (auto &b : n->bufs) cudaFree(b.ptr);
-    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); if (op.d_frag) cudaFree(op.d_frag); if (op.d_hbias) cudaFree(op.d_hbias); if (op.d_xbf) cudaFree(op.d_xbf); }
+    for (auto &op : n->ops) { if (op.d_se_b1) cudaFree(op.d_se_b1); if (op.d_act) cudaFree(op.d_act); if (op.d_wt) cudaFree(op.d_wt); if (op.d_stem_w) cudaFree(op.d_stem_w); if (op.d_stem_par) cudaFree(op.d_stem_par); if (op.d_frag) cudaFree(op.d_frag); if (op.d_hbias) cudaFree(op.d_hbias); if (op.d_xbf) cudaFree(op.d_xbf); if (op.d_frag0) cudaFree(op.d_frag0); }
     cudaFree(n->wf); cudaFree(n->wh); cudaFree(n->d_states); cudaFree(n->d_count); cudaFree(n->d_chunk_count); cudaFree(n->d_policy); cudaFree(n->d_value);
     for (auto e : n->ev) cudaEventDestroy(e);
     cudaStreamDestroy(n->stream);
     cudaStreamDestroy(n->stream2);
     cudaEventDestroy(n->ev_fork); cudaEventDestroy(n->ev_join);
+    delete n->trunk_args;
     delete n;
 }
 

@@ -336,6 +336,8 @@ struct MlpLayer {
 struct MlpArgs {
     const int32_t *count;
     int max_count, n_layers;
+    const uint4 *frag0;   // optional: layer 0 on mma.sync - its weights as B fragments [k-step][n-tile][lane] {hi0, hi1, lo0, lo1}
+                          // (host_frag); needs In % 16 == 0 and Out = 64 or 128
     MlpLayer L[3];
     const float *in;      // [leaf][L[0].In]
     float *out;           // [leaf][L[n-1].Out]
@@ -424,7 +426,72 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
         }
     }
     __syncthreads();
-    for (int li = 0; li < p.n_layers; li++) {
+    int li0 = 0;
+    if (p.frag0) {
+        // ---- layer 0 on the warp-level tensor cores (Connect4: 336 -> 128 is 86 % of a stack's FLOPs and the CUDA-core form is
+        // bound by its shared-memory loads).  Activations and weights are split into bf16 hi + lo parts, three MMAs per fragment
+        // (hi*hi + lo*hi + hi*lo) as in headconv_wide_kernel: fp32-level accuracy.  Warp w: m-tile w % MT (16 leaves), n-tiles
+        // (w / MT) * NPW .. + NPW; A fragments are gathered from the [feature][leaf] activations and split on the fly.
+        const MlpLayer &l = p.L[0];
+        constexpr int MT = MLP_TL / 16;
+        const int NT = l.Out >> 3, NPW = NT / (8 / MT);      // n-tiles per warp: 4 (TL 32) or 2 (TL 16) at Out = 128
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+        const int mt = warp % MT, nt0 = (warp / MT) * NPW;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
+        const float *ab = bufA + mt * 16 + g;
+        const int KS = l.In >> 4;
+        auto split = [](float x0, float x1, uint32_t &hi, uint32_t &lo) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+            hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        };
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks++) {
+            const float *a = ab + (size_t)(ks * 16 + 2 * t) * MLP_TL;
+            uint32_t h[4], lo[4];
+            split(a[0], a[MLP_TL], h[0], lo[0]);                          // row g,     k = 2t, 2t+1
+            split(a[8], a[MLP_TL + 8], h[1], lo[1]);                      // row g + 8
+            split(a[8 * MLP_TL], a[9 * MLP_TL], h[2], lo[2]);             // row g,     k = 2t+8, 2t+9
+            split(a[8 * MLP_TL + 8], a[9 * MLP_TL + 8], h[3], lo[3]);     // row g + 8
+            const uint4 *fr = p.frag0 + ((size_t)ks * NT + nt0) * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j < NPW) {
+                    const uint4 f = __ldg(fr + j * 32);
+                    mma_bf16_16816(acc[j], h[0], h[1], h[2], h[3], f.x, f.y);       // hi * hi
+                    mma_bf16_16816(acc[j], lo[0], lo[1], lo[2], lo[3], f.x, f.y);   // lo * hi
+                    mma_bf16_16816(acc[j], h[0], h[1], h[2], h[3], f.z, f.w);       // hi * lo
+                }
+            }
+        }
+        const bool last = p.n_layers == 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j >= NPW) continue;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {     // C fragment: e 0,1 = row g, columns 2t, 2t+1; e 2,3 = row g + 8
+                const int lf = mt * 16 + g + (e >> 1) * 8, o = (nt0 + j) * 8 + 2 * t + (e & 1);
+                float v = acc[j][e] + l.bias[o];
+                if (l.act == 1) v = fmaxf(v, 0.0f);
+                else if (l.act == 3) v = tanhf(v);
+                if (last) {
+                    if (leaf0 + lf < cnt) p.out[(size_t)(leaf0 + lf) * l.Out + o] = v;
+                } else {
+                    const MlpLayer &nx = p.L[1];
+                    if (nx.pre_affine) v = fmaf(nx.pre_scale[o], v, nx.pre_shift[o]);
+                    if (nx.pre_relu) v = fmaxf(v, 0.0f);
+                    bufB[o * MLP_TL + lf] = v;
+                }
+            }
+        }
+        __syncthreads();
+        float *tswap = bufA; bufA = bufB; bufB = tswap;
+        li0 = 1;
+    }
+    for (int li = li0; li < p.n_layers; li++) {
         const MlpLayer &l = p.L[li];
         const bool last = li + 1 == p.n_layers;
         const int n_o4 = (l.Out + 3) >> 2;                  // threads per leaf group
