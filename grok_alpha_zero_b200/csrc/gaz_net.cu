@@ -1176,17 +1176,22 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         o1.chain_len = len;
         for (int k = 1; k < len; k++) n->ops[i + (size_t)k].chain_skip = 1;
     }
-    // layer 0 of a chain on mma.sync when its shape allows (In a multiple of 16, 64 or 128 outputs, enough work to matter)
+    // layer 0 of a chain on mma.sync when its shape allows (In a multiple of 16, enough work to matter); a lone fp32 dense layer of
+    // that kind (Gomoku's policy_2, 512 -> 225) becomes a one-layer chain
 #ifndef GAZ_NO_MLP_MMA     // A/B builds only
     for (auto &o1 : n->ops) {
         const gaz_net_op &d = o1.d;
-        if (d.type != GAZ_OP_DENSE || o1.chain_len == 0 || d.cin % 16 != 0 || d.cin < 128 || (d.cout != 64 && d.cout != 128)) continue;
-        const int KS = d.cin / 16, NT = d.cout / 8;
+        if (d.type != GAZ_OP_DENSE || o1.dense_tc || o1.chain_skip || d.cin % 16 != 0 || d.cin < 128 || d.cin > 512) continue;
+        if (o1.chain_len == 0) {
+            if (d.cout < 64 || d.cout > 256) continue;
+            o1.chain_len = 1;
+        } else if (d.cout < 64 || d.cout > 128) continue;
+        const int KS = d.cin / 16, NT = (((d.cout + 7) / 8) + 7) & ~7;   // n-tiles padded to a multiple of 8 (zero fragments beyond Out)
         std::vector<gaz_small::Frag> fr((size_t)KS * NT * 32);
         for (int ks = 0; ks < KS; ks++)
             for (int nt = 0; nt < NT; nt++)
                 for (int lane = 0; lane < 32; lane++) {
-                    auto wfun = [&](int k, int nn) -> float { return desc->wf[d.w + (int64_t)k * d.cout + nn]; };   // [In][Out]
+                    auto wfun = [&](int k, int nn) -> float { return nn < d.cout ? desc->wf[d.w + (int64_t)k * d.cout + nn] : 0.0f; };   // [In][Out]
                     fr[((size_t)ks * NT + nt) * 32 + lane] = gaz_small::host_frag(lane, wfun, ks * 16, nt * 8);
                 }
         if (alloc((void **)&o1.d_frag0, fr.size() * sizeof(gaz_small::Frag)) != 0) { gaz_net_destroy(n); return -1; }

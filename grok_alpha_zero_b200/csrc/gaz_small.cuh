@@ -337,7 +337,7 @@ struct MlpArgs {
     const int32_t *count;
     int max_count, n_layers;
     const uint4 *frag0;   // optional: layer 0 on mma.sync - its weights as B fragments [k-step][n-tile][lane] {hi0, hi1, lo0, lo1}
-                          // (host_frag); needs In % 16 == 0 and Out = 64 or 128
+                          // (host_frag); needs In % 16 == 0; n-tiles padded to a multiple of 8 with zero fragments
     MlpLayer L[3];
     const float *in;      // [leaf][L[0].In]
     float *out;           // [leaf][L[n-1].Out]
@@ -345,13 +345,16 @@ struct MlpArgs {
 // leaves per CTA: template parameter TL of the kernel (16: small batches, more CTAs; 32: twice the register tile per shared-memory
 // load once there are enough CTAs to fill the SMs - 117 -> 81 us for the two Connect4 stacks at 4096 leaves)
 constexpr int MLP_KT = 16;       // weight rows per shared-memory tile
+// activations [feature][leaf] with a leading stride of TL + 4 floats: the A-fragment gathers of the mma.sync layer (address
+// (k0 + 2t) * stride + g) then touch 32 different banks, the transposing stores of the load phase 8 instead of 1
 static inline size_t mlp_smem(const MlpArgs &a, int MLP_TL) {
+    if (a.frag0 && a.n_layers == 1) return (size_t)a.L[0].In * (MLP_TL + 4) * 4 + 16;   // only the input lives in shared memory
     int mx = 0, mo = 0;
     for (int i = 0; i < a.n_layers; i++) {
         mx = a.L[i].In > mx ? a.L[i].In : mx; mx = a.L[i].Out > mx ? a.L[i].Out : mx;
         mo = a.L[i].Out > mo ? a.L[i].Out : mo;
     }
-    return (size_t)(2 * mx * MLP_TL + MLP_KT * mo) * 4 + 16;
+    return (size_t)(2 * mx * (MLP_TL + 4) + MLP_KT * mo) * 4 + 16;
 }
 
 // One CTA = MLP_TL leaves through every layer of the chain.  Activations live in shared memory as [feature][leaf]; the
@@ -369,7 +372,7 @@ __device__ __forceinline__ void mlp_tile(float (&acc)[8][4], const float *s_w, c
 #pragma unroll
             for (int b = 0; b < 4; b++) w4[b] = o0 + b < Out ? s_w[kk * Out + o0 + b] : 0.0f;
         }
-        const float *ap = ap0 + kk * MLP_TL;
+        const float *ap = ap0 + kk * (MLP_TL + 4);
         float av[LPG];
         if (LPG >= 4) {
 #pragma unroll
@@ -399,7 +402,8 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
     if (leaf0 >= cnt) return;
     int mx = 0;
     for (int i = 0; i < p.n_layers; i++) { mx = max(mx, max(p.L[i].In, p.L[i].Out)); }
-    float *bufA = s_act, *bufB = s_act + (size_t)mx * MLP_TL, *s_w = s_act + (size_t)2 * mx * MLP_TL;
+    constexpr int LS = MLP_TL + 4;   // leading stride of the [feature][leaf] activations
+    float *bufA = s_act, *bufB = s_act + (size_t)mx * LS, *s_w = s_act + (size_t)2 * mx * LS;
     {   // load + pre-activation of the first layer's input: [leaf][In] -> [In][leaf]; four independent loads in flight per thread
         const MlpLayer &l = p.L[0];
         const int tot = l.In * MLP_TL;
@@ -421,7 +425,7 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
                 float x = l.pre_affine ? fmaf(sc[u], a[u], sh[u]) : a[u];
                 if (l.pre_relu) x = fmaxf(x, 0.0f);
                 if (leaf0 + lf[u] >= cnt) x = 0.0f;
-                bufA[kk[u] * MLP_TL + lf[u]] = x;
+                bufA[kk[u] * LS + lf[u]] = x;
             }
         }
     }
@@ -434,12 +438,13 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
         // (w / MT) * NPW .. + NPW; A fragments are gathered from the [feature][leaf] activations and split on the fly.
         const MlpLayer &l = p.L[0];
         constexpr int MT = MLP_TL / 16;
-        const int NT = l.Out >> 3, NPW = NT / (8 / MT);      // n-tiles per warp: 4 (TL 32) or 2 (TL 16) at Out = 128
+        const int NT = (((l.Out + 7) >> 3) + 7) & ~7, NPW = NT / (8 / MT);   // n-tiles (padded to a multiple of 8; the fragments beyond Out
+                                                                             // are zero) and n-tiles per warp: <= 8 for Out <= 256 (TL 32)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
         const int mt = warp % MT, nt0 = (warp / MT) * NPW;
-        float acc[4][4];
+        float acc[8][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
+        for (int j = 0; j < 8; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
         const float *ab = bufA + mt * 16 + g;
         const int KS = l.In >> 4;
         auto split = [](float x0, float x1, uint32_t &hi, uint32_t &lo) {
@@ -450,15 +455,15 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
         };
 #pragma unroll 1
         for (int ks = 0; ks < KS; ks++) {
-            const float *a = ab + (size_t)(ks * 16 + 2 * t) * MLP_TL;
+            const float *a = ab + (size_t)(ks * 16 + 2 * t) * LS;
             uint32_t h[4], lo[4];
-            split(a[0], a[MLP_TL], h[0], lo[0]);                          // row g,     k = 2t, 2t+1
-            split(a[8], a[MLP_TL + 8], h[1], lo[1]);                      // row g + 8
-            split(a[8 * MLP_TL], a[9 * MLP_TL], h[2], lo[2]);             // row g,     k = 2t+8, 2t+9
-            split(a[8 * MLP_TL + 8], a[9 * MLP_TL + 8], h[3], lo[3]);     // row g + 8
+            split(a[0], a[LS], h[0], lo[0]);                      // row g,     k = 2t, 2t+1
+            split(a[8], a[LS + 8], h[1], lo[1]);                  // row g + 8
+            split(a[8 * LS], a[9 * LS], h[2], lo[2]);             // row g,     k = 2t+8, 2t+9
+            split(a[8 * LS + 8], a[9 * LS + 8], h[3], lo[3]);     // row g + 8
             const uint4 *fr = p.frag0 + ((size_t)ks * NT + nt0) * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 8; j++) {
                 if (j < NPW) {
                     const uint4 f = __ldg(fr + j * 32);
                     mma_bf16_16816(acc[j], h[0], h[1], h[2], h[3], f.x, f.y);       // hi * hi
@@ -469,11 +474,12 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
         }
         const bool last = p.n_layers == 1;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 8; j++) {
             if (j >= NPW) continue;
 #pragma unroll
             for (int e = 0; e < 4; e++) {     // C fragment: e 0,1 = row g, columns 2t, 2t+1; e 2,3 = row g + 8
                 const int lf = mt * 16 + g + (e >> 1) * 8, o = (nt0 + j) * 8 + 2 * t + (e & 1);
+                if (o >= l.Out) continue;
                 float v = acc[j][e] + l.bias[o];
                 if (l.act == 1) v = fmaxf(v, 0.0f);
                 else if (l.act == 3) v = tanhf(v);
@@ -483,7 +489,7 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
                     const MlpLayer &nx = p.L[1];
                     if (nx.pre_affine) v = fmaf(nx.pre_scale[o], v, nx.pre_shift[o]);
                     if (nx.pre_relu) v = fmaxf(v, 0.0f);
-                    bufB[o * MLP_TL + lf] = v;
+                    bufB[o * LS + lf] = v;
                 }
             }
         }
@@ -527,7 +533,7 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
             if (k0 + MLP_KT < l.In) fetch(k0 + MLP_KT);
             if (active) {
                 const int kn = min(MLP_KT, l.In - k0);
-                const float *ap0 = bufA + k0 * MLP_TL + lf0;
+                const float *ap0 = bufA + k0 * LS + lf0;
                 switch (lpg) {     // static trip counts: the generic predicated form spent 6x the useful instructions
                 case 1: mlp_tile<1, MLP_TL>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
                 case 2: mlp_tile<2, MLP_TL>(acc, s_w, ap0, kn, l.Out, o0, vec); break;
@@ -555,7 +561,7 @@ template <int MLP_TL> __global__ void __launch_bounds__(256) mlp_chain_kernel(co
                         const MlpLayer &nx = p.L[li + 1];
                         if (nx.pre_affine) v = fmaf(nx.pre_scale[o], v, nx.pre_shift[o]);
                         if (nx.pre_relu) v = fmaxf(v, 0.0f);
-                        bufB[o * MLP_TL + lf] = v;
+                        bufB[o * LS + lf] = v;
                     }
                 }
             }
