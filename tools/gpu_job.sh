@@ -1,9 +1,15 @@
+# scratch driver of one gpurun call (rewritten per call; see tools/README.md)
 set -x
 mkdir -p gpurun_out
-AB_ORACLE=1 timeout 300 python tools/ab_compare.py libgaz_ab_nomlpmma.so gomoku 100 2>&1 | tail -6
-AB_ORACLE=1 timeout 300 python tools/ab_compare.py libgaz_ab_nomlpmma.so connect4 600 2>&1 | tail -6
-timeout 900 python -m pytest tests/test_net_gpu.py tests/test_net_golden_gpu.py tests/test_net_fusion_gpu.py -m gpu -q -x 2>&1 | tail -4
-timeout 300 python tools/quick_net_bench.py gomoku 16384 2>&1 | tail -4
-timeout 300 python tools/quick_net_bench.py connect4 4096 2>&1 | tail -4
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"mlp_chain|dense_kernel" -s 16 -c 4 --csv --log-file gpurun_out/mlp.csv python tools/quick_net_bench.py gomoku 16384 > gpurun_out/ncu_q.log 2>&1; echo ncu rc=$?
-grep '^"' gpurun_out/mlp.csv | awk -F'","' '{print substr($5,1,60), $(NF)}' | tail -5
+t0=$(date +%s)
+timeout 1500 python bench.py > gpurun_out/r02_bench_default_final.json 2> gpurun_out/bench_df.err; echo bench rc=$?
+echo "default bench wall seconds: $(( $(date +%s) - t0 ))"
+tail -n 3 gpurun_out/bench_df.err
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/r02_bench_default_final.json') if l.startswith('{')][-1])
+print('default', d['value'], d['ms_per_step'], d['e2e']['value'], d['positions_per_s'], d['roofline']['frac'], d['roofline']['traffic'], d['net_tflops'], d['clocks'], d['gpu_launches'])
+for k,v in d.get('configs',{}).items(): print(k, json.dumps({kk:vv for kk,vv in v.items() if kk not in ('workload','whole_move','clocks')})[:600])
+print('cpu', d.get('cpu_baseline'))
+"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-400
