@@ -1,15 +1,12 @@
 # scratch driver of one gpurun call (rewritten per call; see tools/README.md)
 set -x
 mkdir -p gpurun_out
-t0=$(date +%s)
-timeout 1500 python bench.py > gpurun_out/r02_bench_default_final.json 2> gpurun_out/bench_df.err; echo bench rc=$?
-echo "default bench wall seconds: $(( $(date +%s) - t0 ))"
-tail -n 3 gpurun_out/bench_df.err
+nvidia-smi -L | head -8
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --games 32768 --pool-fraction 0.45 --no-cpu-baseline --no-extras > gpurun_out/r02_scale_gomoku_4gpu_131072.json 2> gpurun_out/scale4.err; echo rc=$?
+tail -5 gpurun_out/scale4.err
 python -c "
 import json
-d=json.loads([l for l in open('gpurun_out/r02_bench_default_final.json') if l.startswith('{')][-1])
-print('default', d['value'], d['ms_per_step'], d['e2e']['value'], d['positions_per_s'], d['roofline']['frac'], d['roofline']['traffic'], d['net_tflops'], d['clocks'], d['gpu_launches'])
-for k,v in d.get('configs',{}).items(): print(k, json.dumps({kk:vv for kk,vv in v.items() if kk not in ('workload','whole_move','clocks')})[:600])
-print('cpu', d.get('cpu_baseline'))
+d=json.loads([l for l in open('gpurun_out/r02_scale_gomoku_4gpu_131072.json') if l.startswith('{')][-1])
+print('N=4', d['value'], d['ms_per_step'], d['e2e']['value'], d['n_gpus'], d['config'].get('games_per_gpu'), d['clocks'], d['hbm_bytes'], d['slot_pool'])
+print(json.dumps(d.get('e2e_generation'))[:900])
 "
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-400
