@@ -1,12 +1,16 @@
-# scratch driver of one gpurun call (rewritten per call; see tools/README.md)
+# driver of one gpurun call: the round-end verification on a fresh B200 box
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_job.sh'
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L | head -8
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --games 32768 --pool-fraction 0.45 --no-cpu-baseline --no-extras > gpurun_out/r02_scale_gomoku_4gpu_131072.json 2> gpurun_out/scale4.err; echo rc=$?
-tail -5 gpurun_out/scale4.err
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest rc=$?
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo smoke rc=$?; tail -3 gpurun_out/smoke.log
+timeout 1500 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo bench rc=$?
+tail -n 3 gpurun_out/bench_default.err
 python -c "
 import json
-d=json.loads([l for l in open('gpurun_out/r02_scale_gomoku_4gpu_131072.json') if l.startswith('{')][-1])
-print('N=4', d['value'], d['ms_per_step'], d['e2e']['value'], d['n_gpus'], d['config'].get('games_per_gpu'), d['clocks'], d['hbm_bytes'], d['slot_pool'])
-print(json.dumps(d.get('e2e_generation'))[:900])
+d=json.loads([l for l in open('gpurun_out/bench_default.json') if l.startswith('{')][-1])
+print('default', d['value'], d['ms_per_step'], d['e2e']['value'], d['positions_per_s'], d['roofline']['frac'], d['roofline']['traffic'], d['clocks'], d['gpu_launches'])
+for k,v in d.get('configs',{}).items(): print(k, v.get('value'), v.get('ms_per_step'), v.get('e2e'))
+print('cpu', d.get('cpu_baseline'))
 "
