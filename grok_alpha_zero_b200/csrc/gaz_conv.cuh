@@ -81,6 +81,9 @@ struct BoardConvArgs {
     // dense-layer mode (heads): rows are leaves (all live), one launch per 128-wide slice of the outputs
     int dense;                // 1: every row < valid_rows is live; the padding mask is not applied
     int n_off;                // first output feature of this launch (row offset into the weight tensor / flat_out column)
+    int n_slices;             // dense mode: 128-wide output slices computed by this launch (0 = 1); work items are (tile, slice)
+                              // pairs, slice-minor, so the slices of a tile run on neighbouring CTA pairs at the same time and the
+                              // tile's activations are read from HBM once; slice s uses par[s * 128 ..] as its biases
     float *flat_out;          // fp32 row-major [row][flat_ld] output (optional)
     int flat_ld, flat_n;      // leading dimension and number of valid output features
     // fused Squeeze-Excitation (tile == board, P_pad == 256): dense1 [C][R], dense2 [R][C]
@@ -150,7 +153,8 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const long long valid_rows = (long long)cnt * p.P_pad;
     const int n_tiles = (int)((valid_rows + TILE_ROWS - 1) / TILE_ROWS);
     // loop index space: single CTA = tiles; pair = pair-tiles (tile 2*pt + rank; the last one may be a dummy)
-    const int n_loop = PAIR ? (n_tiles + 1) / 2 : n_tiles;
+    const int n_sl = p.n_slices > 1 ? p.n_slices : 1;
+    const int n_loop = (PAIR ? (n_tiles + 1) / 2 : n_tiles) * n_sl;   // loop index = (pair-)tile * n_sl + slice
     const int dbg = p.base_offset_mode; // timing experiments: 8 no residual loads, 16 no fp32 stores, 32 no bf16 stores, 64 no SE passes
 
     if (threadIdx.x == 0) {
@@ -173,7 +177,8 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) { // ---------------- activation-slab TMA producer
             Ring r;
             for (int lt = tile0; lt < n_loop; lt += tile_step) {
-                const int t = PAIR ? 2 * lt + rank : lt;
+                const int tl = lt / n_sl;
+                const int t = PAIR ? 2 * tl + rank : tl;
                 const int row0 = t * TILE_ROWS - HALO;
                 for (int kc = 0; kc < p.kpt; kc++) {
                     mbar_wait(&a_empty[r.idx], r.phase ^ 1);
@@ -195,19 +200,21 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) { // ---------------- weight-tile TMA producer: order (K-block, tap)
             Ring r;
             const int cin = p.kpt * 64;
-            for (int lt = tile0; lt < n_loop; lt += tile_step)
+            for (int lt = tile0; lt < n_loop; lt += tile_step) {
+                const int n_off = p.n_off + (lt % n_sl) * 128;
                 for (int kc = 0; kc < p.kpt; kc++)
                     for (int tap = 0; tap < p.taps; tap++) {
                         mbar_wait(&b_empty[r.idx], r.phase ^ 1);
                         if (PAIR) {
                             if (rank == 0) mbar_expect_tx(&b_full[r.idx], 2 * Cfg::B_BYTES);
-                            tma_load_2d_pair(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, p.n_off + rank * Cfg::B_ROWS);
+                            tma_load_2d_pair(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, n_off + rank * Cfg::B_ROWS);
                         } else {
                             mbar_expect_tx(&b_full[r.idx], Cfg::B_BYTES);
-                            tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, p.n_off);
+                            tma_load_2d(sB + r.idx * Cfg::B_BYTES, &tmB, &b_full[r.idx], tap * cin + kc * 64, n_off);
                         }
                         r.advance(NB);
                     }
+            }
         }
     } else if (warp == 2) {
         if (rank == 0) { // ---------------- MMA issuer: whole warp, uniform control flow, one elected lane per instruction
@@ -258,7 +265,9 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int lt = tile0; lt < n_loop; lt += tile_step) {
-            const int t = PAIR ? 2 * lt + rank : lt;
+            const int tl = lt / n_sl, sl = lt - tl * n_sl;
+            const int n_off = p.n_off + sl * 128;
+            const int t = PAIR ? 2 * tl + rank : tl;
             if (t >= n_tiles) { // dummy half of the last pair-tile: keep the barrier phases in step, touch nothing
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_before();
@@ -487,7 +496,7 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 tmem_ld_wait();
                 float v[32];
-                const float *pb = p.par + ch * 32; // constant bank, uniform index: no shared-memory traffic
+                const float *pb = p.par + sl * 128 + ch * 32; // constant bank, uniform index: no shared-memory traffic
 #pragma unroll
                 for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + pb[j];
                 if (p.se) {
@@ -505,10 +514,10 @@ conv_board_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const size_t blk = f32_blk_index(row, ch * 32, BN); // this lane's first piece of the 32x32 block
                 if (dbg & 4) continue; // timing experiment only: no output stores
                 if (p.flat_out && live) { // dense layers: plain row-major fp32 [leaf][features]
-                    float *fo = p.flat_out + (size_t)row * p.flat_ld + p.n_off + ch * 32;
+                    float *fo = p.flat_out + (size_t)row * p.flat_ld + n_off + ch * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j++)
-                        if (p.n_off + ch * 32 + j < p.flat_n) fo[j] = v[j];
+                        if (n_off + ch * 32 + j < p.flat_n) fo[j] = v[j];
                 }
                 if (p.out_raw && !(dbg & 16)) {
 #pragma unroll

@@ -767,16 +767,14 @@ static int net_forward(gaz_net *n, const int8_t *states, const int32_t *count, f
             }
             if (op.dense_tc) { // [leaf][In] bf16 x [Out][In] bf16 on the board kernel: rows = leaves, 128 outputs per launch
                 float *outp = (d.flags & 4) ? value : (float *)buf(d.out_raw);
-                for (int n0 = 0; n0 < d.cout; n0 += 128) {
+                {   // one launch: work items are (row tile, 128-wide output slice) pairs (cout <= 512: the biases of up to four
+                    // slices travel in par[0..511])
                     gaz_conv::BoardConvArgs a;
                     memset(&a, 0, sizeof a);
                     a.count = count; a.max_count = n->max_batch; a.P_pad = 1; a.Wp = 1;
                     a.taps = 1; a.kpt = (d.cin + 63) / 64; a.base_offset_mode = 0;
-                    for (int c = 0; c < 128; c++) {
-                        a.par[c] = n0 + c < d.cout ? op.par[n0 + c] : 0.0f;
-                        a.par[128 + c] = 1.0f; a.par[384 + c] = 1.0f;
-                    }
-                    a.dense = 1; a.n_off = n0; a.flat_out = outp; a.flat_ld = d.cout; a.flat_n = d.cout;
+                    for (int c = 0; c < 512; c++) a.par[c] = c < d.cout ? op.par[c] : 0.0f;
+                    a.dense = 1; a.n_off = 0; a.n_slices = (d.cout + 127) / 128; a.flat_out = outp; a.flat_ld = d.cout; a.flat_n = d.cout;
                     NetOp tmp = op; // maps: activations of this dense op, weights
                     tmp.tmA2 = op.tmDA; tmp.tmB2 = op.tmDW2;
                     if (launch_conv_board<128>(n, tmp, a, s) != 0) return -1;
@@ -967,7 +965,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         const NetOp &pr = n->ops[oi - 1];
         if (pr.d.type != GAZ_OP_HEADCONV || pr.d.out_raw != d.in_buf || pr.d.cin != 32) continue;
         if (n->bufs[(size_t)pr.d.in_buf].kind != GAZ_BUF_ROWS_BF16) continue;
-        if (d.cout % 128 != 0 || d.cout > 640 || d.cin > 4096) continue;
+        if (d.cout % 128 != 0 || d.cout > 512 || d.cin > 4096) continue;
         const int in_pad = (d.cin + 7) & ~7; // TMA row pitch must be a multiple of 16 bytes
         if (!((pr.d.cout == 8 && pr.d.ksize == 3) || (pr.d.cout == 4 && pr.d.ksize == 1))) continue; // headconv_board_kernel shapes
         op.rows_dense = (((long long)n->max_batch + 255) / 256) * 256;
@@ -1515,7 +1513,7 @@ int gaz_net_launches_per_forward(gaz_net *n) { // kernels actually launched: ops
     int k = 0;
     for (auto &op : n->ops) {
         if (op.skip || op.in_block || op.in_trunk || op.dual_skip || op.chain_skip || op.chain_joined) continue;
-        k += op.dense_tc ? (op.d.cout + 127) / 128 : 1;   // a tensor-core dense layer launches one kernel per 128 outputs
+        k += 1;
     }
     return k;
 }

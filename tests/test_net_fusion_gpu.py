@@ -26,12 +26,13 @@ def _tags(net):
 
 def test_launch_counts_pin_the_fusion_rules():
     # Gomoku 10 x 128 + SE: stem+projection | 6 + 4 blocks | per head: dx-merged C128->C32, small head conv, tensor-core dense
-    # slices (4 + 2) | fp32 policy_2 | policy_out | value dense chain  = 16 kernels per forward
+    # layer (all its 128-wide slices in one launch) | policy_2 as a one-layer mma chain | policy_out | value dense chain
+    # = 12 kernels per forward
     spec = netspec.build_spec("gomoku", "softmax")
     net = Net(spec, netspec.init_weights(spec, seed=0), max_batch=64)
     tags = _tags(net)
     assert tags.count("intrunk") == 8 and "block+se*6" in tags and "block+se*4" in tags, tags
-    assert net.n_launches == 16, net.n_launches
+    assert net.n_launches == 12, net.n_launches
     net.close()
     # Connect4 5 x 128: tile stem | one trunk launch | both head convolutions | both dense stacks | policy_out
     spec = netspec.build_spec("connect4", "softmax")
