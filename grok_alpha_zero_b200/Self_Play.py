@@ -33,6 +33,21 @@ except Exception:  # noqa: BLE001
 
 
 # ---------------------------------------------------------------------------------------------- replay writer --
+_NPY_HEADERS = {}
+
+
+def _npy_bytes(arr):
+    """`arr` as the bytes of a .npy file (format 1.0); the header depends only on dtype and shape and is cached"""
+    k = (arr.dtype.str, arr.shape)
+    h = _NPY_HEADERS.get(k)
+    if h is None:
+        import io
+        bio = io.BytesIO()
+        np.lib.format.write_array_header_1_0(bio, np.lib.format.header_data_from_array_1_0(arr))
+        h = _NPY_HEADERS[k] = bio.getvalue()
+    return h + arr.tobytes()
+
+
 class ReplayWriter:
     """`Self_Play_Data` with the reference schema (Self_Play.py:178-208): `game_stats` uint32[6] =
     [max game length, total positions, games, wins(-1), draws, wins(+1)] and per game and augmentation
@@ -130,9 +145,8 @@ class ReplayWriter:
         for inc in range(policies_aug.shape[0]):
             for name, arr, dt in self._triple(boards_aug, policies_aug, values_aug, inc):
                 key = "%s_%d" % (name, k0 + inc)
-                with zf.open(key + ".npy", "w", force_zip64=True) as fo:
-                    np.lib.format.write_array(fo, np.ascontiguousarray(arr, dtype=dt), allow_pickle=False)
-                self.keys.append(key)
+                zf.writestr(key + ".npy", _npy_bytes(np.ascontiguousarray(arr, dtype=dt)))   # one call per member: a generation
+                self.keys.append(key)                                                          # of short games is bound by this loop
         self.n_datasets += policies_aug.shape[0]
 
     @staticmethod
