@@ -8,9 +8,10 @@ import numpy as np
 
 def run_flagship():
     """The flagship kernels first, so that they sit at the head of any launch trace of smoke(): one forward pass of a
-    Gomoku 2-block + Squeeze-Excitation network (the layer shapes of BASELINE configs[2]: tcgen05 stem, 1x1 projection, the
-    fused residual-block kernel with SE, C128->C32 head convolutions, mma.sync head convolutions, tensor-core dense) on 6
-    boards, checked against the fp32 restatement with the north-star tolerance."""
+    Gomoku 2-block + Squeeze-Excitation network (the layer shapes of BASELINE configs[2]: tcgen05 stem + shortcut projection
+    (stem_proj_kernel), both residual blocks with SE in one trunk launch (res_trunk_kernel), dx-merged C128->C32 head
+    convolutions (conv_board_kernel<96>), mma.sync head convolutions and dense layers, tensor-core dense) on 6 boards,
+    checked against the fp32 restatement with the north-star tolerance."""
     from . import netspec
     from .net import Net
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
