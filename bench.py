@@ -42,6 +42,10 @@ CONFIGS = {
     "gomoku": dict(game="gomoku", mode="puct", games=16384, sims=800, limit=1200, net={}, head="softmax",
                    c_puct_init=4.5, alpha=0.05, opening=112, label="Gomoku 15x15 self-play, PUCT 800 sims/move (x1.5 = 1200 "
                    "iterations, Self_Play.py:99), 10-block ResNet128+SE bf16, 16384 games/GPU"),
+    # the reference's own Gomoku builder has no Squeeze-Excitation (Gomoku/Build_Model.py:10-88): same trunk without the SE epilogue
+    "gomoku_no_se": dict(game="gomoku", mode="puct", games=16384, sims=800, limit=1200, net=dict(use_se=False), head="softmax",
+                         c_puct_init=4.5, alpha=0.05, opening=112, label="Gomoku 15x15 self-play, PUCT 800 sims/move (x1.5 = 1200 "
+                         "iterations), 10-block ResNet128 WITHOUT SE (the reference's builder) bf16, 16384 games/GPU"),
     "connect4": dict(game="connect4", mode="puct", games=4096, sims=800, limit=1200, net={}, head="softmax",
                      c_puct_init=2.5, alpha=0.5, opening=None, label="Connect4 6x7 self-play, PUCT 800 sims/move, 5-block "
                      "ResNet128 bf16, 4096 games/GPU"),
