@@ -948,7 +948,7 @@ int gaz_net_create(const gaz_net_desc *desc, gaz_net **out) {
         if (d.type == GAZ_OP_SE && n->P_pad == gaz_conv::TILE_ROWS && !n->ops.empty()) {
             NetOp &prev = n->ops.back();
             if (prev.d.type == GAZ_OP_CONV_TC && prev.d.out_raw == d.in_buf && prev.d.out_a < 0 && prev.d.out_b < 0 &&
-                prev.d.res_buf < 0 && prev.d.cout == d.cout && d.cout == 128 && d.cin <= d.cout) {
+                prev.d.res_buf < 0 && prev.d.cout == d.cout && d.cout == 128 && d.cin <= 64 && (d.cin & 1) == 0) {   // fused SE: R <= 64, even
                 prev.fused_se = 1;
                 prev.se = d;
                 op.skip = 1;
