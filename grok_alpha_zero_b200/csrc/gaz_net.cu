@@ -2,10 +2,12 @@
 //
 // Trunk convolutions (C_in in {64,128,256}, C_out in {32,64,128}) run as implicit GEMMs on the 5th-gen tensor cores
 // (tcgen05.mma cta_group::2, bf16 x bf16 -> fp32 in TMEM, operands staged by TMA): gaz_conv.cuh (one convolution per
-// launch, any board geometry), gaz_block.cuh (a whole residual block per launch when a board is one 256-row tile),
-// gaz_stem.cuh (the Gomoku-shaped stem as an implicit GEMM).  This file holds the kernels that are too small for a tcgen05
-// pipeline - stems on 2/4 input planes, head convolutions (mma.sync or CUDA cores), SE fallback, dense layers, policy
-// activation - and the executor that walks the op list of include/gaz_net.h.
+// launch, any board geometry; dx-merged head convolutions; tensor-core dense layers), gaz_block.cuh (whole residual blocks,
+// up to six per launch, when a 256-row tile is a whole number of boards), gaz_stem.cuh (stems as implicit GEMMs, the Gomoku
+// one fused with the first block's shortcut projection), gaz_small.cuh (small layers on mma.sync).  This file holds the
+// remaining CUDA-core kernels - SE fallback, generic head convolution, fp32 dense layer, policy activation - and the executor
+// that walks the op list of include/gaz_net.h: it decides the fusions (gaz_net_create), runs the two heads as two stream
+// branches where they are separable and is captured into the search round's CUDA graph by gaz_engine.cu.
 // Reference network definitions: */Build_Model.py, Net/ResNet/ResNet_Block.py:27-41,
 // Net/SE/SE_Block.py:15-23, Net/Stablemax.py:7-11.
 #include "../../include/gaz_net.h"
